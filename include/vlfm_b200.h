@@ -1,0 +1,147 @@
+/*
+ * vlfm_b200 -- C-ABI of the B200-native VLFM perception -> value-map hot path.
+ *
+ * The reference (bdaiinstitute/vlfm) is pure Python: the boundary it exposes is a
+ * Python class surface (vlfm/mapping/*.py, vlfm/vlm/*.py).  This header is the
+ * thin C-ABI those classes are re-hosted on (vlfm_b200/mapping, vlfm_b200/vlm load it
+ * with ctypes).  Every entry point cites the reference function it replaces.
+ *
+ * Conventions
+ *   - plain C types only; `d_` pointers are DEVICE pointers, `h_` pointers are HOST.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never allocates device memory and never synchronises unless documented.
+ *   - return value: 0 (VLFM_OK) or a VLFM_E_* code; vlfm_last_error() gives text.
+ *   - batched: `batch` environments per call; env b uses grid slot
+ *     d_slot[b] (or b when d_slot == NULL) of the [nslots, G, G(, C)] state tensors.
+ *   - per-environment soft errors (camera off-grid, scatter out of range) are
+ *     reported through `d_status[b]` bit flags (VLFM_ST_*), read by the host at its
+ *     next synchronisation point and turned into the reference's exceptions.
+ */
+#ifndef VLFM_B200_H_
+#define VLFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLFM_OK 0
+#define VLFM_E_INVALID 1   /* bad argument */
+#define VLFM_E_CUDA 2      /* CUDA runtime error, see vlfm_last_error() */
+#define VLFM_E_UNSUPPORTED 3
+#define VLFM_E_DRIVER 4    /* driver entry point (TMA descriptor encode) unavailable */
+
+/* d_status bits */
+#define VLFM_ST_CAMERA_OFF_GRID 1  /* img_utils.py:43 assert -> AssertionError */
+#define VLFM_ST_SCATTER_OOB 2      /* numpy IndexError in obstacle_map.py:101 */
+#define VLFM_ST_FRONTIER_OVERFLOW 4
+
+/* fusion modes (vlfm/mapping/value_map.py:357-429) */
+#define VLFM_FUSE_WEIGHTED 0      /* use_max_confidence=False, fusion_type="default" */
+#define VLFM_FUSE_MAX_CONFIDENCE 1 /* use_max_confidence=True */
+#define VLFM_FUSE_REPLACE 2        /* fusion_type="replace" */
+#define VLFM_FUSE_EQUAL 4          /* OR-ed flag: fusion_type="equal_weighting" */
+
+const char* vlfm_last_error(void);
+int vlfm_version(void);
+/* number of kernels this library has launched since load (bench `gpu_launches`). */
+unsigned long long vlfm_launch_count(void);
+
+/* ------------------------------------------------------------------ value map ---- */
+/* Replaces ValueMap.update_map (vlfm/mapping/value_map.py:100-128), i.e.
+ * _process_local_data (:221-286), _localize_new_data (:288-319), rotate_image
+ * (vlfm/utils/img_utils.py:9-28), place_img_in_img (:31-61), _fuse_new_data
+ * (value_map.py:357-429).                                                          */
+typedef struct VlfmValueParams {
+  int32_t H, W;          /* depth image rows, cols                                   */
+  int32_t G;             /* grid side (BaseMap.size, base_map.py:15)                 */
+  int32_t C;             /* value channels                                           */
+  int32_t R;             /* cone template side = 2*int(max_depth*ppm)+1 (:323)       */
+  int32_t ppm;           /* pixels per metre                                         */
+  float depth_scale;     /* (float)(max_depth - min_depth)     (value_map.py:234)    */
+  float depth_offset;    /* (float)min_depth                                         */
+  float decision_threshold; /* 0.35 (value_map.py:41)                                */
+  int32_t fusion;        /* VLFM_FUSE_*                                              */
+  int32_t rows_per_tile; /* fuse-kernel tiling; 0 = choose from batch               */
+} VlfmValueParams;
+
+/* bytes of scratch needed for `batch` environments. */
+int vlfm_value_workspace_bytes(const VlfmValueParams* p, int batch, size_t* bytes);
+
+/* d_conf   [nslots, G, G]    float32  (ValueMap._map)
+ * d_value  [nslots, G, G, C] float32  (ValueMap._value_map)
+ * d_depth  [batch, H, W]     float32 in [0,1]
+ * d_tf     [batch, 16]       float64 row-major camera->episodic
+ * d_values [batch, C]        float64
+ * d_template [R, R]          float32 cone template (value_map.py:337-355; constant per
+ *                            (fov, max_depth, ppm), built once by the host class)
+ * d_tan    [W]               float64 tan(linspace(-fov/2, fov/2, W)) (value_map.py:237)
+ * d_explored [nslots, G, G]  uint8 or NULL (value_map.py:369-375 masking of the new
+ *                            observation; the full-grid part is vlfm_value_mask_unexplored)
+ * d_workspace                vlfm_value_workspace_bytes(), must be zero-filled once
+ * d_status [batch]           int32, OR-ed with VLFM_ST_* flags                        */
+int vlfm_value_update(const VlfmValueParams* p, int batch, const int32_t* d_slot,
+                      float* d_conf, float* d_value, const float* d_depth,
+                      const double* d_tf, const double* d_values,
+                      const float* d_template, const double* d_tan,
+                      const uint8_t* d_explored, void* d_workspace, int32_t* d_status,
+                      void* stream);
+
+/* value_map.py:369-375: conf/value := 0 where explored == 0, over the whole grid. */
+int vlfm_value_mask_unexplored(int G, int C, int batch, const int32_t* d_slot, float* d_conf,
+                               float* d_value, const uint8_t* d_explored, void* stream);
+
+/* Replaces ValueMap.sort_waypoints' inner pixel_value_within_radius
+ * (value_map.py:163-176, img_utils.py:213-266): median of the non-zero cells of
+ * channel c inside the radius-`radius` disc (d_disc: (2r+1)^2 uint8 mask as drawn by
+ * cv2.circle) around (row,col) = d_points[i]; -1 when empty.
+ * d_out [npoints, C] float64.                                                       */
+int vlfm_value_disc_median(int G, int C, int slot, const float* d_value, const int32_t* d_points,
+                           int npoints, int radius, const uint8_t* d_disc, double* d_out,
+                           void* stream);
+
+/* --------------------------------------------------------------- obstacle map ---- */
+/* Replaces ObstacleMap.update_map obstacle half (vlfm/mapping/obstacle_map.py:86-109):
+ * hole fill (hole_area_thresh == -1 form), depth -> metres, get_point_cloud
+ * (geometry_utils.py:216-236), transform_points (:205-213), filter_points_by_height
+ * (obstacle_map.py:196-197), _xy_to_px (base_map.py:35-46), scatter, k x k dilation. */
+typedef struct VlfmObstacleParams {
+  int32_t H, W, G, ppm;
+  float depth_scale;    /* (float)(max_depth - min_depth) */
+  float depth_offset;   /* (float)min_depth               */
+  float max_depth_f32;  /* (float)max_depth, mask = scaled < max_depth (:93)          */
+  double fx, fy;
+  double min_height, max_height;
+  int32_t kernel;       /* odd dilation size (:43-46)                                 */
+  int32_t full_grid;    /* 1: dilate whole grid (first update after reset); 0: ROI    */
+  int32_t roi_half;     /* ROI half-size in cells around the camera cell              */
+} VlfmObstacleParams;
+
+/* d_obst [nslots,G,G] uint8 (ObstacleMap._map), d_nav [nslots,G,G] uint8
+ * (ObstacleMap._navigable_map as 0/1).                                               */
+int vlfm_obstacle_update(const VlfmObstacleParams* p, int batch, const int32_t* d_slot,
+                         uint8_t* d_obst, uint8_t* d_nav, const float* d_depth,
+                         const double* d_tf, int32_t* d_status, void* stream);
+
+/* ---------------------------------------------------------------- dense (VLM) ---- */
+/* fp16 x fp16 -> fp32-accumulate GEMM on tcgen05 tensor cores, TMA-fed:
+ *   out[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N])
+ * A, W row-major fp16 (K contiguous, K % 8 == 0).
+ * epilogue: 0 = bias -> fp16 out; 1 = bias + GELU(erf) -> fp16 out;
+ *           2 = bias + residual: resid_f32[M,N] += result (fp32 stream, in place)
+ *           3 = bias -> fp32 out
+ * These replace the nn.Linear calls inside lavis' Blip2 ITM forward
+ * (reference call site vlfm/vlm/blip2itm.py:52).                                     */
+#define VLFM_EPI_BIAS_F16 0
+#define VLFM_EPI_BIAS_GELU_F16 1
+#define VLFM_EPI_BIAS_RESID_F32 2
+#define VLFM_EPI_BIAS_F32 3
+int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
+                  int K, int lda, int ldw, int ldo, int epilogue, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLFM_B200_H_ */

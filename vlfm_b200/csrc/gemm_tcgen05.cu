@@ -1,0 +1,295 @@
+// fp16 x fp16 -> fp32 GEMM on Blackwell 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+//   out[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N])      A, W row-major (K-major)
+//
+// Replaces the nn.Linear layers of the BLIP-2 ViT-g / Q-Former forward that
+// vlfm/vlm/blip2itm.py:52 runs through lavis (fp16 autocast in the reference).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the A (128x64) and W
+//               (BNx64) K-slices into a STAGES-deep 128B-swizzled smem ring,
+//               mbarrier complete_tx signalling.
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::f16,
+//               M=128, N=BN, K=16, fp32 accumulators in TMEM); tcgen05.commit
+//               releases smem stages and finally signals the epilogue.
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), fused
+//               bias / GELU(erf) / fp32-residual-add, vectorised global stores.
+// M / N / K tails are handled by TMA out-of-bounds zero fill + store guards.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace vlfm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 bytes = one swizzle atom row
+constexpr int GEMM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();  // a protocol bug must fail loudly, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(1)<<16 | SBO(1024B>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct GemmArgs {
+  const float* bias;
+  void* out;
+  int M, N, K, ldo, epi;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accbar = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+  const int num_k = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+        tma_load_2d(smem_u32(sA + s * A_BYTES), &tmA, kb * BK, m_blk * BM, full0 + 8 * s);
+        tma_load_2d(smem_u32(sB + s * B_BYTES), &tmB, kb * BK, n_blk * BN, full0 + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          tc_mma_f16(tmem_base, umma_desc_k128(a0 + k * 32), umma_desc_k128(b0 + k * 32), IDESC,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty0 + 8 * s);   // smem stage reusable once these MMAs retire
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      tc_commit(accbar);             // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    const int row = m_blk * BM + q * 32 + lane;
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      const int n0 = n_blk * BN + c * 32;
+      if (row >= g.M || n0 >= g.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float b = (g.bias && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
+        v[j] = __uint_as_float(r[j]) + b;
+      }
+      const bool fullw = (n0 + 32 <= g.N);
+      if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16) {
+        if (g.epi == VLFM_EPI_BIAS_GELU_F16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        __half* o = reinterpret_cast<__half*>(g.out) + (size_t)row * g.ldo + n0;
+        if (fullw) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+        } else {
+          for (int j = 0; j < 32 && n0 + j < g.N; ++j) o[j] = __float2half_rn(v[j]);
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
+        const bool add = (g.epi == VLFM_EPI_BIAS_RESID_F32);
+        if (fullw) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (add) {
+              float4 old = *reinterpret_cast<const float4*>(o + j);
+              t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+            }
+            *reinterpret_cast<float4*>(o + j) = t;
+          }
+        } else {
+          for (int j = 0; j < 32 && n0 + j < g.N; ++j) o[j] = add ? o[j] + v[j] : v[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side ------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D fp16 row-major [rows, cols] (cols contiguous, leading dimension ld elements), box {64, boxRows}
+static int make_map(CUtensorMap* m, const void* base, int rows, int cols, int ld, int boxRows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return VLFM_E_DRIVER; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return VLFM_E_DRIVER; }
+  return VLFM_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap tb;
+  int rc = make_map(&tb, W, g.N, g.K, ldw, BN);
+  if (rc) return rc;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gemm)");
+    if (rc) return rc;
+    configured = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, g);
+  VLFM_CHECK_LAUNCH("gemm_f16_tcgen05_kernel");
+  count_launch();
+  return VLFM_OK;
+}
+
+}  // namespace vlfm
+
+using namespace vlfm;
+
+extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
+                             int K, int lda, int ldw, int ldo, int epilogue, void* stream) {
+  if (!d_A || !d_W || !d_out || M < 1 || N < 1 || K < 1) { set_error("vlfm_gemm_f16: bad argument"); return VLFM_E_INVALID; }
+  if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
+    set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
+  if (epilogue < 0 || epilogue > 3) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue};
+  CUtensorMap ta;
+  int rc = make_map(&ta, d_A, M, K, lda, BM);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // tile width: fill >= ~120 of the 148 SMs when M is small, widest tile otherwise
+  const long mt = (M + BM - 1) / BM;
+  if (mt * ((N + 127) / 128) >= 120) return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
+  if (mt * ((N + 63) / 64) >= 120) return launch_gemm<64, 8>(ta, d_W, ldw, g, st);
+  return launch_gemm<32, 8>(ta, d_W, ldw, g, st);
+}
