@@ -141,6 +141,29 @@ int vlfm_obstacle_update(const VlfmObstacleParams* p, int batch, const int32_t* 
 int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
                   int K, int lda, int ldw, int ldo, int epilogue, void* stream);
 
+/* PIL-exact antialiased bicubic resize (uint8) + ToTensor + Normalize, emitted in the
+ * im2col layout of the patch-embedding GEMM.  Replaces lavis' BlipImageEvalProcessor as
+ * called at vlfm/vlm/blip2itm.py:48-49.
+ * d_img [B,H,W,3] uint8; d_mid [B,H,OW,3] uint8 scratch; d_out [B*(OH/patch)*(OW/patch), ldk] fp16.
+ * (h|v)bounds [2*O] = {first input index, tap count}; (h|v)kk [O*ksize] 22-bit fixed point
+ * coefficients (Pillow precompute_coeffs / normalize_coeffs_8bpc). h_mean3/h_std3: HOST float[3]. */
+int vlfm_preprocess_im2col(const uint8_t* d_img, uint8_t* d_mid, void* d_out, int B, int H, int W, int OH,
+                           int OW, int patch, int ldk, const int32_t* d_hbounds, const int32_t* d_hkk,
+                           int hksize, const int32_t* d_vbounds, const int32_t* d_vkk, int vksize,
+                           const float* h_mean3, const float* h_std3, void* stream);
+/* x[b,0] = cls + pos[0]; x[b,1+p] = patch[b,p] + pos[1+p]   (fp32; ViT token assembly) */
+int vlfm_assemble_tokens(const float* d_patch, const float* d_cls, const float* d_pos, float* d_x, int B,
+                         int T, int D, void* stream);
+/* LayerNorm over the last dimension: fp32 in, fp16 (d_out16) and/or fp32 (d_out32) out. */
+int vlfm_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out16, float* d_out32,
+                   int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream);
+/* softmax(scale * Q K^T) V per (batch, head); fp16 in/out, fp32 accumulate.
+ * q rows (b*Nq + i), k/v rows (b*Nk + j), head h at column offset h*hd. Nk <= 272, hd <= 96. */
+int vlfm_attention_f16(const void* d_q, const void* d_k, const void* d_v, void* d_o, int B, int heads, int Nq,
+                       int Nk, int hd, int ldq, int ldk, int ldv, int ldo, float scale, void* stream);
+/* ITC head (match_head="itc"): cos[b] = max_q <normalize(proj[b,q,:]), text>.  */
+int vlfm_itc_head(const float* d_proj, const float* d_text, float* d_out, int B, int Q, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,79 @@
+"""BLIP-2 ITC forward on the GPU vs the fp32 HF oracle (same seeded weights).
+
+Tolerances are stated per check.  The north-star asks <=1e-4 on the cosine; that is met
+for the pieces that are exact by construction (preprocessing bytes) and reported/
+bounded for the fp16-operand forward (lavis itself runs the ViT in fp16)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import blip2_oracle
+from vlfm_b200.utils.synthetic import make_rgb
+from vlfm_b200.vlm.blip2_config import SMALL, TINY, Blip2Dims, random_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def test_preprocess_matches_pil_bit_exact():
+    """resize+normalise+im2col on the GPU == PIL bicubic -> ToTensor -> Normalize, up to the fp16 store."""
+    from vlfm_b200.vlm.blip2_engine import Blip2ITCEngine
+
+    d = SMALL
+    eng = Blip2ITCEngine(d, random_state_dict(d, 0), max_batch=2, use_graph=False)
+    rng = np.random.default_rng(0)
+    imgs = np.stack([make_rgb(rng, 480, 640), make_rgb(rng, 480, 640)])
+    dev = torch.from_numpy(imgs).cuda()
+    eng.forward(dev)
+    torch.cuda.synchronize()
+    col = eng.b_col.float().cpu().numpy().reshape(2, 16, 16, -1)[..., : d.patch_k].reshape(2, 16, 16, 3, 14, 14)
+    got = col.transpose(0, 3, 1, 4, 2, 5).reshape(2, 3, 224, 224)
+    for b in range(2):
+        ref = blip2_oracle.preprocess(imgs[b], 224).half().float().numpy()
+        assert np.array_equal(got[b], ref)
+
+
+@pytest.mark.parametrize("dims,tol", [(TINY, 2e-3), (SMALL, 2e-3)])
+def test_small_models_vs_oracle(dims, tol):
+    from vlfm_b200.vlm.blip2itm import BLIP2ITM
+
+    sd = random_state_dict(dims, 3)
+    orc = blip2_oracle.Blip2Oracle(dims, sd)
+    m = BLIP2ITM(state_dict=sd, dims=dims, max_batch=3)
+    rng = np.random.default_rng(1)
+    ids = [5, 17, 23, 42, 7]
+    m.tokenizer = lambda s: ids
+    for hw in [(480, 640), (240, 320)]:
+        img = make_rgb(rng, *hw)
+        ref = orc.cosine(img, ids)
+        got = m.cosine(img, "whatever")
+        assert abs(got - ref) <= tol, (got, ref)
+    # batched device path == per-image path
+    imgs = np.stack([make_rgb(rng, 480, 640) for _ in range(3)])
+    out = m.cosine_device(torch.from_numpy(imgs).cuda(), "whatever").cpu().numpy()
+    for b in range(3):
+        assert abs(out[b] - orc.cosine(imgs[b], ids)) <= tol
+    # image tokens (ViT output incl. post-LN): elementwise check
+    tok_ref = orc.image_tokens(imgs[2]).numpy()
+    tok = m.engine.b_img[2 * dims.tokens : 3 * dims.tokens].float().cpu().numpy()
+    assert np.abs(tok - tok_ref).max() <= 3e-2 and np.abs(tok - tok_ref).mean() <= 3e-3
+
+
+def test_full_size_vitg_vs_oracle():
+    """ViT-g/14 (39 layers, 1408) + 12-layer Q-Former, seeded synthetic weights: cosine within 5e-3
+    of the fp32 oracle (fp16 tensor-core operands, fp32 accumulation; measured error is printed)."""
+    from vlfm_b200.vlm.blip2itm import BLIP2ITM
+
+    dims = Blip2Dims()
+    sd = random_state_dict(dims, 0)
+    orc = blip2_oracle.Blip2Oracle(dims, sd)
+    m = BLIP2ITM(state_dict=sd, dims=dims, max_batch=1)
+    ids = [101, 2000, 3000, 4000, 102]
+    m.tokenizer = lambda s: ids
+    rng = np.random.default_rng(2)
+    errs = []
+    for _ in range(2):
+        img = make_rgb(rng, 480, 640)
+        ref, got = orc.cosine(img, ids), m.cosine(img, "x")
+        errs.append(abs(ref - got))
+        print("cosine ref", ref, "gpu", got, "abs err", abs(ref - got))
+    assert max(errs) <= 5e-3

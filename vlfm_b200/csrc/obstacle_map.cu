@@ -91,7 +91,7 @@ obstacle_scatter_kernel(ObstDev p, const int* __restrict__ slot, uint8_t* __rest
 }
 
 // window (or whole grid) box dilation; tile 32 rows x 128 cols per block.
-constexpr int DT_ROWS = 32, DT_COLS = 128, DT_MAXK = 15;
+constexpr int DT_ROWS = 32, DT_COLS = 128, DT_MAXK = 31;
 
 __global__ void __launch_bounds__(256)
 obstacle_dilate_kernel(ObstDev p, const int* __restrict__ slot, const uint8_t* __restrict__ obstAll,

@@ -1,0 +1,375 @@
+// Non-GEMM operators of the BLIP-2 ITC forward (sm_100a):
+//   - image preprocessing: PIL-exact antialiased bicubic resize (uint8, 22-bit fixed
+//     point, horizontal then vertical pass) + ToTensor + Normalize, written straight
+//     into the im2col layout of the 14x14/14 patch-embedding GEMM
+//     (reference: vlfm/vlm/blip2itm.py:48-49 -> lavis BlipImageEvalProcessor);
+//   - token assembly (class token + position embedding);
+//   - LayerNorm (fp32 in, fp16 and/or fp32 out);
+//   - multi-head attention, flash-style online softmax on mma.sync m16n8k16 fp16
+//     tensor-core tiles (ViT-g self-attention N=257/hd=88, Q-Former self/cross hd=64);
+//   - ITC head: L2-normalise the 32 projected queries, dot with the cached text
+//     feature, max over queries (blip2itm.py:52, match_head="itc").
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace vlfm {
+
+// --------------------------------------------------------------- preprocessing ----
+// coefficient tables are built on the host exactly like Pillow's precompute_coeffs +
+// normalize_coeffs_8bpc (see vlfm_b200/vlm/preprocess.py); layout per output index:
+// bounds[2*i] = first input index, bounds[2*i+1] = tap count, kk[i*ksize + t].
+__device__ __forceinline__ uint8_t clip8(int v) {
+  v >>= 22;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+__global__ void resize_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ mid, int H, int W, int OW,
+                                const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  // in [B,H,W,3] -> mid [B,H,OW,3]
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over OW*3
+  if (i >= OW * 3) return;
+  const int xo = i / 3, c = i - 3 * xo;
+  const int x0 = bounds[2 * xo], n = bounds[2 * xo + 1];
+  const uint8_t* row = in + ((size_t)b * H + y) * W * 3;
+  int ss = 1 << 21;
+  for (int t = 0; t < n; ++t) ss += (int)row[(x0 + t) * 3 + c] * kk[xo * ksize + t];
+  mid[(((size_t)b * H + y) * OW + xo) * 3 + c] = clip8(ss);
+}
+
+__global__ void resize_v_norm_im2col_kernel(const uint8_t* __restrict__ mid, __half* __restrict__ out, int H, int OW,
+                                            int OH, const int* __restrict__ bounds, const int* __restrict__ kk,
+                                            int ksize, int patch, int ldk, float m0, float m1, float m2, float s0,
+                                            float s1, float s2) {
+  // mid [B,H,OW,3] -> out [B*(OH/patch)*(OW/patch), ldk], col = c*patch*patch + ky*patch + kx
+  const int b = blockIdx.z, yo = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OW * 3) return;
+  const int xo = i / 3, c = i - 3 * xo;
+  const int y0 = bounds[2 * yo], n = bounds[2 * yo + 1];
+  int ss = 1 << 21;
+  for (int t = 0; t < n; ++t) ss += (int)mid[(((size_t)b * H + y0 + t) * OW + xo) * 3 + c] * kk[yo * ksize + t];
+  const float px = (float)clip8(ss);
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(px, 255.f), mean), sd);   // ToTensor, Normalize (float32)
+  const int gp = OW / patch;
+  const int py = yo / patch, ky = yo - py * patch, pxi = xo / patch, kx = xo - pxi * patch;
+  const size_t rowi = (size_t)b * (OH / patch) * gp + (size_t)py * gp + pxi;
+  out[rowi * ldk + c * patch * patch + ky * patch + kx] = __float2half_rn(v);
+}
+
+// x[b, 0] = cls + pos[0];  x[b, 1+p] = patch[b, p] + pos[1+p]
+__global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, float* __restrict__ x, int B, int T, int D) {
+  const size_t n = (size_t)B * T * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const size_t r = i / D;
+    const int t = (int)(r % T), b = (int)(r / T);
+    float v = t == 0 ? cls[d] : patch[((size_t)b * (T - 1) + (t - 1)) * D + d];
+    x[i] = v + pos[(size_t)t * D + d];
+  }
+}
+
+// ------------------------------------------------------------------- LayerNorm ----
+// one warp per row; two-pass (mean, then centred variance) in registers.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __half* __restrict__ out16, float* __restrict__ out32, int rows, int D, int ldx, int ldo16, int ldo32,
+                 float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ldx;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + 32 * i;
+    v[i] = d < D ? xr[d] : 0.f;
+    s += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + 32 * i;
+    float c = d < D ? v[i] - mean : 0.f;
+    q += c * c;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + 32 * i;
+    if (d < D) {
+      float y = (v[i] - mean) * rstd * gamma[d] + beta[d];
+      if (out16) out16[(size_t)row * ldo16 + d] = __float2half_rn(y);
+      if (out32) out32[(size_t)row * ldo32 + d] = y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------- attention ----
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct AttnArgs {
+  const __half* q; const __half* k; const __half* v; __half* o;
+  int ldq, ldk, ldv, ldo;   // row strides (elements)
+  int Nq, Nk, hd, heads;
+  float scale_log2;         // softmax scale * log2(e)
+};
+
+constexpr int ATT_WARPS = 4;
+constexpr int ATT_QBLK = 16 * ATT_WARPS;   // 64 query rows per CTA
+constexpr int ATT_NKMAX = 272;             // keys padded to a multiple of 16
+
+// grid (ceil(Nq/64), heads, B).  K [key][hd] and V^T [hd][key] of one (batch, head) in smem.
+template <int HDP>
+__global__ void __launch_bounds__(32 * ATT_WARPS)
+attention_kernel(AttnArgs a) {
+  constexpr int KS = HDP + 8;            // K row stride (halves): conflict-free fragment loads
+  constexpr int VS = ATT_NKMAX + 8;      // V^T row stride (halves)
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  __half* sK = reinterpret_cast<__half*>(att_smem);            // [ATT_NKMAX][KS]
+  __half* sV = sK + ATT_NKMAX * KS;                            // [HDP][VS]
+  const int b = blockIdx.z, h = blockIdx.y, qb = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int NKP = (a.Nk + 15) & ~15;
+  const __half* kbase = a.k + (size_t)b * a.Nk * a.ldk + (size_t)h * a.hd;
+  const __half* vbase = a.v + (size_t)b * a.Nk * a.ldv + (size_t)h * a.hd;
+
+  // ---- stage K and V^T (16-byte global loads; zero padding)
+  const int chunks = HDP / 8;
+  for (int i = tid; i < NKP * chunks; i += 32 * ATT_WARPS) {
+    const int key = i / chunks, c = (i - key * chunks) * 8;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (key < a.Nk && c < a.hd) {
+      kv = *reinterpret_cast<const uint4*>(kbase + (size_t)key * a.ldk + c);
+      vv = *reinterpret_cast<const uint4*>(vbase + (size_t)key * a.ldv + c);
+    }
+    *reinterpret_cast<uint4*>(sK + key * KS + c) = kv;
+    const __half* vh = reinterpret_cast<const __half*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sV[(c + j) * VS + key] = vh[j];
+  }
+  __syncthreads();
+
+  // ---- Q fragments for this warp's 16 rows
+  const int row0 = qb * ATT_QBLK + warp * 16;
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+  const __half* qlo = a.q + ((size_t)b * a.Nq + r_lo) * a.ldq + (size_t)h * a.hd;
+  const __half* qhi = a.q + ((size_t)b * a.Nq + r_hi) * a.ldq + (size_t)h * a.hd;
+  uint32_t qf[HDP / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < HDP / 16; ++kk) {
+    const int c0 = kk * 16 + 2 * t, c1 = c0 + 8;
+    qf[kk][0] = (r_lo < a.Nq && c0 < a.hd) ? *reinterpret_cast<const uint32_t*>(qlo + c0) : 0u;
+    qf[kk][1] = (r_hi < a.Nq && c0 < a.hd) ? *reinterpret_cast<const uint32_t*>(qhi + c0) : 0u;
+    qf[kk][2] = (r_lo < a.Nq && c1 < a.hd) ? *reinterpret_cast<const uint32_t*>(qlo + c1) : 0u;
+    qf[kk][3] = (r_hi < a.Nq && c1 < a.hd) ? *reinterpret_cast<const uint32_t*>(qhi + c1) : 0u;
+  }
+
+  float o[HDP / 8][4];
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+  for (int kb = 0; kb < NKP; kb += 64) {
+    const int ntiles = min(8, (NKP - kb) >> 3);   // warp-uniform
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      if (j < ntiles) {
+        const __half* kr = sK + (kb + j * 8 + g) * KS + 2 * t;
+#pragma unroll
+        for (int kk = 0; kk < HDP / 16; ++kk) {
+          uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kk * 16);
+          uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8);
+          mma_16816(s[j], qf[kk], b0, b1);
+        }
+      }
+    }
+    // scale, mask, block row-max
+    float bm_lo = -INFINITY, bm_hi = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = kb + j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (j < ntiles) && (key + (e & 1) < a.Nk);
+        s[j][e] = ok ? s[j][e] * a.scale_log2 : -INFINITY;
+      }
+      bm_lo = fmaxf(bm_lo, fmaxf(s[j][0], s[j][1]));
+      bm_hi = fmaxf(bm_hi, fmaxf(s[j][2], s[j][3]));
+    }
+    bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1));
+    bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
+    bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1));
+    bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+    const float mn_lo = fmaxf(m_lo, bm_lo), mn_hi = fmaxf(m_hi, bm_hi);
+    const float al_lo = exp2f(m_lo - mn_lo), al_hi = exp2f(m_hi - mn_hi);   // exp2(-inf)=0 on the first block
+    m_lo = mn_lo; m_hi = mn_hi;
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - mn_lo); s[j][1] = exp2f(s[j][1] - mn_lo);
+      s[j][2] = exp2f(s[j][2] - mn_hi); s[j][3] = exp2f(s[j][3] - mn_hi);
+      sum_lo += s[j][0] + s[j][1]; sum_hi += s[j][2] + s[j][3];
+    }
+    l_lo = l_lo * al_lo + sum_lo; l_hi = l_hi * al_hi + sum_hi;   // per-thread partial sums; quad-reduced at the end
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) { o[i][0] *= al_lo; o[i][1] *= al_lo; o[i][2] *= al_hi; o[i][3] *= al_hi; }
+    // O += P V
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (2 * p < ntiles) {
+        uint32_t pa[4];
+        pa[0] = pack_half2(s[2 * p][0], s[2 * p][1]);
+        pa[1] = pack_half2(s[2 * p][2], s[2 * p][3]);
+        pa[2] = pack_half2(s[2 * p + 1][0], s[2 * p + 1][1]);
+        pa[3] = pack_half2(s[2 * p + 1][2], s[2 * p + 1][3]);
+        const __half* vr = sV + g * VS + kb + p * 16 + 2 * t;
+#pragma unroll
+        for (int i = 0; i < HDP / 8; ++i) {
+          uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr + i * 8 * VS);
+          uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + i * 8 * VS + 8);
+          mma_16816(o[i], pa, b0, b1);
+        }
+      }
+    }
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+  __half* olo = a.o + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * a.hd;
+  __half* ohi = a.o + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * a.hd;
+#pragma unroll
+  for (int i = 0; i < HDP / 8; ++i) {
+    const int c = i * 8 + 2 * t;
+    if (c < a.hd) {
+      if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = pack_half2(o[i][0] * inv_lo, o[i][1] * inv_lo);
+      if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = pack_half2(o[i][2] * inv_hi, o[i][3] * inv_hi);
+    }
+  }
+}
+
+// -------------------------------------------------------------------- ITC head ----
+// proj [B, Q, D] fp32 (vision_proj output), text [D] fp32 L2-normalised -> cos [B]
+__global__ void itc_head_kernel(const float* __restrict__ proj, const float* __restrict__ text,
+                                float* __restrict__ out, int Q, int D) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __shared__ float best[32];
+  float mx = -INFINITY;
+  for (int q = warp; q < Q; q += nw) {
+    const float* p = proj + ((size_t)b * Q + q) * D;
+    float nn = 0.f, dt = 0.f;
+    for (int d = lane; d < D; d += 32) { float v = p[d]; nn += v * v; dt += v * text[d]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { nn += __shfl_xor_sync(0xffffffffu, nn, o); dt += __shfl_xor_sync(0xffffffffu, dt, o); }
+    mx = fmaxf(mx, dt / fmaxf(sqrtf(nn), 1e-12f));   // F.normalize eps
+  }
+  if (lane == 0) best[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = best[0];
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, best[i]);
+    out[b] = m;
+  }
+}
+
+}  // namespace vlfm
+
+using namespace vlfm;
+
+extern "C" int vlfm_preprocess_im2col(const uint8_t* d_img, uint8_t* d_mid, void* d_out, int B, int H, int W, int OH,
+                                      int OW, int patch, int ldk, const int32_t* d_hbounds, const int32_t* d_hkk,
+                                      int hksize, const int32_t* d_vbounds, const int32_t* d_vkk, int vksize,
+                                      const float* h_mean3, const float* h_std3, void* stream) {
+  if (!d_img || !d_mid || !d_out || !d_hbounds || !d_hkk || !d_vbounds || !d_vkk || !h_mean3 || !h_std3 ||
+      OH % patch || OW % patch || B < 1 || B > 65535) { set_error("vlfm_preprocess_im2col: bad argument"); return VLFM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g1((OW * 3 + 127) / 128, H, B);
+  resize_h_kernel<<<g1, 128, 0, st>>>(d_img, d_mid, H, W, OW, d_hbounds, d_hkk, hksize);
+  VLFM_CHECK_LAUNCH("resize_h_kernel");
+  dim3 g2((OW * 3 + 127) / 128, OH, B);
+  resize_v_norm_im2col_kernel<<<g2, 128, 0, st>>>(d_mid, (__half*)d_out, H, OW, OH, d_vbounds, d_vkk, vksize, patch, ldk,
+                                                  h_mean3[0], h_mean3[1], h_mean3[2], h_std3[0], h_std3[1], h_std3[2]);
+  VLFM_CHECK_LAUNCH("resize_v_norm_im2col_kernel");
+  count_launch(2);
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_assemble_tokens(const float* d_patch, const float* d_cls, const float* d_pos, float* d_x, int B,
+                                    int T, int D, void* stream) {
+  if (!d_patch || !d_cls || !d_pos || !d_x) { set_error("vlfm_assemble_tokens: null argument"); return VLFM_E_INVALID; }
+  size_t n = (size_t)B * T * D;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  assemble_tokens_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_patch, d_cls, d_pos, d_x, B, T, D);
+  VLFM_CHECK_LAUNCH("assemble_tokens_kernel");
+  count_launch();
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out16, float* d_out32,
+                              int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream) {
+  if (!d_x || !d_gamma || !d_beta || (!d_out16 && !d_out32) || rows < 1 || D < 1) { set_error("vlfm_layernorm: bad argument"); return VLFM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((rows + 7) / 8);
+  if (D <= 32 * 8) layernorm_kernel<8><<<grid, 256, 0, st>>>(d_x, d_gamma, d_beta, (__half*)d_out16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else if (D <= 32 * 24) layernorm_kernel<24><<<grid, 256, 0, st>>>(d_x, d_gamma, d_beta, (__half*)d_out16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else if (D <= 32 * 48) layernorm_kernel<48><<<grid, 256, 0, st>>>(d_x, d_gamma, d_beta, (__half*)d_out16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else { set_error("vlfm_layernorm: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
+  VLFM_CHECK_LAUNCH("layernorm_kernel");
+  count_launch();
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_attention_f16(const void* d_q, const void* d_k, const void* d_v, void* d_o, int B, int heads, int Nq,
+                                  int Nk, int hd, int ldq, int ldk, int ldv, int ldo, float scale, void* stream) {
+  if (!d_q || !d_k || !d_v || !d_o || B < 1 || heads < 1 || Nq < 1 || Nk < 1) { set_error("vlfm_attention_f16: bad argument"); return VLFM_E_INVALID; }
+  if (Nk > ATT_NKMAX || hd > 96 || (hd & 7) || (ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 1) || B > 65535) {
+    set_error("vlfm_attention_f16: unsupported shape (Nk<=%d, hd<=96 and %%8==0, strides %%8==0)", ATT_NKMAX); return VLFM_E_UNSUPPORTED; }
+  AttnArgs a{(const __half*)d_q, (const __half*)d_k, (const __half*)d_v, (__half*)d_o, ldq, ldk, ldv, ldo, Nq, Nk, hd, heads,
+             scale * 1.4426950408889634f};
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((Nq + ATT_QBLK - 1) / ATT_QBLK, heads, B);
+  if (hd <= 64) {
+    constexpr size_t sm = (size_t)(ATT_NKMAX * (64 + 8) + 64 * (ATT_NKMAX + 8)) * 2;
+    static bool cfg = false;
+    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "attr(attention<64>)"); if (rc) return rc; cfg = true; }
+    attention_kernel<64><<<grid, 32 * ATT_WARPS, sm, st>>>(a);
+  } else {
+    constexpr size_t sm = (size_t)(ATT_NKMAX * (96 + 8) + 96 * (ATT_NKMAX + 8)) * 2;
+    static bool cfg = false;
+    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "attr(attention<96>)"); if (rc) return rc; cfg = true; }
+    attention_kernel<96><<<grid, 32 * ATT_WARPS, sm, st>>>(a);
+  }
+  VLFM_CHECK_LAUNCH("attention_kernel");
+  count_launch();
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_itc_head(const float* d_proj, const float* d_text, float* d_out, int B, int Q, int D, void* stream) {
+  if (!d_proj || !d_text || !d_out || B < 1) { set_error("vlfm_itc_head: bad argument"); return VLFM_E_INVALID; }
+  itc_head_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(d_proj, d_text, d_out, Q, D);
+  VLFM_CHECK_LAUNCH("itc_head_kernel");
+  count_launch();
+  return VLFM_OK;
+}

@@ -1,0 +1,285 @@
+"""BLIP-2 ITC forward on hand-written sm_100a kernels (through the C-ABI).
+
+Replaces what ``self.model({"image": img, "text_input": txt}, match_head="itc")`` does
+inside ``BLIP2ITM.cosine`` (vlfm/vlm/blip2itm.py:52) together with the preprocessing at
+:48-49.  Python here only sequences C-ABI launches over preallocated buffers; the whole
+per-batch forward is captured once in a CUDA graph and replayed.
+
+Numerics: fp16 GEMM/attention operands (lavis runs the ViT under fp16 autocast too),
+fp32 accumulation (TMEM), fp32 residual stream, fp32 LayerNorm / softmax statistics.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .blip2_config import Blip2Dims
+from .preprocess import CLIP_MEAN, CLIP_STD, bicubic_tables
+
+F16, F32 = torch.float16, torch.float32
+
+
+class Blip2ITCEngine:
+    def __init__(self, dims: Blip2Dims, state_dict: Dict[str, torch.Tensor], device="cuda", max_batch: int = 1,
+                 use_graph: bool = True) -> None:
+        if not torch.cuda.is_available():
+            raise _lib.VlfmError("vlfm_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.d = dims
+        self.dev = torch.device(device)
+        self.max_batch = max_batch
+        self.use_graph = use_graph
+        self._graphs: Dict[Tuple[int, int, int], Tuple[torch.cuda.CUDAGraph, torch.Tensor]] = {}
+        self._tables: Dict[Tuple[int, int], Tuple[torch.Tensor, ...]] = {}
+        self._mean = (ctypes.c_float * 3)(*CLIP_MEAN)
+        self._std = (ctypes.c_float * 3)(*CLIP_STD)
+        self._load(state_dict)
+        self._alloc(max_batch)
+        self.text_feat = torch.zeros(dims.proj, dtype=F32, device=self.dev)
+
+    # ------------------------------------------------------------------ weights ----
+    def _load(self, sd: Dict[str, torch.Tensor]) -> None:
+        d, dev = self.d, self.dev
+
+        def h(t):  # fp16 GEMM operand
+            return t.to(dev, F16).contiguous()
+
+        def f(t):
+            return t.to(dev, F32).contiguous()
+
+        D = d.v_hidden
+        pw = sd["vision_model.embeddings.patch_embedding.weight"].reshape(D, d.patch_k)
+        pwp = torch.zeros(D, d.patch_k_padded)
+        pwp[:, : d.patch_k] = pw
+        self.patch_w, self.patch_b = h(pwp), f(sd["vision_model.embeddings.patch_embedding.bias"])
+        self.cls = f(sd["vision_model.embeddings.class_embedding"].reshape(D))
+        self.pos = f(sd["vision_model.embeddings.position_embedding"].reshape(d.tokens, D))
+        self.vit: List[Dict[str, torch.Tensor]] = []
+        for i in range(d.v_layers):
+            p = f"vision_model.encoder.layers.{i}."
+            self.vit.append(dict(
+                ln1_w=f(sd[p + "layer_norm1.weight"]), ln1_b=f(sd[p + "layer_norm1.bias"]),
+                qkv_w=h(sd[p + "self_attn.qkv.weight"]), qkv_b=f(sd[p + "self_attn.qkv.bias"]),
+                proj_w=h(sd[p + "self_attn.projection.weight"]), proj_b=f(sd[p + "self_attn.projection.bias"]),
+                ln2_w=f(sd[p + "layer_norm2.weight"]), ln2_b=f(sd[p + "layer_norm2.bias"]),
+                fc1_w=h(sd[p + "mlp.fc1.weight"]), fc1_b=f(sd[p + "mlp.fc1.bias"]),
+                fc2_w=h(sd[p + "mlp.fc2.weight"]), fc2_b=f(sd[p + "mlp.fc2.bias"]),
+            ))
+        self.post_w, self.post_b = f(sd["vision_model.post_layernorm.weight"]), f(sd["vision_model.post_layernorm.bias"])
+        H = d.q_hidden
+        self.q_ln_w, self.q_ln_b = f(sd["qformer.layernorm.weight"]), f(sd["qformer.layernorm.bias"])
+        self.word_emb, self.pos_emb = f(sd["embeddings.word_embeddings.weight"]), f(sd["embeddings.position_embeddings.weight"])
+        self.qf: List[Dict[str, torch.Tensor]] = []
+        kv_w, kv_b = [], []
+        for i in range(d.q_layers):
+            p = f"qformer.encoder.layer.{i}."
+            a = p + "attention."
+            L = dict(
+                qkv_w=h(torch.cat([sd[a + "attention.query.weight"], sd[a + "attention.key.weight"], sd[a + "attention.value.weight"]], 0)),
+                qkv_b=f(torch.cat([sd[a + "attention.query.bias"], sd[a + "attention.key.bias"], sd[a + "attention.value.bias"]], 0)),
+                so_w=h(sd[a + "output.dense.weight"]), so_b=f(sd[a + "output.dense.bias"]),
+                sln_w=f(sd[a + "output.LayerNorm.weight"]), sln_b=f(sd[a + "output.LayerNorm.bias"]),
+                iq_w=h(sd[p + "intermediate_query.dense.weight"]), iq_b=f(sd[p + "intermediate_query.dense.bias"]),
+                oq_w=h(sd[p + "output_query.dense.weight"]), oq_b=f(sd[p + "output_query.dense.bias"]),
+                oqln_w=f(sd[p + "output_query.LayerNorm.weight"]), oqln_b=f(sd[p + "output_query.LayerNorm.bias"]),
+                it_w=h(sd[p + "intermediate.dense.weight"]), it_b=f(sd[p + "intermediate.dense.bias"]),
+                ot_w=h(sd[p + "output.dense.weight"]), ot_b=f(sd[p + "output.dense.bias"]),
+                otln_w=f(sd[p + "output.LayerNorm.weight"]), otln_b=f(sd[p + "output.LayerNorm.bias"]),
+                cross=-1,
+            )
+            if i % d.cross_freq == 0:
+                c = p + "crossattention."
+                L["cross"] = len(kv_w)
+                L["cq_w"], L["cq_b"] = h(sd[c + "attention.query.weight"]), f(sd[c + "attention.query.bias"])
+                L["co_w"], L["co_b"] = h(sd[c + "output.dense.weight"]), f(sd[c + "output.dense.bias"])
+                L["cln_w"], L["cln_b"] = f(sd[c + "output.LayerNorm.weight"]), f(sd[c + "output.LayerNorm.bias"])
+                kv_w.append(torch.cat([sd[c + "attention.key.weight"], sd[c + "attention.value.weight"]], 0))
+                kv_b.append(torch.cat([sd[c + "attention.key.bias"], sd[c + "attention.value.bias"]], 0))
+            self.qf.append(L)
+        self.ncross = len(kv_w)
+        self.kv_w, self.kv_b = h(torch.cat(kv_w, 0)), f(torch.cat(kv_b, 0))  # one GEMM feeds every cross layer
+        self.vp_w, self.vp_b = h(sd["vision_projection.weight"]), f(sd["vision_projection.bias"])
+        self.tp_w, self.tp_b = h(sd["text_projection.weight"]), f(sd["text_projection.bias"])
+        # layernorm(query_tokens) is input independent (modeling: qformer.layernorm on query_embeds)
+        q0 = f(sd["query_tokens"].reshape(d.queries, H))
+        self.q0_32 = torch.empty_like(q0)
+        self.q0_16 = torch.empty(d.queries, H, dtype=F16, device=dev)
+        self._ln(q0, self.q_ln_w, self.q_ln_b, self.q0_16, self.q0_32, d.q_eps)
+
+    def weight_bytes(self) -> int:
+        n = 0
+        for t in [self.patch_w, self.kv_w, self.vp_w] + [v for L in self.vit for k, v in L.items() if k.endswith("_w") and v.dtype == F16] \
+                + [v for L in self.qf for k, v in L.items() if isinstance(v, torch.Tensor) and v.dtype == F16 and k[:2] not in ("it", "ot")]:
+            n += t.numel() * 2
+        return n
+
+    # ------------------------------------------------------------------ buffers ----
+    def _alloc(self, B: int) -> None:
+        d, dev = self.d, self.dev
+        T, D, Fv, Q, H, I = d.tokens, d.v_hidden, d.v_inter, d.queries, d.q_hidden, d.q_inter
+        e = lambda *s, dt=F16: torch.empty(*s, dtype=dt, device=dev)
+        self.b_col = torch.zeros(B * (T - 1), d.patch_k_padded, dtype=F16, device=dev)  # zero K padding stays zero
+        self.b_patch = e(B * (T - 1), D, dt=F32)
+        self.b_x = e(B * T, D, dt=F32)
+        self.b_xn = e(B * T, D)
+        self.b_qkv = e(B * T, 3 * D)
+        self.b_ao = e(B * T, D)
+        self.b_h = e(B * T, Fv)
+        self.b_img = e(B * T, D)
+        self.b_kv = e(B * T, self.ncross * 2 * H)
+        self.q_h32 = e(B * Q, H, dt=F32)
+        self.q_h16 = e(B * Q, H)
+        self.q_qkv = e(B * Q, 3 * H)
+        self.q_q = e(B * Q, H)
+        self.q_ao = e(B * Q, H)
+        self.q_f = e(B * Q, I)
+        self.q_proj = e(B * Q, d.proj, dt=F32)
+        self.out = torch.zeros(B, dtype=F32, device=dev)
+
+    # ---------------------------------------------------------------- primitives ----
+    def _gemm(self, a, w, bias, epi, out):
+        M, K = a.shape
+        rc = self.lib.vlfm_gemm_f16(a.data_ptr(), w.data_ptr(), _lib.ptr(bias), out.data_ptr(), M, w.shape[0], K,
+                                    a.stride(0), w.stride(0), out.stride(0), epi, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_gemm_f16")
+
+    def _ln(self, x, g, b, out16, out32, eps):
+        rows, D = x.shape
+        rc = self.lib.vlfm_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), _lib.ptr(out16), _lib.ptr(out32), rows, D,
+                                     x.stride(0), out16.stride(0) if out16 is not None else 0,
+                                     out32.stride(0) if out32 is not None else 0, eps, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_layernorm")
+
+    def _attn(self, q, k, v, o, B, heads, Nq, Nk, hd, scale):
+        rc = self.lib.vlfm_attention_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, heads, Nq, Nk, hd,
+                                         q.stride(0), k.stride(0), v.stride(0), o.stride(0), scale, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_attention_f16")
+
+    def _resize_tables(self, h: int, w: int):
+        key = (h, w)
+        if key not in self._tables:
+            hb, hk, hks = bicubic_tables(w, self.d.image)
+            vb, vk, vks = bicubic_tables(h, self.d.image)
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+            self._tables[key] = (t(hb), t(hk), hks, t(vb), t(vk), vks)
+        return self._tables[key]
+
+    # ------------------------------------------------------------------ forward ----
+    def _forward_impl(self, img: torch.Tensor, mid: torch.Tensor) -> None:
+        """img [B,H,W,3] uint8 (device) -> self.out[:B] cosines.  Pure launch sequence."""
+        d = self.d
+        B, Hh, Ww, _ = img.shape
+        T, D, Q, H = d.tokens, d.v_hidden, d.queries, d.q_hidden
+        n, nq = B * T, B * Q
+        hb, hk, hks, vb, vk, vks = self._resize_tables(Hh, Ww)
+        rc = self.lib.vlfm_preprocess_im2col(img.data_ptr(), mid.data_ptr(), self.b_col.data_ptr(), B, Hh, Ww, d.image, d.image,
+                                             d.patch, d.patch_k_padded, hb.data_ptr(), hk.data_ptr(), hks, vb.data_ptr(),
+                                             vk.data_ptr(), vks, self._mean, self._std, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_preprocess_im2col")
+        self._gemm(self.b_col[: B * (T - 1)], self.patch_w, self.patch_b, _lib.EPI_BIAS_F32, self.b_patch[: B * (T - 1)])
+        rc = self.lib.vlfm_assemble_tokens(self.b_patch.data_ptr(), self.cls.data_ptr(), self.pos.data_ptr(), self.b_x.data_ptr(),
+                                           B, T, D, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_assemble_tokens")
+        x, xn, qkv, ao, hb_ = self.b_x[:n], self.b_xn[:n], self.b_qkv[:n], self.b_ao[:n], self.b_h[:n]
+        hd = D // d.v_heads
+        for L in self.vit:
+            self._ln(x, L["ln1_w"], L["ln1_b"], xn, None, d.v_eps)
+            self._gemm(xn, L["qkv_w"], L["qkv_b"], _lib.EPI_BIAS_F16, qkv)
+            self._attn(qkv[:, 0:D], qkv[:, D : 2 * D], qkv[:, 2 * D : 3 * D], ao, B, d.v_heads, T, T, hd, hd**-0.5)
+            self._gemm(ao, L["proj_w"], L["proj_b"], _lib.EPI_BIAS_RESID_F32, x)
+            self._ln(x, L["ln2_w"], L["ln2_b"], xn, None, d.v_eps)
+            self._gemm(xn, L["fc1_w"], L["fc1_b"], _lib.EPI_BIAS_GELU_F16, hb_)
+            self._gemm(hb_, L["fc2_w"], L["fc2_b"], _lib.EPI_BIAS_RESID_F32, x)
+        img16 = self.b_img[:n]
+        self._ln(x, self.post_w, self.post_b, img16, None, d.v_eps)
+        kv = self.b_kv[:n]
+        self._gemm(img16, self.kv_w, self.kv_b, _lib.EPI_BIAS_F16, kv)
+        h32, h16 = self.q_h32[:nq], self.q_h16[:nq]
+        h32.view(B, Q, H).copy_(self.q0_32)
+        h16.view(B, Q, H).copy_(self.q0_16)
+        self._qformer_layers(h32, h16, B, Q, kv, T, text=False)
+        self._gemm(h16, self.vp_w, self.vp_b, _lib.EPI_BIAS_F32, self.q_proj[:nq])
+        rc = self.lib.vlfm_itc_head(self.q_proj.data_ptr(), self.text_feat.data_ptr(), self.out.data_ptr(), B, Q, d.proj,
+                                    _lib.stream_ptr())
+        _lib.check(rc, "vlfm_itc_head")
+
+    def _qformer_layers(self, h32, h16, B, S, kv, T, text: bool) -> None:
+        d = self.d
+        H = d.q_hidden
+        hd = H // d.q_heads
+        n = B * S
+        qkv, qq, ao, ff = self.q_qkv[:n], self.q_q[:n], self.q_ao[:n], self.q_f[:n]
+        sc = 1.0 / math.sqrt(hd)
+        for L in self.qf:
+            self._gemm(h16, L["qkv_w"], L["qkv_b"], _lib.EPI_BIAS_F16, qkv)
+            self._attn(qkv[:, 0:H], qkv[:, H : 2 * H], qkv[:, 2 * H : 3 * H], ao, B, d.q_heads, S, S, hd, sc)
+            self._gemm(ao, L["so_w"], L["so_b"], _lib.EPI_BIAS_RESID_F32, h32)
+            self._ln(h32, L["sln_w"], L["sln_b"], h16, h32, d.q_eps)
+            if not text and L["cross"] >= 0:
+                j = L["cross"]
+                self._gemm(h16, L["cq_w"], L["cq_b"], _lib.EPI_BIAS_F16, qq)
+                self._attn(qq, kv[:, j * 2 * H : j * 2 * H + H], kv[:, j * 2 * H + H : (j + 1) * 2 * H], ao, B, d.q_heads, S, T, hd, sc)
+                self._gemm(ao, L["co_w"], L["co_b"], _lib.EPI_BIAS_RESID_F32, h32)
+                self._ln(h32, L["cln_w"], L["cln_b"], h16, h32, d.q_eps)
+            iw, ib, ow, ob, lw, lb = ((L["it_w"], L["it_b"], L["ot_w"], L["ot_b"], L["otln_w"], L["otln_b"]) if text else
+                                      (L["iq_w"], L["iq_b"], L["oq_w"], L["oq_b"], L["oqln_w"], L["oqln_b"]))
+            self._gemm(h16, iw, ib, _lib.EPI_BIAS_GELU_F16, ff)
+            self._gemm(ff, ow, ob, _lib.EPI_BIAS_RESID_F32, h32)
+            self._ln(h32, lw, lb, h16, h32, d.q_eps)
+
+    # ------------------------------------------------------------------- public ----
+    @torch.inference_mode()
+    def encode_text(self, token_ids: Sequence[int]) -> torch.Tensor:
+        """Q-Former text branch (query_length=0) -> normalised text feature [proj]; run once per prompt."""
+        d = self.d
+        ids = torch.tensor(list(token_ids), dtype=torch.long, device=self.dev)
+        S = len(ids)
+        assert 1 <= S <= self.d.queries * self.max_batch and S <= 272
+        emb = (self.word_emb[ids] + self.pos_emb[:S]).contiguous()
+        h32, h16 = self.q_h32[:S], self.q_h16[:S]
+        with torch.cuda.device(self.dev):
+            self._ln(emb, self.q_ln_w, self.q_ln_b, h16, h32, d.q_eps)
+            self._qformer_layers(h32, h16, 1, S, None, 0, text=True)
+            tp = torch.empty(1, d.proj, dtype=F32, device=self.dev)
+            self._gemm(h16[:1], self.tp_w, self.tp_b, _lib.EPI_BIAS_F32, tp)
+        return torch.nn.functional.normalize(tp[0], dim=-1)
+
+    def set_text(self, feat: torch.Tensor) -> None:
+        self.text_feat.copy_(feat)
+
+    @torch.inference_mode()
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """images [B,H,W,3] uint8 on the device -> cosine [B] (device, fp32) against the
+        text feature last given to set_text()."""
+        B, Hh, Ww, _ = images.shape
+        assert B <= self.max_batch and images.dtype == torch.uint8 and images.is_contiguous()
+        key = (B, Hh, Ww)
+        with torch.cuda.device(self.dev):
+            if not self.use_graph:
+                mid = torch.empty(B, Hh, self.d.image, 3, dtype=torch.uint8, device=self.dev)
+                self._forward_impl(images, mid)
+                return self.out[:B]
+            if key not in self._graphs:
+                static_in = torch.empty_like(images)
+                mid = torch.empty(B, Hh, self.d.image, 3, dtype=torch.uint8, device=self.dev)
+                static_in.copy_(images)
+                self._forward_impl(static_in, mid)  # warm-up: function attributes, table upload
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._forward_impl(static_in, mid)
+                self._graphs[key] = (g, static_in, mid)
+            g, static_in, _ = self._graphs[key]
+            static_in.copy_(images, non_blocking=True)
+            g.replay()
+        return self.out[:B]
+
+    def launches_per_forward(self) -> int:
+        d = self.d
+        per_q = 7 + 0  # qkv, attn, dense, ln, inter, out, ln
+        return 2 + 1 + 1 + d.v_layers * 7 + 1 + 1 + d.q_layers * per_q + self.ncross * 4 + 1 + 1
