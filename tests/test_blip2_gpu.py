@@ -59,8 +59,8 @@ def test_small_models_vs_oracle(dims, tol):
 
 
 def test_full_size_vitg_vs_oracle():
-    """ViT-g/14 (39 layers, 1408) + 12-layer Q-Former, seeded synthetic weights: cosine within 5e-3
-    of the fp32 oracle (fp16 tensor-core operands, fp32 accumulation; measured error is printed)."""
+    """ViT-g/14 (39 layers, 1408) + 12-layer Q-Former, seeded synthetic weights: cosine within 2e-4
+    of the fp32 oracle (fp16 tensor-core operands, fp32 accumulation; measured 5e-5 / 4e-6 on B200, printed)."""
     from vlfm_b200.vlm.blip2itm import BLIP2ITM
 
     dims = Blip2Dims()
@@ -76,4 +76,4 @@ def test_full_size_vitg_vs_oracle():
         ref, got = orc.cosine(img, ids), m.cosine(img, "x")
         errs.append(abs(ref - got))
         print("cosine ref", ref, "gpu", got, "abs err", abs(ref - got))
-    assert max(errs) <= 5e-3
+    assert max(errs) <= 2e-4

@@ -86,7 +86,12 @@ struct GemmArgs {
   const float* bias;
   void* out;
   int M, N, K, ldo, epi;
+  int kb_per_split;   // K-blocks per grid.z slice (split-K, residual epilogue only)
 };
+
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
@@ -108,7 +113,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x, m_blk = blockIdx.y;
-  const int num_k = (g.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * g.kb_per_split;
+  const int num_k = min((g.K + BK - 1) / BK - kb_begin, g.kb_per_split);   // K-blocks of this split
+  const bool split = gridDim.z > 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -133,8 +140,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-        tma_load_2d(smem_u32(sA + s * A_BYTES), &tmA, kb * BK, m_blk * BM, full0 + 8 * s);
-        tma_load_2d(smem_u32(sB + s * B_BYTES), &tmB, kb * BK, n_blk * BN, full0 + 8 * s);
+        tma_load_2d(smem_u32(sA + s * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * s);
+        tma_load_2d(smem_u32(sB + s * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * s);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -170,7 +177,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float b = (g.bias && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
+        float b = (g.bias && blockIdx.z == 0 && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
         v[j] = __uint_as_float(r[j]) + b;
       }
       const bool fullw = (n0 + 32 <= g.N);
@@ -200,6 +207,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (split) { red_add_f32x4(o + j, t.x, t.y, t.z, t.w); continue; }
             if (add) {
               float4 old = *reinterpret_cast<const float4*>(o + j);
               t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
@@ -207,7 +215,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             *reinterpret_cast<float4*>(o + j) = t;
           }
         } else {
-          for (int j = 0; j < 32 && n0 + j < g.N; ++j) o[j] = add ? o[j] + v[j] : v[j];
+          for (int j = 0; j < 32 && n0 + j < g.N; ++j) {
+            if (split) atomicAdd(o + j, v[j]);
+            else o[j] = add ? o[j] + v[j] : v[j];
+          }
         }
       }
     }
@@ -265,7 +276,8 @@ static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const Gemm
     if (rc) return rc;
     configured = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  const int num_k = (g.K + BK - 1) / BK;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (num_k + g.kb_per_split - 1) / g.kb_per_split);
   gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, g);
   VLFM_CHECK_LAUNCH("gemm_f16_tcgen05_kernel");
   count_launch();
@@ -282,13 +294,27 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
     set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
   if (epilogue < 0 || epilogue > 3) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue};
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK};
   CUtensorMap ta;
   int rc = make_map(&ta, d_A, M, K, lda, BM);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // tile width: fill >= ~120 of the 148 SMs when M is small, widest tile otherwise
   const long mt = (M + BM - 1) / BM;
+  if (epilogue == VLFM_EPI_BIAS_RESID_F32) {
+    // small-M residual projections: keep the wide tile (A/B tiles re-read less) and fill the SMs by
+    // splitting K; partial sums are reduced with vectorised fp32 red.add into the residual stream.
+    const long tiles = mt * ((N + 127) / 128);
+    const int num_k = (K + BK - 1) / BK;
+    if (tiles < 120 && num_k >= 8) {
+      int splits = (int)((148 + tiles - 1) / tiles);
+      if (splits > num_k / 4) splits = num_k / 4;
+      if (splits > 1) {
+        g.kb_per_split = (num_k + splits - 1) / splits;
+        return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
+      }
+    }
+  }
   if (mt * ((N + 127) / 128) >= 120) return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
   if (mt * ((N + 63) / 64) >= 120) return launch_gemm<64, 8>(ta, d_W, ldw, g, st);
   return launch_gemm<32, 8>(ta, d_W, ldw, g, st);

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -33,7 +34,7 @@ class Blip2ITCEngine:
         self.d = dims
         self.dev = torch.device(device)
         self.max_batch = max_batch
-        self.use_graph = use_graph
+        self.use_graph = use_graph and os.environ.get("VLFM_NO_GRAPH", "") != "1"
         self._graphs: Dict[Tuple[int, int, int], Tuple[torch.cuda.CUDAGraph, torch.Tensor]] = {}
         self._tables: Dict[Tuple[int, int], Tuple[torch.Tensor, ...]] = {}
         self._mean = (ctypes.c_float * 3)(*CLIP_MEAN)
