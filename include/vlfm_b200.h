@@ -138,6 +138,10 @@ int vlfm_obstacle_update(const VlfmObstacleParams* p, int batch, const int32_t* 
 #define VLFM_EPI_BIAS_GELU_F16 1
 #define VLFM_EPI_BIAS_RESID_F32 2
 #define VLFM_EPI_BIAS_F32 3
+/* development aid: CTA (0,0,0) of every later GEMM launch writes clock64() at its phase boundaries
+ * (start, setup done, dependency wait done, first stage landed, last MMA issued, accumulator ready,
+ * epilogue done) and %globaltimer into d_buf8[0..7]; NULL disables. */
+void vlfm_gemm_debug_timeline(unsigned long long* d_buf8);
 int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
                   int K, int lda, int ldw, int ldo, int epilogue, void* stream);
 

@@ -25,6 +25,11 @@ def main():
         ms = timeit(lambda: gemm_f16(a, w, b, 0, o))
         ms_t = timeit(lambda: torch.matmul(a, w.t()))
         print(f"gemm {M}x{N}x{K}: {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:8.1f} TFLOP/s   (torch/cuBLAS {ms_t*1e3:8.1f} us {2*M*N*K/ms_t/1e9:8.1f} TF)")
+    for (M, N, K) in [(257, 1408, 1408), (257, 1408, 6144), (32, 768, 3072)]:
+        a = torch.randn(M, K, device="cuda").half(); w = torch.randn(N, K, device="cuda").half(); b = torch.zeros(N, device="cuda")
+        o = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+        ms = timeit(lambda: gemm_f16(a, w, b, 2, o))
+        print(f"gemm+resid(split-K) {M}x{N}x{K}: {ms*1e3:8.1f} us  {2*M*N*K/ms/1e9:8.1f} TFLOP/s")
     from vlfm_b200.mapping.value_map import ValueMapBatch
     from vlfm_b200.utils.synthetic import trajectory
     fov = float(np.deg2rad(79))

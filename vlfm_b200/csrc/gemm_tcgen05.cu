@@ -82,11 +82,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// optional per-CTA timeline (development aid): vlfm_gemm_debug_timeline(ptr) makes CTA (0,0,0) of every
+// launch record clock64() at its phase boundaries into ptr[0..7].
+static unsigned long long* g_gemm_dbg = nullptr;
+
 struct GemmArgs {
   const float* bias;
   void* out;
   int M, N, K, ldo, epi;
   int kb_per_split;   // K-blocks per grid.z slice (split-K, residual epilogue only)
+  unsigned long long* dbg;
 };
 
 __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
@@ -111,8 +116,11 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accbar = smem_u32(bars + 2 * STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+  const bool dbg = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg && threadIdx.x == 0) { g.dbg[0] = clock64(); unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[7] = t; }
   const int kb_begin = blockIdx.z * g.kb_per_split;
   const int num_k = min((g.K + BK - 1) / BK - kb_begin, g.kb_per_split);   // K-blocks of this split
   const bool split = gridDim.z > 1;
@@ -133,6 +141,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) g.dbg[1] = clock64();
+  pdl_wait();   // predecessors' global writes (A operand, residual stream) are visible from here on
+  if (dbg && threadIdx.x == 0) g.dbg[2] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -150,6 +161,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(full0 + 8 * s, ph);
+        if (dbg && kb == 0) g.dbg[3] = clock64();
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * B_BYTES);
 #pragma unroll
@@ -161,12 +173,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       tc_commit(accbar);             // accumulator complete
+      if (dbg) g.dbg[4] = clock64();
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
     const int row = m_blk * BM + q * 32 + lane;
     mbar_wait(accbar, 0);
+    if (dbg && threadIdx.x == 64) g.dbg[5] = clock64();
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -175,12 +189,21 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int n0 = n_blk * BN + c * 32;
       if (row >= g.M || n0 >= g.N) continue;
       float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float b = (g.bias && blockIdx.z == 0 && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
-        v[j] = __uint_as_float(r[j]) + b;
-      }
       const bool fullw = (n0 + 32 <= g.N);
+      if (g.bias && blockIdx.z == 0 && fullw) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
+          v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float b = (g.bias && blockIdx.z == 0 && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
+          v[j] = __uint_as_float(r[j]) + b;
+        }
+      }
       if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16) {
         if (g.epi == VLFM_EPI_BIAS_GELU_F16) {
 #pragma unroll
@@ -225,6 +248,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) g.dbg[6] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -278,8 +302,8 @@ static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const Gemm
   }
   const int num_k = (g.K + BK - 1) / BK;
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (num_k + g.kb_per_split - 1) / g.kb_per_split);
-  gemm_f16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, g);
-  VLFM_CHECK_LAUNCH("gemm_f16_tcgen05_kernel");
+  rc = check_cuda(launch_pdl(gemm_f16_tcgen05_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), smem, st, ta, tb, g), "gemm_f16_tcgen05_kernel");
+  if (rc) return rc;
   count_launch();
   return VLFM_OK;
 }
@@ -288,34 +312,46 @@ static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const Gemm
 
 using namespace vlfm;
 
+extern "C" void vlfm_gemm_debug_timeline(unsigned long long* d_buf8) { vlfm::g_gemm_dbg = d_buf8; }
+
 extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
                              int K, int lda, int ldw, int ldo, int epilogue, void* stream) {
   if (!d_A || !d_W || !d_out || M < 1 || N < 1 || K < 1) { set_error("vlfm_gemm_f16: bad argument"); return VLFM_E_INVALID; }
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
     set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
   if (epilogue < 0 || epilogue > 3) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK};
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg};
   CUtensorMap ta;
   int rc = make_map(&ta, d_A, M, K, lda, BM);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // tile width: fill >= ~120 of the 148 SMs when M is small, widest tile otherwise
-  const long mt = (M + BM - 1) / BM;
-  if (epilogue == VLFM_EPI_BIAS_RESID_F32) {
-    // small-M residual projections: keep the wide tile (A/B tiles re-read less) and fill the SMs by
-    // splitting K; partial sums are reduced with vectorised fp32 red.add into the residual stream.
-    const long tiles = mt * ((N + 127) / 128);
-    const int num_k = (K + BK - 1) / BK;
-    if (tiles < 120 && num_k >= 8) {
-      int splits = (int)((148 + tiles - 1) / tiles);
-      if (splits > num_k / 4) splits = num_k / 4;
-      if (splits > 1) {
-        g.kb_per_split = (num_k + splits - 1) / splits;
-        return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
-      }
+  // Tile / split-K plan from a small cost model (us): waves x (fixed + bytes a CTA must pull / its share of
+  // the L2->SM bandwidth).  Never spill into a second wave for a handful of CTAs; split K only for the
+  // fp32 residual epilogue (partials are reduced with red.add into the residual stream).
+  const int mt = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
+  int best_bn = 128, best_s = 1;
+  double best_t = 1e30;
+  const int bns[3] = {128, 64, 32};
+  for (int bi = 0; bi < 3; ++bi) {
+    const int bn = bns[bi], nt = (N + bn - 1) / bn;
+    int smax = (epilogue == VLFM_EPI_BIAS_RESID_F32) ? num_k / 4 : 1;
+    if (smax < 1) smax = 1;
+    if (smax > 8) smax = 8;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const double ctas = (double)mt * nt * sp;
+      const int kb = (num_k + sp - 1) / sp;
+      const double waves = (double)(long)((ctas + 147) / 148);
+      const double active = ctas < 148 ? ctas : 148;
+      double bw = 8000.0 / active;             // KB/us per CTA when the chip-wide rate is shared
+      if (bw > 90.0) bw = 90.0;                // one SM's ingest limit
+      const double kbytes = (double)kb * (128 + bn) * 128 / 1024.0;
+      const double t = waves * (3.5 + kbytes / bw) + (sp > 1 ? 0.7 : 0.0);
+      if (t < best_t) { best_t = t; best_bn = bn; best_s = sp; }
     }
   }
-  if (mt * ((N + 127) / 128) >= 120) return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
-  if (mt * ((N + 63) / 64) >= 120) return launch_gemm<64, 8>(ta, d_W, ldw, g, st);
+  g.kb_per_split = (num_k + best_s - 1) / best_s;
+  if (best_bn == 128) return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
+  if (best_bn == 64) return launch_gemm<64, 8>(ta, d_W, ldw, g, st);
   return launch_gemm<32, 8>(ta, d_W, ldw, g, st);
 }

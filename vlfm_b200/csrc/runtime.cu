@@ -1,6 +1,7 @@
 // Error string, version and launch accounting for the vlfm_b200 C-ABI.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -16,6 +17,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VLFM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 }  // namespace vlfm
 
 extern "C" const char* vlfm_last_error(void) { return vlfm::g_err; }

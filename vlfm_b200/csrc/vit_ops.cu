@@ -74,43 +74,62 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ patch, const fl
 }
 
 // ------------------------------------------------------------------- LayerNorm ----
-// one warp per row; two-pass (mean, then centred variance) in registers.
-template <int MAXV>
-__global__ void __launch_bounds__(256)
+// one warp per row, float4 lanes; x, gamma and beta are all fetched up front (every load of the
+// kernel is in flight before the first reduction), two-pass statistics in registers.
+template <int MAXV4>
+__global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __half* __restrict__ out16, float* __restrict__ out32, int rows, int D, int ldx, int ldo16, int ldo32,
                  float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  pdl_trigger();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  float4 g[MAXV4], bt[MAXV4], v[MAXV4];
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {   // parameters do not depend on the predecessor kernel
+    const int j = lane + 32 * i;
+    g[i] = j < D4 ? __ldg(reinterpret_cast<const float4*>(gamma) + j) : make_float4(0, 0, 0, 0);
+    bt[i] = j < D4 ? __ldg(reinterpret_cast<const float4*>(beta) + j) : make_float4(0, 0, 0, 0);
+  }
+  pdl_wait();
   if (row >= rows) return;
-  const float* xr = x + (size_t)row * ldx;
-  float v[MAXV];
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int d = lane + 32 * i;
-    v[i] = d < D ? xr[d] : 0.f;
-    s += v[i];
+  for (int i = 0; i < MAXV4; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = j < D4 ? xr[j] : make_float4(0, 0, 0, 0);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int d = lane + 32 * i;
-    float c = d < D ? v[i] - mean : 0.f;
-    q += c * c;
+  for (int i = 0; i < MAXV4; ++i) {
+    if (lane + 32 * i < D4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)D + eps);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int d = lane + 32 * i;
-    if (d < D) {
-      float y = (v[i] - mean) * rstd * gamma[d] + beta[d];
-      if (out16) out16[(size_t)row * ldo16 + d] = __float2half_rn(y);
-      if (out32) out32[(size_t)row * ldo32 + d] = y;
+  for (int i = 0; i < MAXV4; ++i) {
+    const int j = lane + 32 * i;
+    if (j < D4) {
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x;
+      y.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
+      y.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z;
+      y.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
+      if (out16) {
+        __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + 4 * j) = pk;
+      }
+      if (out32) *reinterpret_cast<float4*>(out32 + (size_t)row * ldo32 + 4 * j) = y;
     }
   }
 }
@@ -135,42 +154,61 @@ struct AttnArgs {
 };
 
 constexpr int ATT_WARPS = 4;
-constexpr int ATT_QBLK = 16 * ATT_WARPS;   // 64 query rows per CTA
+constexpr int ATT_QBLK = 32;               // query rows per CTA: 2 row groups x 2 key halves
 constexpr int ATT_NKMAX = 272;             // keys padded to a multiple of 16
 
-// grid (ceil(Nq/64), heads, B).  K [key][hd] and V^T [hd][key] of one (batch, head) in smem.
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const __half* p) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+// grid (ceil(Nq/32), heads, B), 4 warps.  K and V of one (batch, head) are staged row-major
+// [key][hd] in padded (conflict-free) shared memory with 16-byte copies.  Warp w owns query rows
+// 16*(w&1).. and the key half (w>>1); the two halves are merged flash-style through shared memory.
+// S = Q K^T and O = P V run on mma.sync m16n8k16 (fp16 in, fp32 accumulate); V fragments come from
+// ldmatrix.trans.
 template <int HDP>
 __global__ void __launch_bounds__(32 * ATT_WARPS)
 attention_kernel(AttnArgs a) {
-  constexpr int KS = HDP + 8;            // K row stride (halves): conflict-free fragment loads
-  constexpr int VS = ATT_NKMAX + 8;      // V^T row stride (halves)
+  constexpr int KS = HDP + 8;            // row stride (halves) of sK / sV
   extern __shared__ __align__(16) uint8_t att_smem[];
-  __half* sK = reinterpret_cast<__half*>(att_smem);            // [ATT_NKMAX][KS]
-  __half* sV = sK + ATT_NKMAX * KS;                            // [HDP][VS]
+  __half* sK = reinterpret_cast<__half*>(att_smem);            // [NKP][KS]
   const int b = blockIdx.z, h = blockIdx.y, qb = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int NKP = (a.Nk + 15) & ~15;
+  __half* sV = sK + NKP * KS;                                  // [NKP][KS]
+  pdl_trigger();
+  pdl_wait();
   const __half* kbase = a.k + (size_t)b * a.Nk * a.ldk + (size_t)h * a.hd;
   const __half* vbase = a.v + (size_t)b * a.Nk * a.ldv + (size_t)h * a.hd;
 
-  // ---- stage K and V^T (16-byte global loads; zero padding)
-  const int chunks = HDP / 8;
-  for (int i = tid; i < NKP * chunks; i += 32 * ATT_WARPS) {
-    const int key = i / chunks, c = (i - key * chunks) * 8;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (key < a.Nk && c < a.hd) {
-      kv = *reinterpret_cast<const uint4*>(kbase + (size_t)key * a.ldk + c);
-      vv = *reinterpret_cast<const uint4*>(vbase + (size_t)key * a.ldv + c);
-    }
-    *reinterpret_cast<uint4*>(sK + key * KS + c) = kv;
-    const __half* vh = reinterpret_cast<const __half*>(&vv);
+  // ---- stage K and V (16-byte copies, zero padding of rows >= Nk and columns >= hd)
+  constexpr int CH = HDP / 8;
+  for (int i0 = tid; i0 < NKP * CH; i0 += 4 * 32 * ATT_WARPS) {
+    uint4 kv[4], vv[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sV[(c + j) * VS + key] = vh[j];
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 * ATT_WARPS;
+      const int key = i / CH, c = (i - key * CH) * 8;
+      kv[u] = make_uint4(0, 0, 0, 0); vv[u] = make_uint4(0, 0, 0, 0);
+      if (i < NKP * CH && key < a.Nk && c < a.hd) {
+        kv[u] = *reinterpret_cast<const uint4*>(kbase + (size_t)key * a.ldk + c);
+        vv[u] = *reinterpret_cast<const uint4*>(vbase + (size_t)key * a.ldv + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 * ATT_WARPS;
+      if (i < NKP * CH) {
+        const int key = i / CH, c = (i - key * CH) * 8;
+        *reinterpret_cast<uint4*>(sK + key * KS + c) = kv[u];
+        *reinterpret_cast<uint4*>(sV + key * KS + c) = vv[u];
+      }
+    }
   }
-  __syncthreads();
 
-  // ---- Q fragments for this warp's 16 rows
-  const int row0 = qb * ATT_QBLK + warp * 16;
+  // ---- Q fragments: rows 16*(warp&1) + {g, g+8} of this CTA's 32-row block
+  const int row0 = qb * ATT_QBLK + (warp & 1) * 16;
   const int r_lo = row0 + g, r_hi = row0 + g + 8;
   const __half* qlo = a.q + ((size_t)b * a.Nq + r_lo) * a.ldq + (size_t)h * a.hd;
   const __half* qhi = a.q + ((size_t)b * a.Nq + r_hi) * a.ldq + (size_t)h * a.hd;
@@ -183,14 +221,18 @@ attention_kernel(AttnArgs a) {
     qf[kk][2] = (r_lo < a.Nq && c1 < a.hd) ? *reinterpret_cast<const uint32_t*>(qlo + c1) : 0u;
     qf[kk][3] = (r_hi < a.Nq && c1 < a.hd) ? *reinterpret_cast<const uint32_t*>(qhi + c1) : 0u;
   }
+  __syncthreads();
 
   float o[HDP / 8][4];
 #pragma unroll
   for (int i = 0; i < HDP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
-  for (int kb = 0; kb < NKP; kb += 64) {
-    const int ntiles = min(8, (NKP - kb) >> 3);   // warp-uniform
+  // key range of this warp: first half gets the extra 16-key tile
+  const int halfk = ((NKP >> 4) + 1) / 2 * 16;
+  const int k_begin = (warp >> 1) ? halfk : 0, k_end = (warp >> 1) ? NKP : halfk;
+  for (int kb = k_begin; kb < k_end; kb += 64) {
+    const int ntiles = min(8, (k_end - kb) >> 3);   // warp-uniform, even
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -205,7 +247,6 @@ attention_kernel(AttnArgs a) {
         }
       }
     }
-    // scale, mask, block row-max
     float bm_lo = -INFINITY, bm_hi = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -222,20 +263,21 @@ attention_kernel(AttnArgs a) {
     bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
     bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1));
     bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+    // a block may be fully masked (keys >= Nk in the second half): keep the running max finite-safe
     const float mn_lo = fmaxf(m_lo, bm_lo), mn_hi = fmaxf(m_hi, bm_hi);
-    const float al_lo = exp2f(m_lo - mn_lo), al_hi = exp2f(m_hi - mn_hi);   // exp2(-inf)=0 on the first block
+    const float ref_lo = mn_lo == -INFINITY ? 0.f : mn_lo, ref_hi = mn_hi == -INFINITY ? 0.f : mn_hi;
+    const float al_lo = exp2f(m_lo - ref_lo), al_hi = exp2f(m_hi - ref_hi);
     m_lo = mn_lo; m_hi = mn_hi;
     float sum_lo = 0.f, sum_hi = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j][0] = exp2f(s[j][0] - mn_lo); s[j][1] = exp2f(s[j][1] - mn_lo);
-      s[j][2] = exp2f(s[j][2] - mn_hi); s[j][3] = exp2f(s[j][3] - mn_hi);
+      s[j][0] = exp2f(s[j][0] - ref_lo); s[j][1] = exp2f(s[j][1] - ref_lo);
+      s[j][2] = exp2f(s[j][2] - ref_hi); s[j][3] = exp2f(s[j][3] - ref_hi);
       sum_lo += s[j][0] + s[j][1]; sum_hi += s[j][2] + s[j][3];
     }
-    l_lo = l_lo * al_lo + sum_lo; l_hi = l_hi * al_hi + sum_hi;   // per-thread partial sums; quad-reduced at the end
+    l_lo = l_lo * al_lo + sum_lo; l_hi = l_hi * al_hi + sum_hi;
 #pragma unroll
     for (int i = 0; i < HDP / 8; ++i) { o[i][0] *= al_lo; o[i][1] *= al_lo; o[i][2] *= al_hi; o[i][3] *= al_hi; }
-    // O += P V
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       if (2 * p < ntiles) {
@@ -244,11 +286,12 @@ attention_kernel(AttnArgs a) {
         pa[1] = pack_half2(s[2 * p][2], s[2 * p][3]);
         pa[2] = pack_half2(s[2 * p + 1][0], s[2 * p + 1][1]);
         pa[3] = pack_half2(s[2 * p + 1][2], s[2 * p + 1][3]);
-        const __half* vr = sV + g * VS + kb + p * 16 + 2 * t;
+        // lanes 0-7 address keys +0..7, lanes 8-15 keys +8..15 (lanes >= 16 ignored by .x2)
+        const __half* vr = sV + (kb + p * 16 + (lane & 15)) * KS;
 #pragma unroll
         for (int i = 0; i < HDP / 8; ++i) {
-          uint32_t b0 = *reinterpret_cast<const uint32_t*>(vr + i * 8 * VS);
-          uint32_t b1 = *reinterpret_cast<const uint32_t*>(vr + i * 8 * VS + 8);
+          uint32_t b0, b1;
+          ldmatrix_x2_trans(b0, b1, vr + i * 8);
           mma_16816(o[i], pa, b0, b1);
         }
       }
@@ -256,15 +299,43 @@ attention_kernel(AttnArgs a) {
   }
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-  const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
-  __half* olo = a.o + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * a.hd;
-  __half* ohi = a.o + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * a.hd;
+
+  // ---- merge the two key halves (warps 2,3 -> warps 0,1) through shared memory
+  __syncthreads();                                   // everyone is done with sK / sV
+  float* mrg = reinterpret_cast<float*>(att_smem);   // [2 warps][HDP/8*4 + 4][32 lanes]
+  constexpr int MW = HDP / 8 * 4 + 4;
+  if (warp >= 2) {
+    float* dst = mrg + (size_t)(warp - 2) * MW * 32 + lane;
 #pragma unroll
-  for (int i = 0; i < HDP / 8; ++i) {
-    const int c = i * 8 + 2 * t;
-    if (c < a.hd) {
-      if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = pack_half2(o[i][0] * inv_lo, o[i][1] * inv_lo);
-      if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = pack_half2(o[i][2] * inv_hi, o[i][3] * inv_hi);
+    for (int i = 0; i < HDP / 8; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dst[(i * 4 + e) * 32] = o[i][e];
+    }
+    dst[(MW - 4) * 32] = m_lo; dst[(MW - 3) * 32] = m_hi; dst[(MW - 2) * 32] = l_lo; dst[(MW - 1) * 32] = l_hi;
+  }
+  __syncthreads();
+  if (warp >= 2) return;
+  {
+    const float* src = mrg + (size_t)warp * MW * 32 + lane;
+    const float m2_lo = src[(MW - 4) * 32], m2_hi = src[(MW - 3) * 32], l2_lo = src[(MW - 2) * 32], l2_hi = src[(MW - 1) * 32];
+    const float mm_lo = fmaxf(m_lo, m2_lo), mm_hi = fmaxf(m_hi, m2_hi);
+    const float r_lo_ = mm_lo == -INFINITY ? 0.f : mm_lo, r_hi_ = mm_hi == -INFINITY ? 0.f : mm_hi;
+    const float a1_lo = exp2f(m_lo - r_lo_), a2_lo = exp2f(m2_lo - r_lo_);
+    const float a1_hi = exp2f(m_hi - r_hi_), a2_hi = exp2f(m2_hi - r_hi_);
+    const float inv_lo = 1.f / (l_lo * a1_lo + l2_lo * a2_lo), inv_hi = 1.f / (l_hi * a1_hi + l2_hi * a2_hi);
+    __half* olo = a.o + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * a.hd;
+    __half* ohi = a.o + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * a.hd;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      const int c = i * 8 + 2 * t;
+      const float v0 = (o[i][0] * a1_lo + src[(i * 4 + 0) * 32] * a2_lo) * inv_lo;
+      const float v1 = (o[i][1] * a1_lo + src[(i * 4 + 1) * 32] * a2_lo) * inv_lo;
+      const float v2 = (o[i][2] * a1_hi + src[(i * 4 + 2) * 32] * a2_hi) * inv_hi;
+      const float v3 = (o[i][3] * a1_hi + src[(i * 4 + 3) * 32] * a2_hi) * inv_hi;
+      if (c < a.hd) {
+        if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = pack_half2(v0, v1);
+        if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = pack_half2(v2, v3);
+      }
     }
   }
 }
@@ -332,11 +403,15 @@ extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const floa
   if (!d_x || !d_gamma || !d_beta || (!d_out16 && !d_out32) || rows < 1 || D < 1) { set_error("vlfm_layernorm: bad argument"); return VLFM_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((rows + 7) / 8);
-  if (D <= 32 * 8) layernorm_kernel<8><<<grid, 256, 0, st>>>(d_x, d_gamma, d_beta, (__half*)d_out16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
-  else if (D <= 32 * 24) layernorm_kernel<24><<<grid, 256, 0, st>>>(d_x, d_gamma, d_beta, (__half*)d_out16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
-  else if (D <= 32 * 48) layernorm_kernel<48><<<grid, 256, 0, st>>>(d_x, d_gamma, d_beta, (__half*)d_out16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  cudaError_t e;
+  __half* o16 = (__half*)d_out16;
+  if ((D & 3) || (ldx & 3) || (ldo16 & 3) || (ldo32 & 3)) { set_error("vlfm_layernorm: D and strides must be multiples of 4"); return VLFM_E_UNSUPPORTED; }
+  grid = dim3((rows + 3) / 4);
+  if (D <= 128 * 2) e = launch_pdl(layernorm_kernel<2>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else if (D <= 128 * 6) e = launch_pdl(layernorm_kernel<6>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else if (D <= 128 * 12) e = launch_pdl(layernorm_kernel<12>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
   else { set_error("vlfm_layernorm: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
-  VLFM_CHECK_LAUNCH("layernorm_kernel");
+  { int rc = check_cuda(e, "layernorm_kernel"); if (rc) return rc; }
   count_launch();
   return VLFM_OK;
 }
@@ -351,17 +426,16 @@ extern "C" int vlfm_attention_f16(const void* d_q, const void* d_k, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((Nq + ATT_QBLK - 1) / ATT_QBLK, heads, B);
   if (hd <= 64) {
-    constexpr size_t sm = (size_t)(ATT_NKMAX * (64 + 8) + 64 * (ATT_NKMAX + 8)) * 2;
+    const size_t sm = (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (64 + 8) * 2 < 2 * 52 * 32 * 4 ? (size_t)2 * 52 * 32 * 4 : (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (64 + 8) * 2;
     static bool cfg = false;
-    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "attr(attention<64>)"); if (rc) return rc; cfg = true; }
-    attention_kernel<64><<<grid, 32 * ATT_WARPS, sm, st>>>(a);
+    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (64 + 8) * 2), "attr(attention<64>)"); if (rc) return rc; cfg = true; }
+    { int rc = check_cuda(launch_pdl(attention_kernel<64>, grid, dim3(32 * ATT_WARPS), sm, st, a), "attention_kernel<64>"); if (rc) return rc; }
   } else {
-    constexpr size_t sm = (size_t)(ATT_NKMAX * (96 + 8) + 96 * (ATT_NKMAX + 8)) * 2;
+    const size_t sm = (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (96 + 8) * 2 < 2 * 52 * 32 * 4 ? (size_t)2 * 52 * 32 * 4 : (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (96 + 8) * 2;
     static bool cfg = false;
-    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "attr(attention<96>)"); if (rc) return rc; cfg = true; }
-    attention_kernel<96><<<grid, 32 * ATT_WARPS, sm, st>>>(a);
+    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (96 + 8) * 2), "attr(attention<96>)"); if (rc) return rc; cfg = true; }
+    { int rc = check_cuda(launch_pdl(attention_kernel<96>, grid, dim3(32 * ATT_WARPS), sm, st, a), "attention_kernel<96>"); if (rc) return rc; }
   }
-  VLFM_CHECK_LAUNCH("attention_kernel");
   count_launch();
   return VLFM_OK;
 }
