@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -101,7 +102,7 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, STAGES <= 4 ? 2 : 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -120,7 +121,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x, m_blk = blockIdx.y;
   const bool dbg = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  if (dbg && threadIdx.x == 0) { g.dbg[0] = clock64(); unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[7] = t; }
+  const unsigned cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (g.dbg && threadIdx.x == 0 && cta_lin < 2048) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[8 + 2 * cta_lin] = t; }
+  if (dbg && threadIdx.x == 0) { g.dbg[0] = clock64(); }
   const int kb_begin = blockIdx.z * g.kb_per_split;
   const int num_k = min((g.K + BK - 1) / BK - kb_begin, g.kb_per_split);   // K-blocks of this split
   const bool split = gridDim.z > 1;
@@ -249,6 +252,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) g.dbg[6] = clock64();
+  if (g.dbg && threadIdx.x == 0 && cta_lin < 2048) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[9 + 2 * cta_lin] = t; }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -351,6 +355,16 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
     }
   }
   g.kb_per_split = (num_k + best_s - 1) / best_s;
+  // Small grids (<= one wave) use the shallow-pipeline variants (<= 100 KB smem, 2 CTAs/SM) so that, with
+  // programmatic dependent launch, the next GEMM's CTAs are already resident when this one drains.
+  static int shallow = -1;
+  if (shallow < 0) { const char* e = getenv("VLFM_GEMM_SHALLOW"); shallow = (e && e[0] == '1') ? 1 : 0; }  // measured slower on B200 (3 stages cannot cover the latency): off
+  const bool one_wave = (long)mt * ((N + best_bn - 1) / best_bn) * best_s <= 148;
+  if (shallow && one_wave) {
+    if (best_bn == 128) return launch_gemm<128, 3>(ta, d_W, ldw, g, st);
+    if (best_bn == 64) return launch_gemm<64, 4>(ta, d_W, ldw, g, st);
+    return launch_gemm<32, 4>(ta, d_W, ldw, g, st);
+  }
   if (best_bn == 128) return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
   if (best_bn == 64) return launch_gemm<64, 8>(ta, d_W, ldw, g, st);
   return launch_gemm<32, 8>(ta, d_W, ldw, g, st);
