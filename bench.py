@@ -201,9 +201,11 @@ def run_b200(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    value = world * B * K / (ms * 1e-3)
+    from vlfm_b200.utils.dist import aggregate_throughput, gather_metrics, max_over_ranks
+
+    ms_local = ms
+    ms = max_over_ranks(ms, dev)                       # slowest rank defines the job
+    value = aggregate_throughput(world, B, K, ms)
 
     # ---- e2e: public class API, host buffers, H2D/D2H inside the timed region
     vm = ValueMap(1, size=G, use_max_confidence=False, device=dev)
@@ -223,9 +225,10 @@ def run_b200(args):
         step_host(Wm + i)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); t_e2e = float(t.item())
+    t_e2e = max_over_ranks(t_e2e, dev)
     e2e = world * K / t_e2e
+    # optional NCCL all-gather of a small per-rank metrics vector (never on the step path)
+    per_rank = gather_metrics([rank, ms_local, float(eng.conf.sum().item())], dev)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): GEMM-only replay, CUDA events
@@ -248,6 +251,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 4, "api": "BLIP2ITM.cosine + ValueMap.update_map (host numpy in, pinned staging)"},
             "gpu_launches": launches_per_step * K,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "per_rank": [{"rank": int(r[0]), "ms": r[1], "conf_checksum": r[2]} for r in per_rank],
         }
         print(json.dumps(line))
     if world > 1:

@@ -168,6 +168,21 @@ int vlfm_attention_f16(const void* d_q, const void* d_k, const void* d_v, void* 
 /* ITC head (match_head="itc"): cos[b] = max_q <normalize(proj[b,q,:]), text>.  */
 int vlfm_itc_head(const float* d_proj, const float* d_text, float* d_out, int B, int Q, int D, void* stream);
 
+/* ----------------------------------------------- GroundingDINO Swin-T backbone ---- */
+/* Replaces the image branch of groundingdino's predict() up to the backbone feature maps
+ * (reference call site vlfm/vlm/grounding_dino.py:52-67).  GEMMs / LayerNorms reuse
+ * vlfm_gemm_f16 / vlfm_layernorm.
+ * vlfm_swin_patch_im2col: uint8 [B,H,W,3] -> to_tensor + ImageNet normalise (grounding_dino.py:53-54)
+ *   -> fp16 [B*ceil(H/4)*ceil(W/4), 48] rows of the 4x4/4 patch-embedding GEMM.
+ * vlfm_swin_window_attention: (shifted) 7x7-window attention, head_dim 32, with relative position
+ *   bias [169, heads] and the SW-MSA region mask; qkv [B*H*W, 3C] fp16 -> out [B*H*W, C] fp16.
+ * vlfm_swin_patch_merge: [B,H,W,C] fp32 -> [B*ceil(H/2)*ceil(W/2), 4C] fp32 (2x2 gather). */
+int vlfm_swin_patch_im2col(const uint8_t* d_img, void* d_out, int B, int H, int W, const float* h_mean3,
+                           const float* h_std3, void* stream);
+int vlfm_swin_window_attention(const void* d_qkv, const float* d_qkv_bias, const float* d_rel_bias, void* d_out, int B,
+                               int H, int W, int C, int heads, int shift, void* stream);
+int vlfm_swin_patch_merge(const float* d_x, float* d_out, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,56 @@
+"""GroundingDINO: Swin-T backbone on the hand-written kernels vs the fp32 HF oracle, and the
+predict() surface.  Tolerances stated per check (fp16 tensor-core operands, fp32 accumulate)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.gdino_oracle import GdinoOracle
+from vlfm_b200.utils.synthetic import make_rgb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair():
+    from vlfm_b200.vlm.grounding_dino import GroundingDINO
+
+    orc = GdinoOracle(0)
+    g = GroundingDINO(state_dict={k: v.clone() for k, v in orc.state_dict().items()}, seed=0)
+    return orc, g
+
+
+@pytest.mark.parametrize("hw", [(480, 640), (225, 318)])   # second: not a multiple of 4 / 7 / 2 anywhere
+def test_swin_backbone_feature_maps(pair, hw):
+    orc, g = pair
+    img = make_rgb(np.random.default_rng(hw[0]), *hw)
+    ref = orc.backbone_features(img)
+    got = g.backbone.forward(torch.from_numpy(img[None]).cuda())
+    torch.cuda.synchronize()
+    assert len(ref) == len(got) == 3
+    for r, o in zip(ref, got):
+        o = o[0].cpu()
+        assert o.shape == r.shape
+        err = (o - r).abs()
+        print("stage", tuple(r.shape), "max", float(err.max()), "mean", float(err.mean()))
+        assert float(err.mean()) <= 5e-3 and float(err.max()) <= 1e-1
+
+
+def test_predict_surface_and_outputs(pair):
+    orc, g = pair
+    img = make_rgb(np.random.default_rng(5), 480, 640)
+    ids = g.tokenizer.encode("chair . person . dog .")
+    ref_l, ref_b = orc.raw_outputs(img, ids)
+    got_l, got_b = g.raw_outputs(img, ids)
+    got_l, got_b = got_l.cpu(), got_b.cpu()
+    assert got_l.shape == ref_l.shape == (900, 256) and got_b.shape == (900, 4)
+    print("logit mean abs err", float((got_l - ref_l).abs().mean()), "box mean abs err", float((got_b - ref_b).abs().mean()))
+    assert float((got_b - ref_b).abs().mean()) <= 2e-2
+    det = g.predict(img)                       # default caption (grounding_dino.py:20)
+    assert det.boxes.shape[1] == 4 and len(det.phrases) == det.boxes.shape[0] == det.logits.shape[0]
+    assert all(p in ("chair", "person", "dog") for p in det.phrases)     # filter_by_class
+    assert (det.boxes[:, 2] >= det.boxes[:, 0]).all()                    # xyxy
+    j = det.to_json()
+    from vlfm_b200.vlm.detections import ObjectDetections
+
+    back = ObjectDetections.from_json(j, image_source=img)
+    assert back.num_detections == det.num_detections

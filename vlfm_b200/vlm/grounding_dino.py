@@ -1,0 +1,151 @@
+"""GroundingDINO behind the reference's class surface (vlfm/vlm/grounding_dino.py:23-85).
+
+The Swin-T backbone -- the dense contraction north_star names -- runs on the hand-written
+sm_100a kernels (``SwinBackboneEngine``).  The rest of the detector (BERT text encoder,
+feature enhancer, deformable encoder/decoder, heads) is not on the hand-written path yet
+(SURVEY.md section 8f rank 1): it runs as the architecture-equivalent HF
+``GroundingDinoForObjectDetection`` PyTorch modules on the same GPU, fed with our backbone
+feature maps.  Post-processing restates groundingdino.util.inference.predict.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .detections import ObjectDetections
+from .swin_engine import SwinBackboneEngine
+
+GROUNDING_DINO_CONFIG = "GroundingDINO/groundingdino/config/GroundingDINO_SwinT_OGC.py"
+GROUNDING_DINO_WEIGHTS = "data/groundingdino_swint_ogc.pth"
+CLASSES = "chair . person . dog ."  # grounding_dino.py:20
+BACKBONE_PREFIX = "model.backbone.conv_encoder.model."
+
+
+class _Features(torch.nn.Module):
+    """Stands in for the HF backbone module: returns the feature maps our engine produced."""
+
+    def __init__(self):
+        super().__init__()
+        self.maps: List[torch.Tensor] = []
+
+    def forward(self, pixel_values=None, **kw):
+        from transformers.utils.backbone_utils import BackboneOutput  # type: ignore
+
+        return BackboneOutput(feature_maps=tuple(self.maps))
+
+
+class SimpleCaptionTokenizer:
+    """SYNTHETIC stand-in for bert-base-uncased (no vocab offline): [CLS]=101, '.'=1012, [SEP]=102,
+    words -> stable ids in [2000, vocab).  decode() inverts it for the words it has seen."""
+
+    def __init__(self, vocab: int = 30522):
+        self.vocab = vocab
+        self.words: Dict[int, str] = {}
+
+    def encode(self, caption: str) -> List[int]:
+        import zlib
+
+        ids = [101]
+        for tok in caption.replace(".", " . ").split():
+            if tok == ".":
+                ids.append(1012)
+            else:
+                i = 2000 + zlib.crc32(tok.encode()) % (self.vocab - 2000)
+                self.words[i] = tok
+                ids.append(i)
+        return ids + [102]
+
+    def decode(self, ids: List[int]) -> str:
+        return " ".join("." if i == 1012 else self.words.get(i, "[UNK]") for i in ids if i not in (101, 102))
+
+
+class GroundingDINO:
+    def __init__(self, config_path: str = GROUNDING_DINO_CONFIG, weights_path: str = GROUNDING_DINO_WEIGHTS,
+                 caption: str = CLASSES, box_threshold: float = 0.35, text_threshold: float = 0.25,
+                 device: torch.device = torch.device("cuda"), state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 tokenizer: Optional[Any] = None, seed: int = 0):
+        from transformers import GroundingDinoConfig, GroundingDinoForObjectDetection
+
+        cfg = GroundingDinoConfig()
+        if state_dict is None:
+            path = os.environ.get("VLFM_GDINO_WEIGHTS", "")
+            if path:
+                state_dict = torch.load(path, map_location="cpu")
+        torch.manual_seed(seed)
+        model = GroundingDinoForObjectDetection(cfg)  # random init when no checkpoint (there is none offline)
+        if state_dict is not None:
+            model.load_state_dict(state_dict, strict=False)
+        sd = model.state_dict()
+        self.device = device
+        self.backbone = SwinBackboneEngine(sd, prefix=BACKBONE_PREFIX, embed_dim=cfg.backbone_config.embed_dim,
+                                           depths=cfg.backbone_config.depths, heads=cfg.backbone_config.num_heads,
+                                           out_stages=tuple(cfg.backbone_config.out_indices), eps=cfg.backbone_config.layer_norm_eps,
+                                           device=device)
+        self._features = _Features()
+        model.model.backbone.conv_encoder.model = self._features
+        self.model = model.to(device).eval()
+        self.caption = caption
+        self.box_threshold = box_threshold
+        self.text_threshold = text_threshold
+        self.tokenizer = tokenizer or SimpleCaptionTokenizer(cfg.text_config.vocab_size)
+        self._pin: Optional[torch.Tensor] = None
+        self._dev: Optional[torch.Tensor] = None
+
+    @torch.inference_mode()
+    def raw_outputs(self, image: np.ndarray, input_ids: List[int]):
+        """-> (sigmoid logits [900,256], boxes [900,4] cxcywh) on the device."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        if self._pin is None or self._pin.shape[1:] != image.shape:
+            self._pin = torch.empty((1,) + image.shape, dtype=torch.uint8).pin_memory()
+            self._dev = torch.empty((1,) + image.shape, dtype=torch.uint8, device=self.device)
+        self._pin[0].numpy()[...] = image
+        self._dev.copy_(self._pin, non_blocking=True)
+        self._features.maps = self.backbone.forward(self._dev)
+        h, w = image.shape[:2]
+        ids = torch.tensor([input_ids], dtype=torch.long, device=self.device)
+        dummy = torch.zeros(1, 3, h, w, device=self.device)  # only its shape is used (pixel mask); features come from our engine
+        out = self.model(pixel_values=dummy, input_ids=ids, token_type_ids=torch.zeros_like(ids), attention_mask=torch.ones_like(ids),
+                         pixel_mask=torch.ones(1, h, w, dtype=torch.long, device=self.device))
+        return out.logits[0].sigmoid(), out.pred_boxes[0]
+
+    def predict(self, image: np.ndarray, caption: Optional[str] = None) -> ObjectDetections:
+        """grounding_dino.py:38-74."""
+        caption_to_use = self.caption if caption is None else caption
+        text = caption_to_use.lower().strip()
+        if not text.endswith("."):
+            text = text + "."
+        ids = self.tokenizer.encode(text)
+        logits, boxes = self.raw_outputs(image, ids)
+        logits, boxes = logits.cpu(), boxes.cpu()
+        keep = logits.max(dim=1)[0] > self.box_threshold
+        logits, boxes = logits[keep], boxes[keep]
+        phrases = []
+        for row in logits:
+            pos = row > self.text_threshold
+            pos[0] = False
+            pos[len(ids) - 1 :] = False
+            phrases.append(self.tokenizer.decode([ids[i] for i in pos.nonzero(as_tuple=True)[0].tolist()]).replace(".", "").strip())
+        det = ObjectDetections(boxes, logits.max(dim=1)[0], phrases, image_source=image)
+        classes = caption_to_use[: -len(" .")].split(" . ")
+        det.filter_by_class(classes)
+        return det
+
+
+_SHARED: Dict[str, GroundingDINO] = {}
+
+
+class GroundingDINOClient:
+    """Same signature as the HTTP client (grounding_dino.py:77-85); in-process."""
+
+    def __init__(self, port: int = 12181, model: Optional[GroundingDINO] = None):
+        if model is None:
+            if "default" not in _SHARED:
+                _SHARED["default"] = GroundingDINO()
+            model = _SHARED["default"]
+        self.model = model
+
+    def predict(self, image_numpy: np.ndarray, caption: Optional[str] = "") -> ObjectDetections:
+        return self.model.predict(image_numpy, caption=caption if caption else None)
