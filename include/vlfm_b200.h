@@ -48,6 +48,9 @@ const char* vlfm_last_error(void);
 int vlfm_version(void);
 /* number of kernels this library has launched since load (bench `gpu_launches`). */
 unsigned long long vlfm_launch_count(void);
+/* development probe for programmatic dependent launch: each block spins pre_ns, waits for its
+ * predecessor grid, spins post_ns. */
+int vlfm_pdl_probe(int blocks, int smem_bytes, int pre_ns, int post_ns, int* d_sink, void* stream);
 
 /* ------------------------------------------------------------------ value map ---- */
 /* Replaces ValueMap.update_map (vlfm/mapping/value_map.py:100-128), i.e.

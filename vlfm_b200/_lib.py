@@ -40,6 +40,7 @@ _SIGNATURES = {
     "vlfm_last_error": (C.c_char_p, []),
     "vlfm_version": (C.c_int, []),
     "vlfm_launch_count": (C.c_ulonglong, []),
+    "vlfm_pdl_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vlfm_value_workspace_bytes": (C.c_int, [C.POINTER(ValueParams), C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_value_update": (C.c_int, [C.POINTER(ValueParams), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vlfm_value_mask_unexplored": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

@@ -334,7 +334,7 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   // the L2->SM bandwidth).  Never spill into a second wave for a handful of CTAs; split K only for the
   // fp32 residual epilogue (partials are reduced with red.add into the residual stream).
   const int mt = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
-  int best_bn = 128, best_s = 1;
+  int best_bn = 128, best_s = 1, force_shallow = 0;
   double best_t = 1e30;
   const int bns[3] = {128, 64, 32};
   for (int bi = 0; bi < 3; ++bi) {
@@ -354,13 +354,21 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
       if (t < best_t) { best_t = t; best_bn = bn; best_s = sp; }
     }
   }
+  if (const char* f = getenv("VLFM_GEMM_FORCE")) {   // development sweep: "bn:splits"
+    int fb = 0, fs = 0, fsh = 0;
+    if (sscanf(f, "%d:%d:%d", &fb, &fs, &fsh) >= 2 && (fb == 128 || fb == 64 || fb == 32) && fs >= 1) {
+      best_bn = fb;
+      best_s = (epilogue == VLFM_EPI_BIAS_RESID_F32) ? (fs > num_k ? num_k : fs) : 1;
+      force_shallow = fsh;
+    }
+  }
   g.kb_per_split = (num_k + best_s - 1) / best_s;
   // Small grids (<= one wave) use the shallow-pipeline variants (<= 100 KB smem, 2 CTAs/SM) so that, with
   // programmatic dependent launch, the next GEMM's CTAs are already resident when this one drains.
   static int shallow = -1;
   if (shallow < 0) { const char* e = getenv("VLFM_GEMM_SHALLOW"); shallow = (e && e[0] == '1') ? 1 : 0; }  // measured slower on B200 (3 stages cannot cover the latency): off
   const bool one_wave = (long)mt * ((N + best_bn - 1) / best_bn) * best_s <= 148;
-  if (shallow && one_wave) {
+  if ((shallow && one_wave) || force_shallow) {
     if (best_bn == 128) return launch_gemm<128, 3>(ta, d_W, ldw, g, st);
     if (best_bn == 64) return launch_gemm<64, 4>(ta, d_W, ldw, g, st);
     return launch_gemm<32, 4>(ta, d_W, ldw, g, st);

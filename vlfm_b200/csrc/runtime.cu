@@ -29,3 +29,25 @@ extern "C" int vlfm_version(void) { return 100; }
 extern "C" unsigned long long vlfm_launch_count(void) {
   return vlfm::g_launches.load(std::memory_order_relaxed);
 }
+
+// ---- development probe: does programmatic dependent launch overlap kernels (in streams / in graphs)?
+namespace vlfm {
+__global__ void pdl_probe_kernel(int pre_ns, int post_ns, int* sink) {
+  pdl_trigger();
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < (unsigned long long)pre_ns);
+  pdl_wait();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < (unsigned long long)post_ns);
+  if (sink && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(sink, 1);
+}
+}  // namespace vlfm
+extern "C" int vlfm_pdl_probe(int blocks, int smem_bytes, int pre_ns, int post_ns, int* d_sink, void* stream) {
+  static int cfg = 0;
+  if (smem_bytes > 48 * 1024 && smem_bytes > cfg) {
+    int rc = vlfm::check_cuda(cudaFuncSetAttribute(vlfm::pdl_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), "attr(pdl_probe)");
+    if (rc) return rc; cfg = smem_bytes;
+  }
+  return vlfm::check_cuda(vlfm::launch_pdl(vlfm::pdl_probe_kernel, dim3(blocks), dim3(128), (size_t)smem_bytes, (cudaStream_t)stream, pre_ns, post_ns, d_sink), "pdl_probe_kernel");
+}

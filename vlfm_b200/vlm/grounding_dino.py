@@ -32,7 +32,7 @@ class _Features(torch.nn.Module):
         self.maps: List[torch.Tensor] = []
 
     def forward(self, pixel_values=None, **kw):
-        from transformers.utils.backbone_utils import BackboneOutput  # type: ignore
+        from transformers.modeling_outputs import BackboneOutput
 
         return BackboneOutput(feature_maps=tuple(self.maps))
 
