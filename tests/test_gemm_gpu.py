@@ -15,10 +15,10 @@ def run_gemm(a, w, bias, epi, resid=None):
 
 @pytest.mark.parametrize("M,N,K", [(257, 4224, 1408), (257, 1408, 6144), (128, 128, 64), (1, 256, 768),
                                    (300, 1408, 592), (32, 768, 768), (1000, 6144, 1408), (257, 9216, 1408),
-                                   (77, 264, 72)])
+                                   (77, 264, 72), (8224, 4224, 1408), (2100, 2312, 520)])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_gemm_matches_torch(M, N, K, epi):
-    if epi in (1, 2) and (M, N, K) not in [(257, 4224, 1408), (300, 1408, 592), (77, 264, 72), (32, 768, 768)]:
+    if epi in (1, 2) and (M, N, K) not in [(257, 4224, 1408), (300, 1408, 592), (77, 264, 72), (32, 768, 768), (8224, 4224, 1408), (2100, 2312, 520)]:
         pytest.skip("epilogue variants checked on a subset of shapes")
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + epi)
     a = (torch.randn(M, K, generator=g) * 0.5).half().cuda()

@@ -101,6 +101,75 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
+// Epilogue of one 128-row accumulator slab: TMEM -> registers (32 lanes x 32 columns per tcgen05.ld),
+// fused bias / GELU / residual, vectorised global stores.  `q` = TMEM lane quarter of this warp.
+template <int BN>
+__device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row, int n_blk, const GemmArgs& g, bool split) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+    const int n0 = n_blk * BN + c * 32;
+    if (row >= g.M || n0 >= g.N) continue;
+    float v[32];
+    const bool fullw = (n0 + 32 <= g.N);
+    if (g.bias && blockIdx.z == 0 && fullw) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
+        v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float b = (g.bias && blockIdx.z == 0 && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
+        v[j] = __uint_as_float(r[j]) + b;
+      }
+    }
+    if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16) {
+      if (g.epi == VLFM_EPI_BIAS_GELU_F16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      }
+      __half* o = reinterpret_cast<__half*>(g.out) + (size_t)row * g.ldo + n0;
+      if (fullw) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+          __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(o + j) = pk;
+        }
+      } else {
+        for (int j = 0; j < 32 && n0 + j < g.N; ++j) o[j] = __float2half_rn(v[j]);
+      }
+    } else {
+      float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
+      const bool add = (g.epi == VLFM_EPI_BIAS_RESID_F32);
+      if (fullw) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (split) { red_add_f32x4(o + j, t.x, t.y, t.z, t.w); continue; }
+          if (add) {
+            float4 old = *reinterpret_cast<const float4*>(o + j);
+            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+          }
+          *reinterpret_cast<float4*>(o + j) = t;
+        }
+      } else {
+        for (int j = 0; j < 32 && n0 + j < g.N; ++j) {
+          if (split) atomicAdd(o + j, v[j]);
+          else o[j] = add ? o[j] + v[j] : v[j];
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, STAGES <= 4 ? 2 : 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
@@ -185,69 +254,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     mbar_wait(accbar, 0);
     if (dbg && threadIdx.x == 64) g.dbg[5] = clock64();
     tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      const int n0 = n_blk * BN + c * 32;
-      if (row >= g.M || n0 >= g.N) continue;
-      float v[32];
-      const bool fullw = (n0 + 32 <= g.N);
-      if (g.bias && blockIdx.z == 0 && fullw) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
-          v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float b = (g.bias && blockIdx.z == 0 && n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
-          v[j] = __uint_as_float(r[j]) + b;
-        }
-      }
-      if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16) {
-        if (g.epi == VLFM_EPI_BIAS_GELU_F16) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        __half* o = reinterpret_cast<__half*>(g.out) + (size_t)row * g.ldo + n0;
-        if (fullw) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(o + j) = pk;
-          }
-        } else {
-          for (int j = 0; j < 32 && n0 + j < g.N; ++j) o[j] = __float2half_rn(v[j]);
-        }
-      } else {
-        float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
-        const bool add = (g.epi == VLFM_EPI_BIAS_RESID_F32);
-        if (fullw) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (split) { red_add_f32x4(o + j, t.x, t.y, t.z, t.w); continue; }
-            if (add) {
-              float4 old = *reinterpret_cast<const float4*>(o + j);
-              t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
-            }
-            *reinterpret_cast<float4*>(o + j) = t;
-          }
-        } else {
-          for (int j = 0; j < 32 && n0 + j < g.N; ++j) {
-            if (split) atomicAdd(o + j, v[j]);
-            else o[j] = add ? o[j] + v[j] : v[j];
-          }
-        }
-      }
-    }
+    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split);
   }
   tc_fence_before();
   __syncthreads();
@@ -255,6 +262,125 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (g.dbg && threadIdx.x == 0 && cta_lin < 2048) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[9 + 2 * cta_lin] = t; }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ================================================================================================
+// 2-CTA variant (cta_group::2): a thread-block cluster of two CTAs on one TPC computes a 256 x BN
+// output tile with UMMA M=256.  Each CTA stages its own 128 rows of A and HALF of the B tile
+// (BN/2 rows); the tensor core reads both halves, so every SM ingests (128 + BN/2) x 128 B per
+// K-block for 128 x BN outputs -- half the operand bytes per FLOP of the 1-CTA kernel, which is
+// SM-ingest bound (~60 B/clk/SM measured).  Leader CTA (cluster rank 0) issues the MMAs; both
+// CTAs' TMA loads complete on the leader's full barrier; tcgen05.commit multicasts stage-release
+// and accumulator-ready to both CTAs; each CTA drains its own 128 TMEM lanes.
+// ================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t leader_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, BH_BYTES = (BN / 2) * BK * 2;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * BH_BYTES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accbar = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_blk = blockIdx.x, n_blk = blockIdx.y;     // this CTA's own 128-row slab; the pair is (2p, 2p+1)
+  const int kb_begin = blockIdx.z * g.kb_per_split;
+  const int num_k = min((g.K + BK - 1) / BK - kb_begin, g.kb_per_split);
+  const bool split = gridDim.z > 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }   // full: leader expect_tx + peer arrive
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();        // both CTAs' barriers are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t lead_full = (full0 + 8 * s) & PEER_MASK;
+        if (leader) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + BH_BYTES));
+        else mbar_arrive_leader(lead_full);
+        tma_load_2d_2sm(smem_u32(sA + s * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, lead_full);
+        tma_load_2d_2sm(smem_u32(sB + s * BH_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN + (int)rank * (BN / 2), lead_full);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * BH_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          tc_mma_f16_2sm(tmem_base, umma_desc_k128(a0 + k * 32), umma_desc_k128(b0 + k * 32), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+        tc_commit_2sm(empty0 + 8 * s);     // frees stage s in BOTH CTAs
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      tc_commit_2sm(accbar);               // accumulator ready in BOTH CTAs
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m_blk * BM + q * 32 + lane;
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split);
+  }
+  tc_fence_before();
+  cluster_sync_all();        // the peer may still be reading our smem / signalling our barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -312,6 +438,28 @@ static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const Gemm
   return VLFM_OK;
 }
 
+
+template <int BN, int STAGES>
+static int launch_gemm_2cta(const CUtensorMap& ta, const void* W, int ldw, const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap tb;
+  int rc = make_map(&tb, W, g.N, g.K, ldw, BN / 2);
+  if (rc) return rc;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 2) * 8 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_f16_tcgen05_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gemm 2cta)");
+    if (rc) return rc;
+    configured = true;
+  }
+  const int num_k = (g.K + BK - 1) / BK;
+  const int pairs = (g.M + 2 * BM - 1) / (2 * BM);
+  dim3 grid(2 * pairs, (g.N + BN - 1) / BN, (num_k + g.kb_per_split - 1) / g.kb_per_split);
+  rc = check_cuda(launch_pdl(gemm_f16_tcgen05_2cta_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), smem, st, ta, tb, g), "gemm_f16_tcgen05_2cta_kernel");
+  if (rc) return rc;
+  count_launch();
+  return VLFM_OK;
+}
+
 }  // namespace vlfm
 
 using namespace vlfm;
@@ -334,6 +482,16 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   // the L2->SM bandwidth).  Never spill into a second wave for a handful of CTAs; split K only for the
   // fp32 residual epilogue (partials are reduced with red.add into the residual stream).
   const int mt = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
+  {
+    // Large problems (>= ~2 waves of 128x128 tiles): CTA pairs, 256 x 256 tiles, half the operand bytes per FLOP.
+    static int two = -1;
+    if (two < 0) { const char* e = getenv("VLFM_GEMM_2CTA"); two = (e && e[0] == '0') ? 0 : 1; }
+    const long tiles128 = (long)mt * ((N + 127) / 128);
+    if (two && tiles128 >= 296 && N >= 256) {
+      g.kb_per_split = num_k;
+      return launch_gemm_2cta<256, 6>(ta, d_W, ldw, g, st);
+    }
+  }
   int best_bn = 128, best_s = 1, force_shallow = 0;
   double best_t = 1e30;
   const int bns[3] = {128, 64, 32};

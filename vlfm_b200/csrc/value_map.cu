@@ -16,10 +16,10 @@
 //         bitmap in shared memory: 8-connected outline (closed-form OpenCV
 //         LineIterator) + even-odd 16.16 scanline interior (XOR toggles + per-row
 //         prefix XOR),
-//       - derives cv2.warpAffine's fixed-point coordinate tables for the rotation by
-//         -yaw (img_utils.py:23-26; AB_BITS=10, INTER_BITS=5) and the camera cell
-//         (:309-313),
-//     and publishes {camera cell, tables, kill bitmap} ("geometry blob") to HBM.
+//     and publishes the kill bitmap; block (0,0) of each environment, concurrently with the
+//     streaming pass, derives cv2.warpAffine's fixed-point coordinate tables for the rotation
+//     by -yaw (img_utils.py:23-26; AB_BITS=10, INTER_BITS=5) and the camera cell (:309-313).
+//     {camera cell, tables, kill bitmap} = the "geometry blob" K2 consumes.
 //  K2 value_cone_fuse_kernel    grid (tiles, B)
 //     for every cell of the R x R window around the camera cell: inverse-map through
 //     the fixed-point rotation, 4-tap bilinear sample of (template AND NOT kill),
@@ -170,6 +170,52 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
     }
   }
 
+  // ---- block (0,0) of each environment: pose-only geometry (independent of the depth image), overlapped
+  // with the other blocks' streaming pass: camera cell (:309-313) and cv2.warpAffine's fixed-point tables
+  // for the rotation by -yaw (img_utils.py:23-26).
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    __shared__ double s_mi[6];
+    const int R = p.R;
+    if (tid == 0) {
+      const double* T = tf + (size_t)b * 16;
+      // extract_yaw (geometry_utils.py:145-159), rotate_image(curr, -yaw) (value_map.py:306)
+      double yaw = atan2(T[4], T[0]);
+      double deg = (-yaw) * 57.295779513082323;           // np.degrees
+      double ang = deg * 0.017453292519943295;            // cv: angle *= CV_PI/180
+      double a = cos(ang), bb = sin(ang);
+      double c = (double)(R / 2);
+      // cv2.getRotationMatrix2D, then cv2.warpAffine's in-place inversion (no FMA)
+      double m00 = a, m01 = bb, m02 = __dsub_rn(__dmul_rn(__dsub_rn(1.0, a), c), __dmul_rn(bb, c));
+      double m10 = -bb, m11 = a, m12 = __dadd_rn(__dmul_rn(bb, c), __dmul_rn(__dsub_rn(1.0, a), c));
+      double det = __dsub_rn(__dmul_rn(m00, m11), __dmul_rn(m01, m10));
+      det = det != 0.0 ? __ddiv_rn(1.0, det) : 0.0;
+      double i00 = __dmul_rn(m11, det), i11 = __dmul_rn(m00, det);
+      double i01 = __dmul_rn(m01, -det), i10 = __dmul_rn(m10, -det);
+      double b1 = __dsub_rn(__dmul_rn(-i00, m02), __dmul_rn(i01, m12));
+      double b2 = __dsub_rn(__dmul_rn(-i10, m02), __dmul_rn(i11, m12));
+      s_mi[0] = i00; s_mi[1] = i01; s_mi[2] = b1; s_mi[3] = i10; s_mi[4] = i11; s_mi[5] = b2;
+      // camera cell (value_map.py:309-313): int() truncation, not rint
+      double cx = __ddiv_rn(T[3], T[15]), cy = __ddiv_rn(T[7], T[15]);
+      int px = (int)__dmul_rn(cx, (double)p.ppm) + p.G / 2;
+      int py = (int)__dmul_rn(-cy, (double)p.ppm) + p.G / 2;
+      int valid = (px >= 0 && px < p.G && py >= 0 && py < p.G);
+      if (!valid) atomicOr(&status[b], VLFM_ST_CAMERA_OFF_GRID);
+      wsb[p.offHeader + 0] = (uint32_t)px;
+      wsb[p.offHeader + 1] = (uint32_t)py;
+      wsb[p.offHeader + 2] = (uint32_t)valid;
+    }
+    __syncthreads();
+    int* tab = reinterpret_cast<int*>(wsb + p.offTables);
+    for (int i = tid; i < R; i += K1_THREADS) {
+      double di = (double)i;
+      // X0 = saturate_cast<int>((M[1]*y + M[2])*AB_SCALE) + round_delta; adelta = saturate_cast<int>(M[0]*x*AB_SCALE)
+      tab[0 * R + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[1], di), s_mi[2]), 1024.0)) + 16;
+      tab[1 * R + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[4], di), s_mi[5]), 1024.0)) + 16;
+      tab[2 * R + i] = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[0], di), 1024.0));
+      tab[3 * R + i] = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[3], di), 1024.0));
+    }
+  }
+
   // ---- last block of this environment?
   __shared__ int s_last;
   __threadfence();
@@ -189,37 +235,12 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
   uint32_t* tog = smem + 2 * ((E + 1) & ~1);                   // [R*WPR]
   uint32_t* orb = tog + R * WPR;                               // [R*WPR]
   int* longList = reinterpret_cast<int*>(orb + R * WPR);       // [E]
-  __shared__ double s_mi[6];
-  __shared__ int s_nlong, s_px, s_py, s_valid;
+  __shared__ int s_nlong;
   __syncthreads();  // phase-1 smem no longer read
 
   for (int i = tid; i < R * WPR; i += K1_THREADS) { tog[i] = 0; orb[i] = 0; }
   if (tid == 0) {
     s_nlong = 0;
-    const double* T = tf + (size_t)b * 16;
-    // extract_yaw (geometry_utils.py:145-159), rotate_image(curr, -yaw) (value_map.py:306)
-    double yaw = atan2(T[4], T[0]);
-    double deg = (-yaw) * 57.295779513082323;           // np.degrees
-    double ang = deg * 0.017453292519943295;            // cv: angle *= CV_PI/180
-    double a = cos(ang), bb = sin(ang);
-    double c = (double)(R / 2);
-    // cv2.getRotationMatrix2D, then cv2.warpAffine's in-place inversion (no FMA)
-    double m00 = a, m01 = bb, m02 = __dsub_rn(__dmul_rn(__dsub_rn(1.0, a), c), __dmul_rn(bb, c));
-    double m10 = -bb, m11 = a, m12 = __dadd_rn(__dmul_rn(bb, c), __dmul_rn(__dsub_rn(1.0, a), c));
-    double det = __dsub_rn(__dmul_rn(m00, m11), __dmul_rn(m01, m10));
-    det = det != 0.0 ? __ddiv_rn(1.0, det) : 0.0;
-    double i00 = __dmul_rn(m11, det), i11 = __dmul_rn(m00, det);
-    double i01 = __dmul_rn(m01, -det), i10 = __dmul_rn(m10, -det);
-    double b1 = __dsub_rn(__dmul_rn(-i00, m02), __dmul_rn(i01, m12));
-    double b2 = __dsub_rn(__dmul_rn(-i10, m02), __dmul_rn(i11, m12));
-    s_mi[0] = i00; s_mi[1] = i01; s_mi[2] = b1; s_mi[3] = i10; s_mi[4] = i11; s_mi[5] = b2;
-    // camera cell (value_map.py:309-313): int() truncation, not rint
-    double cx = __ddiv_rn(T[3], T[15]), cy = __ddiv_rn(T[7], T[15]);
-    int px = (int)__dmul_rn(cx, (double)p.ppm) + p.G / 2;
-    int py = (int)__dmul_rn(-cy, (double)p.ppm) + p.G / 2;
-    s_px = px; s_py = py;
-    s_valid = (px >= 0 && px < p.G && py >= 0 && py < p.G);
-    if (!s_valid) atomicOr(&status[b], VLFM_ST_CAMERA_OFF_GRID);
     verts[0] = make_int2(0, R - 1);          // start = [[0, last_col]]  (value_map.py:255)
     verts[E - 1] = make_int2(R - 1, R - 1);  // end   = [[last_row, last_col]]
   }
@@ -245,7 +266,15 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
       longList[atomicAdd(&s_nlong, 1)] = e;
       continue;
     }
-    for (int k = 0; k <= lw.major; ++k) { int x, y; lw.pixel(k, x, y); plot_or(orb, WPR, R, x, y); }
+    {  // OpenCV LineIterator, incremental form (no divisions): err<0 steps the minor axis
+      int x = lw.x0, y = lw.y0, err = lw.major - 2 * lw.minor;
+      for (int k = 0; k <= lw.major; ++k) {
+        plot_or(orb, WPR, R, x, y);
+        const bool m = err < 0;
+        err += -2 * lw.minor + (m ? 2 * lw.major : 0);
+        if (lw.ymajor) { y += lw.sy; x += m ? 1 : 0; } else { x += 1; y += m ? lw.sy : 0; }
+      }
+    }
     if (A.y != B.y) {
       int xa = A.x, ya = A.y, xb = B.x, yb = B.y;
       if (ya > yb) { int t = xa; xa = xb; xb = t; t = ya; ya = yb; yb = t; }
@@ -272,21 +301,7 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
   }
   __syncthreads();
 
-  // publish: header, warpAffine tables, kill bitmap
-  if (tid == 0) {
-    wsb[p.offHeader + 0] = (uint32_t)s_px;
-    wsb[p.offHeader + 1] = (uint32_t)s_py;
-    wsb[p.offHeader + 2] = (uint32_t)s_valid;
-  }
-  int* tab = reinterpret_cast<int*>(wsb + p.offTables);
-  for (int i = tid; i < R; i += K1_THREADS) {
-    double di = (double)i;
-    // X0 = saturate_cast<int>((M[1]*y + M[2])*AB_SCALE) + round_delta; adelta = saturate_cast<int>(M[0]*x*AB_SCALE)
-    tab[0 * R + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[1], di), s_mi[2]), 1024.0)) + 16;
-    tab[1 * R + i] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[4], di), s_mi[5]), 1024.0)) + 16;
-    tab[2 * R + i] = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[0], di), 1024.0));
-    tab[3 * R + i] = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[3], di), 1024.0));
-  }
+  // publish the kill bitmap
   uint32_t* kill = wsb + p.offKill;
   for (int r = tid; r < R; r += K1_THREADS) {
     uint32_t carry = 0;
