@@ -154,7 +154,6 @@ struct AttnArgs {
 };
 
 constexpr int ATT_WARPS = 4;
-constexpr int ATT_QBLK = 32;               // query rows per CTA: 2 row groups x 2 key halves
 constexpr int ATT_NKMAX = 272;             // keys padded to a multiple of 16
 
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const __half* p) {
@@ -167,9 +166,14 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 // 16*(w&1).. and the key half (w>>1); the two halves are merged flash-style through shared memory.
 // S = Q K^T and O = P V run on mma.sync m16n8k16 (fp16 in, fp32 accumulate); V fragments come from
 // ldmatrix.trans.
-template <int HDP>
+// KH = 2: 32 query rows per CTA, each row group's keys split over two warps (small batches: more CTAs,
+// shorter critical path).  KH = 1: 64 query rows per CTA, every warp sees all keys (large batches: the K/V
+// staging is amortised over twice the queries, no merge).
+template <int HDP, int KH>
 __global__ void __launch_bounds__(32 * ATT_WARPS)
 attention_kernel(AttnArgs a) {
+  constexpr int RG = ATT_WARPS / KH;     // row groups of 16 queries
+  constexpr int ATT_QBLK = 16 * RG;
   constexpr int KS = HDP + 8;            // row stride (halves) of sK / sV
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* sK = reinterpret_cast<__half*>(att_smem);            // [NKP][KS]
@@ -208,7 +212,7 @@ attention_kernel(AttnArgs a) {
   }
 
   // ---- Q fragments: rows 16*(warp&1) + {g, g+8} of this CTA's 32-row block
-  const int row0 = qb * ATT_QBLK + (warp & 1) * 16;
+  const int row0 = qb * ATT_QBLK + (warp % RG) * 16;
   const int r_lo = row0 + g, r_hi = row0 + g + 8;
   const __half* qlo = a.q + ((size_t)b * a.Nq + r_lo) * a.ldq + (size_t)h * a.hd;
   const __half* qhi = a.q + ((size_t)b * a.Nq + r_hi) * a.ldq + (size_t)h * a.hd;
@@ -229,8 +233,8 @@ attention_kernel(AttnArgs a) {
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
   // key range of this warp: first half gets the extra 16-key tile
-  const int halfk = ((NKP >> 4) + 1) / 2 * 16;
-  const int k_begin = (warp >> 1) ? halfk : 0, k_end = (warp >> 1) ? NKP : halfk;
+  const int halfk = KH == 2 ? ((NKP >> 4) + 1) / 2 * 16 : NKP;
+  const int k_begin = (warp / RG) ? halfk : 0, k_end = (warp / RG) ? NKP : halfk;
   for (int kb = k_begin; kb < k_end; kb += 64) {
     const int ntiles = min(8, (k_end - kb) >> 3);   // warp-uniform, even
     float s[8][4];
@@ -300,6 +304,20 @@ attention_kernel(AttnArgs a) {
   l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
 
+  if (KH == 1) {   // every warp already holds complete rows
+    const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+    __half* olo = a.o + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * a.hd;
+    __half* ohi = a.o + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * a.hd;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      const int c = i * 8 + 2 * t;
+      if (c < a.hd) {
+        if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = pack_half2(o[i][0] * inv_lo, o[i][1] * inv_lo);
+        if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = pack_half2(o[i][2] * inv_hi, o[i][3] * inv_hi);
+      }
+    }
+    return;
+  }
   // ---- merge the two key halves (warps 2,3 -> warps 0,1) through shared memory
   __syncthreads();                                   // everyone is done with sK / sV
   float* mrg = reinterpret_cast<float*>(att_smem);   // [2 warps][HDP/8*4 + 4][32 lanes]
@@ -424,18 +442,27 @@ extern "C" int vlfm_attention_f16(const void* d_q, const void* d_k, const void* 
   AttnArgs a{(const __half*)d_q, (const __half*)d_k, (const __half*)d_v, (__half*)d_o, ldq, ldk, ldv, ldo, Nq, Nk, hd, heads,
              scale * 1.4426950408889634f};
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((Nq + ATT_QBLK - 1) / ATT_QBLK, heads, B);
-  if (hd <= 64) {
-    const size_t sm = (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (64 + 8) * 2 < 2 * 52 * 32 * 4 ? (size_t)2 * 52 * 32 * 4 : (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (64 + 8) * 2;
-    static bool cfg = false;
-    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (64 + 8) * 2), "attr(attention<64>)"); if (rc) return rc; cfg = true; }
-    { int rc = check_cuda(launch_pdl(attention_kernel<64>, grid, dim3(32 * ATT_WARPS), sm, st, a), "attention_kernel<64>"); if (rc) return rc; }
-  } else {
-    const size_t sm = (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (96 + 8) * 2 < 2 * 52 * 32 * 4 ? (size_t)2 * 52 * 32 * 4 : (size_t)2 * (((size_t)Nk + 15) & ~(size_t)15) * (96 + 8) * 2;
-    static bool cfg = false;
-    if (!cfg) { int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (96 + 8) * 2), "attr(attention<96>)"); if (rc) return rc; cfg = true; }
-    { int rc = check_cuda(launch_pdl(attention_kernel<96>, grid, dim3(32 * ATT_WARPS), sm, st, a), "attention_kernel<96>"); if (rc) return rc; }
+  // few (batch, head, block) work items -> 32-row blocks with split keys; many -> 64-row blocks
+  const bool big = (long)B * heads * ((Nq + 31) / 32) > 2 * 296;
+  const int qblk = big ? 64 : 32;
+  dim3 grid((Nq + qblk - 1) / qblk, heads, B);
+  const size_t nkp = ((size_t)Nk + 15) & ~(size_t)15;
+  static bool cfg = false;
+  if (!cfg) {
+    int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (64 + 8) * 2), "attr(attention)");
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (64 + 8) * 2), "attr(attention)");
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (96 + 8) * 2), "attr(attention)");
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (96 + 8) * 2), "attr(attention)");
+    if (rc) return rc;
+    cfg = true;
   }
+  const int hdp = hd <= 64 ? 64 : 96;
+  size_t sm = 2 * nkp * (hdp + 8) * 2;
+  if (sm < 2 * 52 * 32 * 4) sm = 2 * 52 * 32 * 4;   // merge buffer of the split-key variant
+  cudaError_t e;
+  if (hdp == 64) e = big ? launch_pdl(attention_kernel<64, 1>, grid, dim3(32 * ATT_WARPS), sm, st, a) : launch_pdl(attention_kernel<64, 2>, grid, dim3(32 * ATT_WARPS), sm, st, a);
+  else e = big ? launch_pdl(attention_kernel<96, 1>, grid, dim3(32 * ATT_WARPS), sm, st, a) : launch_pdl(attention_kernel<96, 2>, grid, dim3(32 * ATT_WARPS), sm, st, a);
+  { int rc = check_cuda(e, "attention_kernel"); if (rc) return rc; }
   count_launch();
   return VLFM_OK;
 }
