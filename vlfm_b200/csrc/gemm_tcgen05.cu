@@ -384,6 +384,117 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   }
 }
 
+// ================================================================================================
+// Persistent 2-CTA variant: one cluster (CTA pair) per TPC loops over 256 x 256 output tiles
+// (static round-robin, M fastest so concurrently processed tiles share weight tiles in L2).
+// TMEM holds TWO 256-column accumulators (all 512 columns): the epilogue of tile i (tcgen05.ld,
+// bias/GELU/residual, stores) overlaps the TMA + MMA main loop of tile i+1.  Pipelines:
+//   smem ring   full[s]  (leader, 2 arrivals + tx)   / empty[s]  (per CTA, multicast commit)
+//   accumulators tfull[a] (per CTA, multicast commit) / tempty[a] (leader, 8 epilogue-warp arrivals)
+// ================================================================================================
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_tcgen05_2cta_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+  constexpr uint32_t A_BYTES = BM * BK * 2, BH_BYTES = (BN / 2) * BK * 2;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * BH_BYTES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_k = (g.K + BK - 1) / BK;
+  const int pairsM = (g.M + 2 * BM - 1) / (2 * BM), tilesN = (g.N + BN - 1) / BN;
+  const int total = pairsM * tilesN;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = cluster_id; tile < total; tile += num_clusters) {
+        const int m_blk = 2 * (tile % pairsM) + (int)rank, n_blk = tile / pairsM;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const uint32_t lead_full = (full0 + 8 * s) & PEER_MASK;
+          if (leader) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + BH_BYTES));
+          else mbar_arrive_leader(lead_full);
+          tma_load_2d_2sm(smem_u32(sA + s * A_BYTES), &tmA, kb * BK, m_blk * BM, lead_full);
+          tma_load_2d_2sm(smem_u32(sB + s * BH_BYTES), &tmB, kb * BK, n_blk * BN + (int)rank * (BN / 2), lead_full);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < total; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tempty0 + 8 * acc, ((it >> 1) & 1) ^ 1);     // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + s * A_BYTES), b0 = smem_u32(sB + s * BH_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_f16_2sm(d_tmem, umma_desc_k128(a0 + k * 32), umma_desc_k128(b0 + k * 32), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_2sm(empty0 + 8 * s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit_2sm(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = cluster_id; tile < total; tile += num_clusters, ++it) {
+      const int acc = it & 1;
+      const int m_blk = 2 * (tile % pairsM) + (int)rank, n_blk = tile / pairsM;
+      const int row = m_blk * BM + q * 32 + lane;
+      mbar_wait(tfull0 + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      epilogue_slab<BN>(tmem_base + (uint32_t)(acc * BN), q, row, n_blk, g, false);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader((tempty0 + 8 * acc) & PEER_MASK);   // this warp no longer reads accumulator `acc`
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side ------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -460,6 +571,32 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const void* W, int ldw, const
   return VLFM_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_gemm_2cta_persistent(const CUtensorMap& ta, const void* W, int ldw, const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap tb;
+  int rc = make_map(&tb, W, g.N, g.K, ldw, BN / 2);
+  if (rc) return rc;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 6) * 8 + 1024;
+  static bool configured = false;
+  static int clusters_max = 74;
+  if (!configured) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_f16_tcgen05_2cta_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gemm 2cta persistent)");
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    clusters_max = sms / 2;
+    configured = true;
+  }
+  const int pairs = (g.M + 2 * BM - 1) / (2 * BM), tiles = pairs * ((g.N + BN - 1) / BN);
+  const int clusters = tiles < clusters_max ? tiles : clusters_max;
+  rc = check_cuda(launch_pdl(gemm_f16_tcgen05_2cta_persistent_kernel<BN, STAGES>, dim3(2 * clusters), dim3(GEMM_THREADS), smem, st, ta, tb, g),
+                  "gemm_f16_tcgen05_2cta_persistent_kernel");
+  if (rc) return rc;
+  count_launch();
+  return VLFM_OK;
+}
+
 }  // namespace vlfm
 
 using namespace vlfm;
@@ -489,6 +626,9 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
     const long tiles128 = (long)mt * ((N + 127) / 128);
     if (two && tiles128 >= 296 && N >= 256) {
       g.kb_per_split = num_k;
+      static int persist = -1;
+      if (persist < 0) { const char* e = getenv("VLFM_GEMM_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+      if (persist) return launch_gemm_2cta_persistent<256, 6>(ta, d_W, ldw, g, st);
       return launch_gemm_2cta<256, 6>(ta, d_W, ldw, g, st);
     }
   }
