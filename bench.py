@@ -294,8 +294,16 @@ def gemm_roofline(engine, B, dims):
     ms = e0.elapsed_time(e1) / reps
     ach = flops / (ms * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-    return {"kernel": "gemm_f16_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak, "traffic": None, "peak_source": f"{src} (sustained dense bf16)",
+    traffic = None
+    if B == 1:  # dram__bytes_read+write per launch from the committed ncu capture of this same workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_b1.json")) as fh:
+                traffic = json.load(fh)["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
+    return {"kernel": "gemm_f16_tcgen05_kernel (1-CTA 128xBN tiles at batch 1; 2-CTA persistent 256x256 tiles for large M)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum+dram__bytes_write.sum, profiles/r01_gemm_traffic_b1.json)",
+            "algorithmic_bytes_per_launch": sum(2.0 * w.numel() + 2.0 * a.numel() for a, w, *_ in calls) / len(calls), "peak_source": f"{src} (sustained dense bf16)",
             "launches_per_step": len(calls), "flops_per_launch_avg": flops / len(calls),
             "us_per_launch_avg": ms * 1e3 / len(calls), "gemm_ms_per_step": ms}
 

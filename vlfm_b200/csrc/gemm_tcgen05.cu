@@ -5,14 +5,15 @@
 // Replaces the nn.Linear layers of the BLIP-2 ViT-g / Q-Former forward that
 // vlfm/vlm/blip2itm.py:52 runs through lavis (fp16 autocast in the reference).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the A (128x64) and W
 //               (BNx64) K-slices into a STAGES-deep 128B-swizzled smem ring,
 //               mbarrier complete_tx signalling.
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::f16,
 //               M=128, N=BN, K=16, fp32 accumulators in TMEM); tcgen05.commit
 //               releases smem stages and finally signals the epilogue.
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), fused
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, interleaved column chunks):
+//               tcgen05.ld (32 lanes x 32 columns per instruction), fused
 //               bias / GELU(erf) / fp32-residual-add, vectorised global stores.
 // M / N / K tails are handled by TMA out-of-bounds zero fill + store guards.
 #include <cuda.h>
@@ -26,7 +27,7 @@ namespace vlfm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 bytes = one swizzle atom row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -104,9 +105,11 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // Epilogue of one 128-row accumulator slab: TMEM -> registers (32 lanes x 32 columns per tcgen05.ld),
 // fused bias / GELU / residual, vectorised global stores.  `q` = TMEM lane quarter of this warp.
 template <int BN>
-__device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row, int n_blk, const GemmArgs& g, bool split) {
+__device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row, int n_blk, const GemmArgs& g, bool split,
+                                              int c_first) {
+  // the two warps sharing a lane quarter interleave the 32-column chunks
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_first; c < BN / 32; c += 2) {
     uint32_t r[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
     const int n0 = n_blk * BN + c * 32;
@@ -254,7 +257,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     mbar_wait(accbar, 0);
     if (dbg && threadIdx.x == 64) g.dbg[5] = clock64();
     tc_fence_after();
-    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split);
+    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split, (warp - 2) >> 2);
   }
   tc_fence_before();
   __syncthreads();
@@ -375,7 +378,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     const int row = m_blk * BM + q * 32 + lane;
     mbar_wait(accbar, 0);
     tc_fence_after();
-    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split);
+    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split, (warp - 2) >> 2);
   }
   tc_fence_before();
   cluster_sync_all();        // the peer may still be reading our smem / signalling our barriers
@@ -390,7 +393,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 // TMEM holds TWO 256-column accumulators (all 512 columns): the epilogue of tile i (tcgen05.ld,
 // bias/GELU/residual, stores) overlaps the TMA + MMA main loop of tile i+1.  Pipelines:
 //   smem ring   full[s]  (leader, 2 arrivals + tx)   / empty[s]  (per CTA, multicast commit)
-//   accumulators tfull[a] (per CTA, multicast commit) / tempty[a] (leader, 8 epilogue-warp arrivals)
+//   accumulators tfull[a] (per CTA, multicast commit) / tempty[a] (leader, 16 epilogue-warp arrivals)
 // ================================================================================================
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -421,7 +424,7 @@ gemm_f16_tcgen05_2cta_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -482,7 +485,7 @@ gemm_f16_tcgen05_2cta_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
       const int row = m_blk * BM + q * 32 + lane;
       mbar_wait(tfull0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
-      epilogue_slab<BN>(tmem_base + (uint32_t)(acc * BN), q, row, n_blk, g, false);
+      epilogue_slab<BN>(tmem_base + (uint32_t)(acc * BN), q, row, n_blk, g, false, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader((tempty0 + 8 * acc) & PEER_MASK);   // this warp no longer reads accumulator `acc`
