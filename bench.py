@@ -272,11 +272,14 @@ def gemm_roofline(engine, B, dims):
         calls.append((a, w, bias, epi, out))
         orig(a, w, bias, epi, out)
 
+    orig_fuse = engine.fuse_ln
+    engine.fuse_ln = False          # the replay times the GEMMs alone (LayerNorm launched separately, not replayed)
     engine._gemm = rec
     mid = torch.empty(B, H, dims.image, 3, dtype=torch.uint8, device=engine.dev)
     img = torch.zeros(B, H, W, 3, dtype=torch.uint8, device=engine.dev)
     engine._forward_impl(img, mid)
     engine._gemm = orig
+    engine.fuse_ln = orig_fuse
     torch.cuda.synchronize()
     flops = sum(2.0 * a.shape[0] * w.shape[0] * a.shape[1] for a, w, *_ in calls)
     for _ in range(2):

@@ -145,6 +145,13 @@ int vlfm_obstacle_update(const VlfmObstacleParams* p, int batch, const int32_t* 
  * (start, setup done, dependency wait done, first stage landed, last MMA issued, accumulator ready,
  * epilogue done) and %globaltimer into d_buf8[0..7]; NULL disables. */
 void vlfm_gemm_debug_timeline(unsigned long long* d_buf8);
+/* x[M,N] (fp32 residual stream) += A @ W^T + bias, then LayerNorm(x) -> d_out16 (fp16) and/or d_out32 (fp32, may
+ * alias x for the post-LN Q-Former blocks).  When the GEMM is a single wave the LayerNorm runs inside the same
+ * kernel after a grid-wide barrier (d_sync2: two zero-initialised uint32 owned by the caller); otherwise it is
+ * launched as a second kernel.  Replaces `x = x + proj(...)` followed by `layer_norm` in the BLIP-2 forward. */
+int vlfm_gemm_f16_resid_ln(const void* d_A, const void* d_W, const float* d_bias, float* d_x, int M, int N, int K,
+                           int lda, int ldw, int ldx, const float* d_gamma, const float* d_beta, void* d_out16,
+                           int ld16, float* d_out32, int ld32, float eps, uint32_t* d_sync2, void* stream);
 int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
                   int K, int lda, int ldw, int ldo, int epilogue, void* stream);
 

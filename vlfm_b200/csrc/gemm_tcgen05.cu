@@ -94,6 +94,9 @@ struct GemmArgs {
   int M, N, K, ldo, epi;
   int kb_per_split;   // K-blocks per grid.z slice (split-K, residual epilogue only)
   unsigned long long* dbg;
+  // optional fused LayerNorm of the updated residual rows (grid-wide barrier, then warp-per-row LN)
+  const float* ln_gamma; const float* ln_beta; __half* ln_out16; float* ln_out32; unsigned* ln_sync;
+  int ln_ld16, ln_ld32; float ln_eps;
 };
 
 __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
@@ -219,6 +222,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (dbg && threadIdx.x == 0) g.dbg[1] = clock64();
   pdl_wait();   // predecessors' global writes (A operand, residual stream) are visible from here on
   if (dbg && threadIdx.x == 0) g.dbg[2] = clock64();
+  unsigned ln_epoch = 0;
+  if (g.ln_sync && threadIdx.x == 0) ln_epoch = *reinterpret_cast<volatile unsigned*>(g.ln_sync + 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -261,6 +266,35 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (g.ln_sync) {
+    // ---- fused LayerNorm: every CTA's residual update is done -> grid barrier -> rows are normalised by all warps.
+    // All CTAs are co-resident (the host only fuses single-wave launches).
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+      const unsigned old = atomicAdd(g.ln_sync, 1u);
+      if (old == total - 1) {
+        g.ln_sync[0] = 0;
+        __threadfence();
+        atomicAdd(g.ln_sync + 1, 1u);
+      } else {
+        unsigned spin = 0;
+        while (*reinterpret_cast<volatile unsigned*>(g.ln_sync + 1) == ln_epoch) {
+          __nanosleep(64);
+          if (++spin > (1u << 24)) __trap();
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const unsigned nwarps = GEMM_THREADS / 32;
+    const unsigned gw = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * nwarps + warp;
+    const unsigned tw = gridDim.x * gridDim.y * gridDim.z * nwarps;
+    const float* xbase = reinterpret_cast<const float*>(g.out);
+    for (unsigned r = gw; r < (unsigned)g.M; r += tw)
+      ln_row_warp(xbase + (size_t)r * g.ldo, g.ln_gamma, g.ln_beta, g.ln_out16 ? g.ln_out16 + (size_t)r * g.ln_ld16 : nullptr,
+                  g.ln_out32 ? g.ln_out32 + (size_t)r * g.ln_ld32 : nullptr, g.N, g.ln_eps, lane);
+  }
   if (dbg && threadIdx.x == 0) g.dbg[6] = clock64();
   if (g.dbg && threadIdx.x == 0 && cta_lin < 2048) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[9 + 2 * cta_lin] = t; }
   if (warp == 1) {
@@ -604,6 +638,8 @@ static int launch_gemm_2cta_persistent(const CUtensorMap& ta, const void* W, int
 
 using namespace vlfm;
 
+static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, int lda, int ldw, GemmArgs g, void* stream, bool* fused);
+
 extern "C" void vlfm_gemm_debug_timeline(unsigned long long* d_buf8) { vlfm::g_gemm_dbg = d_buf8; }
 
 extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
@@ -612,7 +648,12 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
     set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
   if (epilogue < 0 || epilogue > 3) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg};
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  return gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, nullptr);
+}
+
+static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, int lda, int ldw, GemmArgs g, void* stream, bool* fused) {
+  const int epilogue = g.epi;
   CUtensorMap ta;
   int rc = make_map(&ta, d_A, M, K, lda, BM);
   if (rc) return rc;
@@ -629,6 +670,8 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
     const long tiles128 = (long)mt * ((N + 127) / 128);
     if (two && tiles128 >= 296 && N >= 256) {
       g.kb_per_split = num_k;
+      g.ln_sync = nullptr;                       // multi-wave problem: the caller runs LayerNorm as its own launch
+      if (fused) *fused = false;
       static int persist = -1;
       if (persist < 0) { const char* e = getenv("VLFM_GEMM_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
       if (persist) return launch_gemm_2cta_persistent<256, 6>(ta, d_W, ldw, g, st);
@@ -669,6 +712,10 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   static int shallow = -1;
   if (shallow < 0) { const char* e = getenv("VLFM_GEMM_SHALLOW"); shallow = (e && e[0] == '1') ? 1 : 0; }  // measured slower on B200 (3 stages cannot cover the latency): off
   const bool one_wave = (long)mt * ((N + best_bn - 1) / best_bn) * best_s <= 148;
+  if (g.ln_sync) {                               // grid-barrier fusion needs every CTA resident at once
+    if (one_wave) { if (fused) *fused = true; }
+    else { g.ln_sync = nullptr; if (fused) *fused = false; }
+  }
   if ((shallow && one_wave) || force_shallow) {
     if (best_bn == 128) return launch_gemm<128, 3>(ta, d_W, ldw, g, st);
     if (best_bn == 64) return launch_gemm<64, 4>(ta, d_W, ldw, g, st);
@@ -677,4 +724,23 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   if (best_bn == 128) return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
   if (best_bn == 64) return launch_gemm<64, 8>(ta, d_W, ldw, g, st);
   return launch_gemm<32, 8>(ta, d_W, ldw, g, st);
+}
+
+extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out16, float* d_out32,
+                   int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream);
+
+extern "C" int vlfm_gemm_f16_resid_ln(const void* d_A, const void* d_W, const float* d_bias, float* d_x, int M, int N, int K,
+                                      int lda, int ldw, int ldx, const float* d_gamma, const float* d_beta, void* d_out16,
+                                      int ld16, float* d_out32, int ld32, float eps, uint32_t* d_sync2, void* stream) {
+  if (!d_A || !d_W || !d_x || !d_gamma || !d_beta || (!d_out16 && !d_out32) || !d_sync2 || M < 1 || N < 1 || K < 1) {
+    set_error("vlfm_gemm_f16_resid_ln: bad argument"); return VLFM_E_INVALID; }
+  if ((K & 7) || (lda & 7) || (ldw & 7) || (ldx & 7) || (N & 3) || (ld16 & 3) || (ld32 & 3) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) ||
+      ((uintptr_t)d_x & 15)) { set_error("vlfm_gemm_f16_resid_ln: alignment (K, strides %% 8; N %% 4; 16-byte pointers)"); return VLFM_E_INVALID; }
+  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, g_gemm_dbg,
+             d_gamma, d_beta, (__half*)d_out16, d_out32, d_sync2, ld16, ld32, eps};
+  bool fused = false;
+  int rc = gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, &fused);
+  if (rc) return rc;
+  if (!fused) return vlfm_layernorm(d_x, d_gamma, d_beta, d_out16, d_out32, M, N, ldx, ld16, ld32, eps, stream);
+  return VLFM_OK;
 }

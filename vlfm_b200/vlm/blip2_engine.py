@@ -42,6 +42,8 @@ class Blip2ITCEngine:
         self._load(state_dict)
         self._alloc(max_batch)
         self.text_feat = torch.zeros(dims.proj, dtype=F32, device=self.dev)
+        self.fuse_ln = os.environ.get("VLFM_FUSE_LN", "1") != "0"
+        self._sync = torch.zeros(2, dtype=torch.int32, device=self.dev)   # grid-barrier words of the fused GEMM+LN
 
     # ------------------------------------------------------------------ weights ----
     def _load(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -149,6 +151,19 @@ class Blip2ITCEngine:
                                     a.stride(0), w.stride(0), out.stride(0), epi, _lib.stream_ptr())
         _lib.check(rc, "vlfm_gemm_f16")
 
+    def _gemm_resid_ln(self, a, w, bias, x, g, b, out16, out32, eps):
+        """x += a @ w^T + bias ; LayerNorm(x) -> out16 / out32 (one launch when the GEMM is a single wave)."""
+        if not self.fuse_ln:
+            self._gemm(a, w, bias, _lib.EPI_BIAS_RESID_F32, x)
+            self._ln(x, g, b, out16, out32, eps)
+            return
+        M, K = a.shape
+        rc = self.lib.vlfm_gemm_f16_resid_ln(a.data_ptr(), w.data_ptr(), _lib.ptr(bias), x.data_ptr(), M, w.shape[0], K, a.stride(0),
+                                             w.stride(0), x.stride(0), g.data_ptr(), b.data_ptr(), _lib.ptr(out16),
+                                             out16.stride(0) if out16 is not None else 0, _lib.ptr(out32),
+                                             out32.stride(0) if out32 is not None else 0, eps, self._sync.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "vlfm_gemm_f16_resid_ln")
+
     def _ln(self, x, g, b, out16, out32, eps):
         rows, D = x.shape
         rc = self.lib.vlfm_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), _lib.ptr(out16), _lib.ptr(out32), rows, D,
@@ -188,16 +203,18 @@ class Blip2ITCEngine:
         _lib.check(rc, "vlfm_assemble_tokens")
         x, xn, qkv, ao, hb_ = self.b_x[:n], self.b_xn[:n], self.b_qkv[:n], self.b_ao[:n], self.b_h[:n]
         hd = D // d.v_heads
-        for L in self.vit:
-            self._ln(x, L["ln1_w"], L["ln1_b"], xn, None, d.v_eps)
+        img16 = self.b_img[:n]
+        self._ln(x, self.vit[0]["ln1_w"], self.vit[0]["ln1_b"], xn, None, d.v_eps)
+        for i, L in enumerate(self.vit):
             self._gemm(xn, L["qkv_w"], L["qkv_b"], _lib.EPI_BIAS_F16, qkv)
             self._attn(qkv[:, 0:D], qkv[:, D : 2 * D], qkv[:, 2 * D : 3 * D], ao, B, d.v_heads, T, T, hd, hd**-0.5)
-            self._gemm(ao, L["proj_w"], L["proj_b"], _lib.EPI_BIAS_RESID_F32, x)
-            self._ln(x, L["ln2_w"], L["ln2_b"], xn, None, d.v_eps)
+            self._gemm_resid_ln(ao, L["proj_w"], L["proj_b"], x, L["ln2_w"], L["ln2_b"], xn, None, d.v_eps)
             self._gemm(xn, L["fc1_w"], L["fc1_b"], _lib.EPI_BIAS_GELU_F16, hb_)
-            self._gemm(hb_, L["fc2_w"], L["fc2_b"], _lib.EPI_BIAS_RESID_F32, x)
-        img16 = self.b_img[:n]
-        self._ln(x, self.post_w, self.post_b, img16, None, d.v_eps)
+            if i + 1 < len(self.vit):   # the next block's pre-norm rides on this block's residual GEMM
+                nx = self.vit[i + 1]
+                self._gemm_resid_ln(hb_, L["fc2_w"], L["fc2_b"], x, nx["ln1_w"], nx["ln1_b"], xn, None, d.v_eps)
+            else:                       # ... and the post-LayerNorm on the last one
+                self._gemm_resid_ln(hb_, L["fc2_w"], L["fc2_b"], x, self.post_w, self.post_b, img16, None, d.v_eps)
         kv = self.b_kv[:n]
         self._gemm(img16, self.kv_w, self.kv_b, _lib.EPI_BIAS_F16, kv)
         h32, h16 = self.q_h32[:nq], self.q_h16[:nq]
@@ -219,19 +236,16 @@ class Blip2ITCEngine:
         for L in self.qf:
             self._gemm(h16, L["qkv_w"], L["qkv_b"], _lib.EPI_BIAS_F16, qkv)
             self._attn(qkv[:, 0:H], qkv[:, H : 2 * H], qkv[:, 2 * H : 3 * H], ao, B, d.q_heads, S, S, hd, sc)
-            self._gemm(ao, L["so_w"], L["so_b"], _lib.EPI_BIAS_RESID_F32, h32)
-            self._ln(h32, L["sln_w"], L["sln_b"], h16, h32, d.q_eps)
+            self._gemm_resid_ln(ao, L["so_w"], L["so_b"], h32, L["sln_w"], L["sln_b"], h16, h32, d.q_eps)
             if not text and L["cross"] >= 0:
                 j = L["cross"]
                 self._gemm(h16, L["cq_w"], L["cq_b"], _lib.EPI_BIAS_F16, qq)
                 self._attn(qq, kv[:, j * 2 * H : j * 2 * H + H], kv[:, j * 2 * H + H : (j + 1) * 2 * H], ao, B, d.q_heads, S, T, hd, sc)
-                self._gemm(ao, L["co_w"], L["co_b"], _lib.EPI_BIAS_RESID_F32, h32)
-                self._ln(h32, L["cln_w"], L["cln_b"], h16, h32, d.q_eps)
+                self._gemm_resid_ln(ao, L["co_w"], L["co_b"], h32, L["cln_w"], L["cln_b"], h16, h32, d.q_eps)
             iw, ib, ow, ob, lw, lb = ((L["it_w"], L["it_b"], L["ot_w"], L["ot_b"], L["otln_w"], L["otln_b"]) if text else
                                       (L["iq_w"], L["iq_b"], L["oq_w"], L["oq_b"], L["oqln_w"], L["oqln_b"]))
             self._gemm(h16, iw, ib, _lib.EPI_BIAS_GELU_F16, ff)
-            self._gemm(ff, ow, ob, _lib.EPI_BIAS_RESID_F32, h32)
-            self._ln(h32, lw, lb, h16, h32, d.q_eps)
+            self._gemm_resid_ln(ff, ow, ob, h32, lw, lb, h16, h32, d.q_eps)
 
     # ------------------------------------------------------------------- public ----
     @torch.inference_mode()
