@@ -220,15 +220,25 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) g.dbg[1] = clock64();
-  pdl_wait();   // predecessors' global writes (A operand, residual stream) are visible from here on
-  if (dbg && threadIdx.x == 0) g.dbg[2] = clock64();
   unsigned ln_epoch = 0;
-  if (g.ln_sync && threadIdx.x == 0) ln_epoch = *reinterpret_cast<volatile unsigned*>(g.ln_sync + 1);
 
   if (warp == 0) {
     if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < num_k; ++kb) {
+      // Weights do not depend on the predecessor kernel: start streaming the first STAGES W tiles BEFORE the
+      // programmatic-dependency wait (hides the HBM/L2 latency of the first loads behind the predecessor's tail);
+      // the matching A tiles (activations) are issued right after the wait and complete the same barriers.
+      const int pre = num_k < STAGES ? num_k : STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(full0 + 8 * kb, A_BYTES + B_BYTES);
+        tma_load_2d(smem_u32(sB + kb * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * kb);
+      }
+      pdl_wait();
+      if (dbg) g.dbg[2] = clock64();
+      if (g.ln_sync) ln_epoch = *reinterpret_cast<volatile unsigned*>(g.ln_sync + 1);
+      for (int kb = 0; kb < pre; ++kb)
+        tma_load_2d(smem_u32(sA + kb * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * kb);
+      int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
+      for (int kb = pre; kb < num_k; ++kb) {
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
         tma_load_2d(smem_u32(sA + s * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * s);
@@ -259,6 +269,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
     const int row = m_blk * BM + q * 32 + lane;
+    pdl_wait();          // residual stream / output buffers of the predecessor are visible
     mbar_wait(accbar, 0);
     if (dbg && threadIdx.x == 64) g.dbg[5] = clock64();
     tc_fence_after();
@@ -267,6 +278,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_before();
   __syncthreads();
   if (g.ln_sync) {
+    pdl_wait();
     // ---- fused LayerNorm: every CTA's residual update is done -> grid barrier -> rows are normalised by all warps.
     // All CTAs are co-resident (the host only fuses single-wave launches).
     if (threadIdx.x == 0) {

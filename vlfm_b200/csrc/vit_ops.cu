@@ -186,30 +186,20 @@ attention_kernel(AttnArgs a) {
   const __half* kbase = a.k + (size_t)b * a.Nk * a.ldk + (size_t)h * a.hd;
   const __half* vbase = a.v + (size_t)b * a.Nk * a.ldv + (size_t)h * a.hd;
 
-  // ---- stage K and V (16-byte copies, zero padding of rows >= Nk and columns >= hd)
+  // ---- stage K and V with cp.async (16-byte LDGSTS, all copies in flight at once; src-size 0 zero-fills the
+  // padding rows >= Nk and columns >= hd)
   constexpr int CH = HDP / 8;
-  for (int i0 = tid; i0 < NKP * CH; i0 += 4 * 32 * ATT_WARPS) {
-    uint4 kv[4], vv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 32 * ATT_WARPS;
-      const int key = i / CH, c = (i - key * CH) * 8;
-      kv[u] = make_uint4(0, 0, 0, 0); vv[u] = make_uint4(0, 0, 0, 0);
-      if (i < NKP * CH && key < a.Nk && c < a.hd) {
-        kv[u] = *reinterpret_cast<const uint4*>(kbase + (size_t)key * a.ldk + c);
-        vv[u] = *reinterpret_cast<const uint4*>(vbase + (size_t)key * a.ldv + c);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 32 * ATT_WARPS;
-      if (i < NKP * CH) {
-        const int key = i / CH, c = (i - key * CH) * 8;
-        *reinterpret_cast<uint4*>(sK + key * KS + c) = kv[u];
-        *reinterpret_cast<uint4*>(sV + key * KS + c) = vv[u];
-      }
-    }
+  for (int i = tid; i < NKP * CH; i += 32 * ATT_WARPS) {
+    const int key = i / CH, c = (i - key * CH) * 8;
+    const bool ok = key < a.Nk && c < a.hd;
+    const __half* ksrc = ok ? kbase + (size_t)key * a.ldk + c : kbase;
+    const __half* vsrc = ok ? vbase + (size_t)key * a.ldv + c : vbase;
+    const uint32_t kd = (uint32_t)__cvta_generic_to_shared(sK + key * KS + c), vd = (uint32_t)__cvta_generic_to_shared(sV + key * KS + c);
+    const int nbytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(kd), "l"(ksrc), "r"(nbytes) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vd), "l"(vsrc), "r"(nbytes) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   // ---- Q fragments: rows 16*(warp&1) + {g, g+8} of this CTA's 32-row block
   const int row0 = qb * ATT_QBLK + (warp % RG) * 16;
@@ -225,6 +215,7 @@ attention_kernel(AttnArgs a) {
     qf[kk][2] = (r_lo < a.Nq && c1 < a.hd) ? *reinterpret_cast<const uint32_t*>(qlo + c1) : 0u;
     qf[kk][3] = (r_hi < a.Nq && c1 < a.hd) ? *reinterpret_cast<const uint32_t*>(qhi + c1) : 0u;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   float o[HDP / 8][4];

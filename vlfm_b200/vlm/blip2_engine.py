@@ -42,7 +42,8 @@ class Blip2ITCEngine:
         self._load(state_dict)
         self._alloc(max_batch)
         self.text_feat = torch.zeros(dims.proj, dtype=F32, device=self.dev)
-        self.fuse_ln = os.environ.get("VLFM_FUSE_LN", "1") != "0"
+        # measured on B200: the in-kernel grid barrier costs more than the separate LayerNorm launch (4.01 vs 3.38 ms/step): off
+        self.fuse_ln = os.environ.get("VLFM_FUSE_LN", "0") == "1"
         self._sync = torch.zeros(2, dtype=torch.int32, device=self.dev)   # grid-barrier words of the fused GEMM+LN
 
     # ------------------------------------------------------------------ weights ----
