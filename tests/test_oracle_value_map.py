@@ -71,3 +71,23 @@ def test_oracle_matches_live_reference():
             r.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
             o.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
         assert np.array_equal(r._map, o._map) and np.array_equal(r._value_map, o._value_map)
+
+
+@pytest.mark.skipif(not has_reference(), reason="/root/reference not present")
+def test_oracle_ppm40_matches_patched_reference():
+    """configs[4]/[5] geometry: the reference needs `pixels_per_meter` patched and its cone cache cleared
+    (value_map.py:65, :339); the oracle takes ppm as a parameter."""
+    from oracle import ref_import
+
+    RV = ref_import.value_map_class()
+    RV._confidence_masks.clear()
+    r = RV(1, size=1000, use_max_confidence=False)
+    r.pixels_per_meter = 40
+    o = ValueMapOracle(1, size=1000, use_max_confidence=False, pixels_per_meter=40, prims="numpy")
+    rng = np.random.default_rng(9)
+    for f in trajectory(62, 2, h=128, w=128, bound_m=6.0):
+        v = rng.random(1)
+        r.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
+        o.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
+    RV._confidence_masks.clear()
+    assert np.array_equal(r._map, o._map) and np.array_equal(r._value_map, o._value_map)

@@ -121,3 +121,51 @@ def test_full_size_properties():
     g.update_map(np.array([0.5]), f.depth, f.tf, 0.5, 5.0, FOV)
     assert np.array_equal(a, g._map) and np.array_equal(va, g._value_map)  # same view twice changes nothing
     assert a.max() <= 1.0 and a.min() >= 0.0 and 0 < (a > 0).sum() <= 7081 + 600
+
+
+def test_explored_area_masking_matches_oracle():
+    """value_map.py:365-375: with an obstacle map attached, unexplored cells are zeroed in the new observation,
+    the confidence grid and the value grid (whole grid, every step)."""
+    import torch
+
+    class FakeObstacleMap:
+        pixels_per_meter, size = 20, 500
+
+        def __init__(self):
+            self.dev = torch.zeros((1, 500, 500), dtype=torch.uint8, device="cuda")
+            self.host = np.zeros((500, 500), dtype=bool)
+
+        def explored_device(self):
+            return self.dev
+
+        def set(self, mask):
+            self.host = mask
+            self.dev.copy_(torch.from_numpy(mask.astype(np.uint8))[None])
+
+    om = FakeObstacleMap()
+    o = ValueMapOracle(1, size=500, use_max_confidence=False, explored_fn=lambda: om.host)
+    g = _gpu_map(1, size=500, use_max_confidence=False, obstacle_map=om)
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:500, 0:500]
+    for i, f in enumerate(trajectory(61, 8, h=120, w=160, bound_m=4.0)):
+        cx, cy = 250 + 60 * np.cos(i), 250 + 60 * np.sin(i)
+        om.set(((yy - cy) ** 2 + (xx - cx) ** 2) < (90 + 10 * i) ** 2)     # a moving, growing explored disc
+        v = rng.random(1)
+        o.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
+        g.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
+        assert np.array_equal(g._map, o._map), f"step {i}"
+        assert np.abs(g._value_map - o._value_map).max() <= VAL_TOL
+
+
+def test_other_resolution_ppm40():
+    """configs[4]-style geometry: 0.025 m cells (ppm 40 -> R = 401), square depth image.  The reference class
+    needs the documented patch (pixels_per_meter attribute + cone-cache clear); the oracle takes ppm."""
+    o = ValueMapOracle(1, size=1400, use_max_confidence=False, pixels_per_meter=40)
+    g = _gpu_map(1, size=1400, use_max_confidence=False, pixels_per_meter=40)
+    rng = np.random.default_rng(9)
+    for i, f in enumerate(trajectory(62, 5, h=256, w=256, bound_m=10.0)):
+        v = rng.random(1)
+        o.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
+        g.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
+    assert np.array_equal(g._map, o._map)
+    assert np.abs(g._value_map - o._value_map).max() <= VAL_TOL
