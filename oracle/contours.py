@@ -123,3 +123,63 @@ def contour_area(c: np.ndarray) -> float:
         return 0.0
     q = np.roll(p, 1, axis=0)
     return float(abs(np.sum(q[:, 0] * p[:, 1] - p[:, 0] * q[:, 1]) * 0.5))
+
+
+def is_convex(c: np.ndarray) -> bool:
+    """cv2.isContourConvex for an integer contour: every consecutive turn has the same strict sign
+    (a collinear triple makes the contour non-convex)."""
+    p = c.reshape(-1, 2).astype(np.int64)
+    n = len(p)
+    if n == 0:
+        return False
+    prev, cur = p[(n - 2) % n], p[n - 1]
+    dx0, dy0 = cur[0] - prev[0], cur[1] - prev[1]
+    orient = 0
+    for i in range(n):
+        prev, cur = cur, p[i]
+        dx, dy = cur[0] - prev[0], cur[1] - prev[1]
+        dxdy0, dydx0 = dx * dy0, dy * dx0
+        orient |= 1 if dydx0 > dxdy0 else (2 if dydx0 < dxdy0 else 3)
+        if orient == 3:
+            return False
+        dx0, dy0 = dx, dy
+    return True
+
+
+def point_polygon_distance(c: np.ndarray, pt) -> float:
+    """cv2.pointPolygonTest(c, pt, True): signed distance (>0 inside) to an integer contour, float32 points,
+    float64 accumulation exactly as OpenCV evaluates it."""
+    p = c.reshape(-1, 2)
+    n = len(p)
+    if n == 0:
+        return -np.finfo(np.float64).max
+    px, py = np.float32(pt[0]), np.float32(pt[1])
+    v = p[n - 1].astype(np.float32)
+    min_num, min_den = float(np.finfo(np.float32).max), 1.0
+    counter = 0
+    for i in range(n):
+        v0, v = v, p[i].astype(np.float32)
+        dx, dy = float(v[0] - v0[0]), float(v[1] - v0[1])
+        dx1, dy1 = float(px - v0[0]), float(py - v0[1])
+        dx2, dy2 = float(px - v[0]), float(py - v[1])
+        den = 1.0
+        if dx1 * dx + dy1 * dy <= 0:
+            num = dx1 * dx1 + dy1 * dy1
+        elif dx2 * dx + dy2 * dy >= 0:
+            num = dx2 * dx2 + dy2 * dy2
+        else:
+            num = dy1 * dx - dx1 * dy
+            num *= num
+            den = dx * dx + dy * dy
+        if num * min_den < min_num * den:
+            min_num, min_den = num, den
+            if min_num == 0:
+                break
+        if (v0[1] <= py and v[1] <= py) or (v0[1] > py and v[1] > py):
+            continue
+        cross = dy1 * dx - dx1 * dy
+        if dy < 0:
+            cross = -cross
+        counter += cross > 0
+    r = float(np.sqrt(min_num / min_den))
+    return r if counter % 2 else -r

@@ -33,6 +33,48 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import contours as _ct
+from . import cv_draw as _dr
+from . import cv_prims as _pr
+
+# "cv2": call OpenCV exactly where frontier_exploration does.  "numpy": the same steps through the pinned
+# restatements in oracle/contours.py, oracle/cv_draw.py, oracle/cv_prims.py (the rules a GPU port follows).
+# Both are asserted identical by tests/test_oracle_explore.py.
+PRIMS = "cv2"
+
+
+def _contours(img, simple=True):
+    if PRIMS == "cv2":
+        import cv2
+
+        return list(cv2.findContours(img, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE if simple else cv2.CHAIN_APPROX_NONE)[0])
+    return _ct.find_external_contours(img, simple)
+
+
+def _fill_contour(img, contour, value):
+    if PRIMS == "cv2":
+        import cv2
+
+        return cv2.drawContours(img, [contour], 0, value, -1)
+    img[_pr.fill_polygon(img.shape[0], img.shape[1], contour.reshape(-1, 2))] = value
+    return img
+
+
+def _ppt(contour, pt):
+    if PRIMS == "cv2":
+        import cv2
+
+        return cv2.pointPolygonTest(contour, pt, True)
+    return _ct.point_polygon_distance(contour, pt)
+
+
+def _dilate(img, k):
+    if PRIMS == "cv2":
+        import cv2
+
+        return cv2.dilate(img, np.ones((k, k), np.uint8), iterations=1)
+    return _pr.dilate_box(img, k)
+
 
 def wrap_heading(h: float) -> float:
     return (h + np.pi) % (2 * np.pi) - np.pi
@@ -53,35 +95,46 @@ def _ray_segments(src: np.ndarray, pts: np.ndarray, length: float) -> np.ndarray
 
 
 def reveal_fog_of_war(top_down_map, current_fog_of_war_mask, current_point, current_angle, fov=90, max_line_len=100):
-    import cv2
-
     src = np.asarray(current_point)[::-1].astype(int)
     heading = np.rad2deg(wrap_heading(-current_angle + np.pi / 2))
-    cone = cv2.ellipse(np.zeros_like(top_down_map), tuple(int(v) for v in src), (int(max_line_len), int(max_line_len)), 0,
-                       heading - fov / 2, heading + fov / 2, 1, -1)                                        # R1
-    blocked = cv2.bitwise_and(cone, 1 - top_down_map)
-    contours, _ = cv2.findContours(blocked, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)                   # R2
+    if PRIMS == "cv2":
+        import cv2
+
+        cone = cv2.ellipse(np.zeros_like(top_down_map), tuple(int(v) for v in src), (int(max_line_len), int(max_line_len)), 0,
+                           heading - fov / 2, heading + fov / 2, 1, -1)                                    # R1
+    else:
+        cone = _dr.ellipse_sector(top_down_map.shape[0], top_down_map.shape[1], (int(src[0]), int(src[1])), int(max_line_len),
+                                  heading - fov / 2, heading + fov / 2).astype(top_down_map.dtype)
+    blocked = cone & (1 - top_down_map)
+    contours = _contours(blocked)                                                                          # R2
     if len(contours) == 0:
         return current_fog_of_war_mask
     pts = []
     for c in contours:                                                                                     # R3
-        if cv2.isContourConvex(c):
+        if (cv2.isContourConvex(c) if PRIMS == "cv2" else _ct.is_convex(c)):
             a, b = _extreme_bearing_points(src, c, heading)
             pts.append(a.reshape(-1, 2)); pts.append(b.reshape(-1, 2))
         else:
             pts.append(c.reshape(-1, 2))
     pts = np.concatenate(pts, axis=0)
-    visible = cv2.bitwise_and(cone, top_down_map)
-    cv2.polylines(visible, _ray_segments(src, pts, max_line_len * 1.05), isClosed=False, color=0, thickness=2)  # R4
-    final, _ = cv2.findContours(visible, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)                      # R5
+    visible = cone & top_down_map
+    segs = _ray_segments(src, pts, max_line_len * 1.05)                                                   # R4
+    if PRIMS == "cv2":
+        cv2.polylines(visible, segs, isClosed=False, color=0, thickness=2)
+    else:
+        cut = np.zeros(visible.shape, dtype=bool)
+        for a, b in segs:
+            _dr.thick_line2(cut, (int(a[0]), int(a[1])), (int(b[0]), int(b[1])))
+        visible = np.where(cut, 0, visible).astype(top_down_map.dtype)
+    final = _contours(visible)                                                                             # R5
     best, best_d = None, np.inf
     for c in final:
-        d = abs(cv2.pointPolygonTest(c, tuple(int(i) for i in src), True))
+        d = abs(_ppt(c, tuple(int(i) for i in src)))
         if d < best_d:
             best, best_d = c, d
     if best_d > 3:
         return current_fog_of_war_mask
-    return cv2.drawContours(current_fog_of_war_mask, [best], 0, 1, -1)
+    return _fill_contour(current_fog_of_war_mask, best, 1)
 
 
 def _bresenham(x0, y0, x1, y1):
@@ -111,22 +164,20 @@ def _interpolate(contour: np.ndarray) -> np.ndarray:
 
 
 def _absorb_small_unexplored(full_map, explored, area_thresh):
-    import cv2
-
     if area_thresh == -1:
         return explored
     unexplored = full_map.copy()
     unexplored[explored > 0] = 0
-    contours, _ = cv2.findContours(unexplored, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
     small = []
-    for c in contours:                                                                                     # F1
-        if cv2.contourArea(c) < area_thresh:
-            m = cv2.drawContours(np.zeros_like(explored), [c], 0, 1, -1)
+    for c in _contours(unexplored):                                                                        # F1
+        if _ct.contour_area(c) < area_thresh:
+            m = _fill_contour(np.zeros_like(explored), c, 1)
             vals = set(unexplored[m.astype(bool)].tolist())
             if 1 in vals and len(vals) == 1:
                 small.append(c)
     out = explored.copy()
-    cv2.drawContours(out, small, -1, 255, -1)
+    for c in small:
+        _fill_contour(out, c, 255)
     return out
 
 
@@ -156,12 +207,16 @@ def _midpoint(f: np.ndarray) -> np.ndarray:
 
 
 def detect_frontier_waypoints(full_map, explored_mask, area_thresh=-1, xy=None):
-    import cv2
-
     explored = _absorb_small_unexplored(full_map, explored_mask, area_thresh)
-    contours, _ = cv2.findContours(explored, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)                     # F2
+    contours = _contours(explored, simple=False)                                                           # F2
     unexplored = np.where(explored > 0, 0, full_map)
-    blur = cv2.blur(np.where(unexplored > 0, 255, unexplored), (3, 3))
+    u255 = np.where(unexplored > 0, 255, unexplored).astype(np.uint8)
+    if PRIMS == "cv2":
+        import cv2
+
+        blur = cv2.blur(u255, (3, 3))
+    else:
+        blur = _dr.blur3(u255)
     fronts = []
     for c in contours:
         fronts.extend(_split(_interpolate(c), blur))
@@ -173,8 +228,6 @@ def detect_frontier_waypoints(full_map, explored_mask, area_thresh=-1, xy=None):
 
 def explore_step(m, tf, max_depth, topdown_fov) -> None:
     """obstacle_map.py:114-153 on an ObstacleMapOracle ``m``."""
-    import cv2
-
     agent_px = m.xy_to_px(tf[:2, 3].reshape(1, 2))[0]
     yaw = float(np.arctan2(tf[1, 0], tf[0, 0]))
     new = reveal_fog_of_war(
@@ -182,22 +235,21 @@ def explore_step(m, tf, max_depth, topdown_fov) -> None:
         current_fog_of_war_mask=np.zeros_like(m._map, dtype=np.uint8),
         current_point=agent_px[::-1], current_angle=-yaw, fov=np.rad2deg(topdown_fov),
         max_line_len=max_depth * m.ppm)
-    new = cv2.dilate(new, np.ones((3, 3), np.uint8), iterations=1)
+    new = _dilate(new, 3)
     m.explored_area[new > 0] = 1
     m.explored_area[np.asarray(m._navigable_map) == 0] = 0
-    contours, _ = cv2.findContours(m.explored_area.astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    contours = _contours(m.explored_area.astype(np.uint8))
     if len(contours) > 1:
         best, best_d = 0, np.inf
         for i, c in enumerate(contours):
-            d = cv2.pointPolygonTest(c, tuple(int(v) for v in agent_px), True)
+            d = _ppt(c, tuple(int(v) for v in agent_px))
             if d >= 0:
                 best = i
                 break
             if abs(d) < best_d:
                 best, best_d = i, abs(d)
-        area = np.zeros_like(m.explored_area, dtype=np.uint8)
-        cv2.drawContours(area, contours, best, 1, -1)
+        area = _fill_contour(np.zeros_like(m.explored_area, dtype=np.uint8), contours[best], 1)
         m.explored_area = area.astype(bool)
-    grown = cv2.dilate(m.explored_area.astype(np.uint8), np.ones((5, 5), np.uint8), iterations=1)
+    grown = _dilate(m.explored_area.astype(np.uint8), 5)
     m._frontiers_px = detect_frontier_waypoints(np.asarray(m._navigable_map).astype(np.uint8), grown, m.area_thresh_px)
     m.frontiers = m.px_to_xy(m._frontiers_px) if len(m._frontiers_px) else np.array([])
