@@ -193,6 +193,20 @@ int vlfm_swin_window_attention(const void* d_qkv, const float* d_qkv_bias, const
                                int H, int W, int C, int heads, int shift, void* stream);
 int vlfm_swin_patch_merge(const float* d_x, float* d_out, int B, int H, int W, int C, void* stream);
 
+/* ------------------------------------------------------------- explore half ---- */
+/* Replaces ObstacleMap.update_map's explore half (vlfm/mapping/obstacle_map.py:114-153) and _get_frontiers
+ * (:155-169) including the two third-party frontier_exploration functions they call (spec:
+ * oracle/explore_oracle.py).  One environment per call.
+ * d_explored / d_nav [G,G] uint8; agent cell (col,row) = _xy_to_px(tf[:2,3]); heading_deg =
+ * rad2deg(wrap(yaw + pi/2)); fov_deg = rad2deg(topdown_fov); max_line_len = max_depth*ppm;
+ * area_thresh_px = area_thresh*ppm^2; nav_half = half-size of the window in which the navigable map changed.
+ * d_frontiers [4096,2] float64 (x=col, y=row), d_count int32, d_status int32 (non-zero: a scratch buffer overflowed).
+ * Fails (VLFM_E_UNSUPPORTED) when the fog-of-war window would leave the grid.                                  */
+int vlfm_explore_workspace_bytes(int G, size_t* bytes);
+int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_nav, int agent_col, int agent_row, double heading_deg,
+                        double fov_deg, double max_line_len, double area_thresh_px, int nav_half, double* d_frontiers,
+                        int32_t* d_count, void* d_workspace, int32_t* d_status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
