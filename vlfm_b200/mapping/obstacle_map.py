@@ -39,8 +39,7 @@ class ObstacleMap(BaseMap):
         kernel_size = self.pixels_per_meter * agent_radius * 2  # :43-46
         self._kernel = int(kernel_size) + (int(kernel_size) % 2 == 0)
         self._nav_valid = False  # before the first obstacle update the reference's navigable map is all 0
-        self._frontiers_px: np.ndarray = np.array([])
-        self.frontiers: np.ndarray = np.array([])
+        self._front_cache: Optional[np.ndarray] = np.array([])
         self._pin: Optional[torch.Tensor] = None
         self._pin_tf: Optional[torch.Tensor] = None
         self._dev_depth: Optional[torch.Tensor] = None
@@ -61,6 +60,18 @@ class ObstacleMap(BaseMap):
     def explored_area(self) -> np.ndarray:
         return self._explored[0].cpu().numpy().astype(bool)
 
+    # frontier waypoints are produced on the device; the host copy is fetched (and the stream synchronised) on access
+    @property
+    def _frontiers_px(self) -> np.ndarray:
+        if self._front_cache is None:
+            self._front_cache = self._explore_impl.fetch_frontiers_px()
+        return self._front_cache
+
+    @property
+    def frontiers(self) -> np.ndarray:
+        px = self._frontiers_px
+        return np.array([]) if len(px) == 0 else self._px_to_xy(px)      # obstacle_map.py:149-153
+
     def explored_device(self) -> torch.Tensor:
         return self._explored
 
@@ -68,8 +79,7 @@ class ObstacleMap(BaseMap):
         super().reset()
         self._obst.zero_(); self._nav.zero_(); self._explored.zero_(); self._status.zero_()
         self._nav_valid = False
-        self._frontiers_px = np.array([])
-        self.frontiers = np.array([])
+        self._front_cache = np.array([])
 
     def _upload(self, depth: Optional[np.ndarray], tf: np.ndarray) -> None:
         if self._pin_tf is None:
@@ -103,6 +113,7 @@ class ObstacleMap(BaseMap):
                 self._upload(depth, tf_camera_to_episodic)
                 h, w = depth.shape
                 half = int(math.ceil(max_depth * self.pixels_per_meter * math.sqrt(1.0 + (w / 2.0 / fx) ** 2))) + self._kernel // 2 + 2
+                self._last_half = half if self._nav_valid else self.size    # first update: the navigable map changed everywhere
                 p = _lib.ObstacleParams(h, w, self.size, self.pixels_per_meter,
                                         float(np.float32(max_depth - min_depth)), float(np.float32(min_depth)),
                                         float(np.float32(max_depth)), float(fx), float(fy),
@@ -130,7 +141,8 @@ class ObstacleMap(BaseMap):
                 from .explore import ExploreEngine
 
                 self._explore_impl = ExploreEngine(self)
-            self._explore_impl.update(tf_camera_to_episodic, max_depth, topdown_fov)
+            self._explore_impl.update(tf_camera_to_episodic, max_depth, topdown_fov, getattr(self, "_last_half", 0))
+            self._front_cache = None
 
     def visualize(self) -> np.ndarray:
         """obstacle_map.py:171-193 (trajectory overlay omitted)."""
