@@ -320,7 +320,7 @@ __global__ void fog_masks_kernel(const uint8_t* __restrict__ cone, const uint8_t
 
 // R3/R4: obstacle contours -> ray list (x0,y0,x1,y1 in window coordinates)
 __global__ void rays_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, int4* __restrict__ rays, int cap, int sx, int sy,
-                            double heading_deg, double ray_len, ExState* st) {
+                            int ox, int oy, double heading_deg, double ray_len, ExState* st) {
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= st->n_cont) return;
   const Contour c = cont[ci];
@@ -347,7 +347,8 @@ __global__ void rays_kernel(const Contour* __restrict__ cont, const int2* __rest
   }
   auto emit = [&](int qx, int qy) {
     const double ang = atan2((double)(qy - sy), (double)(qx - sx));
-    const int ex = (int)((double)qx + ray_len * cos(ang)), ey = (int)((double)qy + ray_len * sin(ang));   // astype(np.int32): truncation
+    // astype(np.int32) truncates toward zero in GRID coordinates (the window origin is subtracted afterwards)
+    const int ex = (int)((double)(qx + ox) + ray_len * cos(ang)) - ox, ey = (int)((double)(qy + oy) + ray_len * sin(ang)) - oy;
     const int k = atomicAdd(&st->n_rays, 1);
     if (k < cap) rays[k] = make_int4(qx, qy, ex, ey); else st->overflow = 1;
   };
@@ -821,7 +822,7 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   // ---- R2/R3/R4: obstacle contours -> rays -> cut
   contours(w, w.blocked, W0, W0, st, 0);
   fog_gate_kernel<<<1, 1, 0, st>>>(w.st);
-  rays_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.cont, w.chain, w.rays, w.rays_cap, sx, sy, heading_deg, max_line_len * 1.05, w.st);
+  rays_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.cont, w.chain, w.rays, w.rays_cap, sx, sy, ox, oy, heading_deg, max_line_len * 1.05, w.st);
   clear_bytes_kernel<<<nblk(wn), 256, 0, st>>>(w.cut, wn);
   thick_rays_kernel<<<RAYS_CAP / 64, 64, 0, st>>>(w.rays, w.cut, W0, W0, w.st);
   apply_cut_kernel<<<nblk(wn), 256, 0, st>>>(w.visible, w.cut, wn, w.st);
