@@ -63,22 +63,36 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
+// init: every pixel of the set points at the first pixel of its horizontal run (one thread per row), so that the
+// union phase only has to stitch runs of adjacent rows instead of every pixel pair.
 template <bool FG>
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int* __restrict__ L, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    L[i] = ((img[i] != 0) == FG) ? i : -1;
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int* __restrict__ L, int W, int H) {
+  for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < H; y += gridDim.x * blockDim.x) {
+    int run = -1;
+    const uint8_t* row = img + (size_t)y * W;
+    int* lr = L + (size_t)y * W;
+    for (int x = 0; x < W; ++x) {
+      const bool in = (row[x] != 0) == FG;
+      if (in) { if (run < 0) run = y * W + x; lr[x] = run; } else { run = -1; lr[x] = -1; }
+    }
+  }
 }
+// stitch: a pixel unions with the row above only where a NEW overlap between runs begins
 template <bool FG>
 __global__ void ccl_merge_kernel(const uint8_t* __restrict__ img, int* __restrict__ L, int W, int H) {
   const int n = W * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (((img[i] != 0) == FG) == false) continue;
     const int y = i / W, x = i - y * W;
-    if (x > 0 && ((img[i - 1] != 0) == FG)) uf_union(L, i, i - 1);
-    if (y > 0 && ((img[i - W] != 0) == FG)) uf_union(L, i, i - W);
-    if (FG) {   // foreground is 8-connected
-      if (y > 0 && x > 0 && img[i - W - 1] != 0) uf_union(L, i, i - W - 1);
-      if (y > 0 && x + 1 < W && img[i - W + 1] != 0) uf_union(L, i, i - W + 1);
+    if (y == 0) continue;
+    const bool west = x > 0 && ((img[i - 1] != 0) == FG);
+    const bool north = (img[i - W] != 0) == FG;
+    const bool nwest = x > 0 && ((img[i - W - 1] != 0) == FG);
+    if (north && (!west || !nwest)) uf_union(L, i, i - W);
+    if (FG) {   // foreground is 8-connected: diagonal contacts not already implied by a north contact
+      const bool neast = x + 1 < W && img[i - W + 1] != 0;
+      if (nwest && !north && !west) uf_union(L, i, i - W - 1);
+      if (neast && !north) uf_union(L, i, i - W + 1);
     }
   }
 }
@@ -108,6 +122,16 @@ __global__ void collect_roots_kernel(const int* __restrict__ Lfg, const int* __r
     if (!top) continue;                             // nested inside a hole of another component: not external
     const int k = atomicAdd(&st->n_cont, 1);
     if (k < EX_MAXC) cont[k].start = i; else st->overflow = 1;
+  }
+}
+// a foreground component that directly encloses a background region (a hole): flag its root
+__global__ void mark_holes_kernel(const int* __restrict__ Lfg, const int* __restrict__ Lbg, const uint8_t* __restrict__ outer,
+                                  uint8_t* __restrict__ hashole, int W, int H) {
+  const int n = W * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (Lbg[i] != i || outer[i]) continue;            // raster-first pixel of an enclosed background region
+    const int x = i % W;
+    if (x > 0 && Lfg[i - 1] >= 0) hashole[Lfg[i - 1]] = 1;
   }
 }
 // reverse raster order (cv2 returns the last-found contour first); one block, bitonic sort in shared memory
@@ -176,11 +200,14 @@ __device__ int trace_border(const uint8_t* img, int W, int H, int x0, int y0, in
   if (WRITE) { c->x0 = minx; c->x1 = maxx; c->y0 = miny; c->y1 = maxy; }
   return n;
 }
+// mode 0: trace every contour; 1: only when more than one contour exists (component selection); 2: skip components
+// that enclose a hole (their filled polygon contains a zero cell, so F1 can never absorb them)
 __global__ void trace_kernel(const uint8_t* __restrict__ img, int W, int H, Contour* __restrict__ cont, int2* __restrict__ chain,
-                             int cap, ExState* st) {
+                             int cap, ExState* st, int mode, const uint8_t* __restrict__ hashole) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st->n_cont) return;
   const int s = cont[c].start, y0 = s / W, x0 = s - y0 * W;
+  if ((mode == 1 && st->n_cont <= 1) || (mode == 2 && hashole[s])) { cont[c].off = 0; cont[c].len = 0; return; }
   const int n = trace_border<false>(img, W, H, x0, y0, nullptr, nullptr);
   const int off = atomicAdd(&st->cursor, n);
   if (off + n > cap) { st->overflow = 1; cont[c].off = 0; cont[c].len = 0; return; }
@@ -549,6 +576,7 @@ __global__ void absorb_small_kernel(const Contour* __restrict__ cont, const int2
   const int ci = blockIdx.x;
   if (ci >= st->n_cont) return;
   const Contour c = cont[ci];
+  if (c.len == 0) return;                       // not traced: the component encloses a hole
   const int2* p = chain + c.off;
   __shared__ long long s_a2;
   __shared__ int s_bad;
@@ -695,7 +723,7 @@ using namespace vlfm;
 namespace {
 
 struct Ws {       // carved from the caller's workspace
-  uint8_t *cone, *blocked, *visible, *cut, *newexp, *outer, *grown, *unexp, *ex2;
+  uint8_t *cone, *blocked, *visible, *cut, *newexp, *outer, *grown, *unexp, *ex2, *hashole;
   int *Lfg, *Lbg, *which;
   Contour* cont; int2* chain; int4* rays; double* dist; uint32_t *tog, *orb; long long* verts; ExState* st;
   int chain_cap, rays_cap;
@@ -717,6 +745,7 @@ size_t carve(Ws* w, uint8_t* base, int G) {
   p = take(n); if (w) w->grown = p;
   p = take(n); if (w) w->unexp = p;
   p = take(n); if (w) w->ex2 = p;
+  p = take(n); if (w) w->hashole = p;
   p = take(n * 4); if (w) w->Lfg = (int*)p;
   p = take(n * 4); if (w) w->Lbg = (int*)p;
   p = take(sizeof(Contour) * EX_MAXC); if (w) w->cont = (Contour*)p;
@@ -736,11 +765,11 @@ size_t carve(Ws* w, uint8_t* base, int G) {
 inline int nblk(long n, int t = 256) { long b = (n + t - 1) / t; return (int)(b < 1 ? 1 : (b > 2368 ? 2368 : b)); }
 
 // external contours of `img` (W x H): CCL fg/bg, top-level roots in cv2 order, traced chains
-void contours(const Ws& w, const uint8_t* img, int W, int H, cudaStream_t st, int keep_fog) {
+void contours(const Ws& w, const uint8_t* img, int W, int H, cudaStream_t st, int keep_fog, int mode = 0) {
   const int n = W * H;
   reset_state_kernel<<<1, 1, 0, st>>>(w.st, keep_fog);
-  ccl_init_kernel<true><<<nblk(n), 256, 0, st>>>(img, w.Lfg, n);
-  ccl_init_kernel<false><<<nblk(n), 256, 0, st>>>(img, w.Lbg, n);
+  ccl_init_kernel<true><<<nblk(H, 64), 64, 0, st>>>(img, w.Lfg, W, H);
+  ccl_init_kernel<false><<<nblk(H, 64), 64, 0, st>>>(img, w.Lbg, W, H);
   ccl_merge_kernel<true><<<nblk(n), 256, 0, st>>>(img, w.Lfg, W, H);
   ccl_merge_kernel<false><<<nblk(n), 256, 0, st>>>(img, w.Lbg, W, H);
   ccl_flatten_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, n);
@@ -749,7 +778,11 @@ void contours(const Ws& w, const uint8_t* img, int W, int H, cudaStream_t st, in
   bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
   collect_roots_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, w.st);
   sort_roots_kernel<<<1, 1024, 0, st>>>(w.cont, w.st);
-  trace_kernel<<<EX_MAXC / 64, 64, 0, st>>>(img, W, H, w.cont, w.chain, w.chain_cap, w.st);
+  if (mode == 2) {
+    clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(w.hashole, n);
+    mark_holes_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, w.hashole, W, H);
+  }
+  trace_kernel<<<EX_MAXC / 64, 64, 0, st>>>(img, W, H, w.cont, w.chain, w.chain_cap, w.st, mode, w.hashole);
   count_launch(12);
 }
 
@@ -842,7 +875,7 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   explored_update_kernel<<<nblk((long)(rx1 - rx0) * (ry1 - ry0)), 256, 0, st>>>(w.newexp, W0, ox, oy, d_explored, d_nav, G, rx0, ry0, rx1 - rx0,
                                                                               ry1 - ry0, w.st);
   // ---- component selection on the whole explored map (obstacle_map.py:128-146)
-  contours(w, d_explored, G, G, st, 1);
+  contours(w, d_explored, G, G, st, 1, 1);
   select_component_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.cont, w.chain, w.dist, agent_col, agent_row, w.st, w.which, 0);
   select_component_kernel<<<1, 1, 0, st>>>(w.cont, w.chain, w.dist, agent_col, agent_row, w.st, w.which, 1);
   zero_planes_kernel<<<nblk(pwG * G), 256, 0, st>>>(w.tog, w.orb, pwG * G);
@@ -852,7 +885,7 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   dilate_full_kernel<<<nblk(n), 256, 0, st>>>(d_explored, w.grown, G, G, 5);
   unexplored_kernel<<<nblk(n), 256, 0, st>>>(d_nav, w.grown, w.unexp, n);
   copy_bytes_kernel<<<nblk(n), 256, 0, st>>>(w.grown, w.ex2, n);
-  contours(w, w.unexp, G, G, st, 1);
+  contours(w, w.unexp, G, G, st, 1, 2);
   absorb_small_kernel<<<EX_MAXC, 128, 0, st>>>(w.cont, w.chain, w.unexp, w.ex2, G, G, area_thresh_px, w.st);
   contours(w, w.ex2, G, G, st, 1);
   frontier_kernel<<<1, 32, 0, st>>>(w.cont, w.chain, d_nav, w.ex2, G, G, d_frontiers, MAXF, w.st);
