@@ -124,9 +124,16 @@ typedef struct VlfmObstacleParams {
 
 /* d_obst [nslots,G,G] uint8 (ObstacleMap._map), d_nav [nslots,G,G] uint8
  * (ObstacleMap._navigable_map as 0/1).                                               */
+/* d_hole_fill [batch,H,W] uint8 or NULL: output of vlfm_fill_small_holes (pixels whose depth becomes 1.0);
+ * NULL selects the hole_area_thresh == -1 form (every zero depth becomes 1.0, obstacle_map.py:87-89). */
 int vlfm_obstacle_update(const VlfmObstacleParams* p, int batch, const int32_t* d_slot,
                          uint8_t* d_obst, uint8_t* d_nav, const float* d_depth,
-                         const double* d_tf, int32_t* d_status, void* stream);
+                         const double* d_tf, const uint8_t* d_hole_fill, int32_t* d_status, void* stream);
+/* fill_small_holes (vlfm/utils/img_utils.py:361-390): zero-depth regions AND the islands they enclose whose
+ * cv2.contourArea (RETR_TREE borders) is below area_thresh; d_filled [H,W] uint8 := 1 on the pixels set to 1.0. */
+int vlfm_holes_workspace_bytes(int H, int W, size_t* bytes);
+int vlfm_fill_small_holes(const float* d_depth, int H, int W, double area_thresh, uint8_t* d_filled, void* d_workspace,
+                          int32_t* d_status, void* stream);
 
 /* ---------------------------------------------------------------- dense (VLM) ---- */
 /* fp16 x fp16 -> fp32-accumulate GEMM on tcgen05 tensor cores, TMA-fed:

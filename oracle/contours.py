@@ -69,7 +69,13 @@ def _trace(f: np.ndarray, x0: int, y0: int, fx: int, fy: int, nbd: int) -> List[
     return pts
 
 
-def find_external_contours(img: np.ndarray, simple: bool = False) -> List[np.ndarray]:
+def find_all_contours(img: np.ndarray) -> List[np.ndarray]:
+    """Every border cv2.findContours(img, RETR_TREE, CHAIN_APPROX_NONE) returns (outer borders of all
+    components and all hole borders), as a set -- order is not restated (fill_small_holes takes a union)."""
+    return find_external_contours(img, False, _all=True)
+
+
+def find_external_contours(img: np.ndarray, simple: bool = False, _all: bool = False) -> List[np.ndarray]:
     """-> list of (n,1,2) int32 arrays exactly like cv2.findContours(img, RETR_EXTERNAL, ...)."""
     h, w = img.shape
     f = np.zeros((h + 2, w + 2), dtype=np.int32)
@@ -96,7 +102,7 @@ def find_external_contours(img: np.ndarray, simple: bool = False) -> List[np.nda
                 parent = (pp if pk == "outer" else abs(lnbd)) if kind == "outer" else (abs(lnbd) if pk == "outer" else pp)
                 borders[nbd] = (kind, parent)
                 pts = _trace(f, x, y, fx, fy, nbd)
-                if kind == "outer" and parent == 1:
+                if _all or (kind == "outer" and parent == 1):
                     out.append(np.array([(px - 1, py - 1) for px, py in pts], dtype=np.int32).reshape(-1, 1, 2))
             if f[y, x] != 1:
                 lnbd = abs(f[y, x])

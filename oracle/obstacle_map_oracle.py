@@ -43,6 +43,19 @@ def fill_holes(depth: np.ndarray, area_thresh: int) -> np.ndarray:
     return np.where(fill == 1, 1, depth)
 
 
+def fill_holes_numpy(depth: np.ndarray, area_thresh: int) -> np.ndarray:
+    """fill_holes without cv2: Suzuki-Abe borders (outer and hole), shoelace area, polygon fill."""
+    from . import contours as ct
+    from . import cv_prims as pr
+
+    holes = np.where(depth == 0, 1, 0).astype("uint8")
+    fill = np.zeros(holes.shape, dtype=bool)
+    for c in ct.find_all_contours(holes):
+        if ct.contour_area(c) < area_thresh:
+            fill |= pr.fill_polygon(holes.shape[0], holes.shape[1], c.reshape(-1, 2))
+    return np.where(fill, 1, depth)
+
+
 class ObstacleMapOracle:
     def __init__(self, min_height: float, max_height: float, agent_radius: float, area_thresh: float = 3.0,
                  hole_area_thresh: int = 100000, size: int = 1000, pixels_per_meter: int = 20):

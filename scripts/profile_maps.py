@@ -26,7 +26,7 @@ def run(B):
             eng.update(vals, depth, tf, 0.5, 5.0, FOV)
             p = _lib.ObstacleParams(H, W, G, 20, 4.5, 0.5, 5.0, fx, fx, 0.61, 0.88, 7, 1 if full else 0, half)
             _lib.check(lib.vlfm_obstacle_update(ctypes.byref(p), B, None, obst.data_ptr(), nav.data_ptr(), depth.data_ptr(),
-                                                tf.data_ptr(), status.data_ptr(), _lib.stream_ptr()), "obstacle")
+                                                tf.data_ptr(), None, status.data_ptr(), _lib.stream_ptr()), "obstacle")
         return go
     step(0, True)(); step(1, False)(); torch.cuda.synchronize()
     go = step(2, False)

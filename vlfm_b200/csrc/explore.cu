@@ -30,7 +30,7 @@ constexpr int EX_MAXC = 8192;      // contours per image
 constexpr int XYS = 16;
 constexpr long long XYONE = 1ll << XYS;
 
-struct Contour { int start, off, len, x0, y0, x1, y1; };   // start pixel index, chain offset/length, bbox
+struct Contour { int start, off, len, x0, y0, x1, y1, ed; };   // start pixel, chain offset/length, bbox, entry direction (0 = west: outer border, 4 = east: hole border)
 
 // device-side bookkeeping of one explore step
 struct ExState {
@@ -121,7 +121,7 @@ __global__ void collect_roots_kernel(const int* __restrict__ Lfg, const int* __r
     if (x > 0) { const int lb = Lbg[i - 1]; top = lb >= 0 && outer[lb]; }
     if (!top) continue;                             // nested inside a hole of another component: not external
     const int k = atomicAdd(&st->n_cont, 1);
-    if (k < EX_MAXC) cont[k].start = i; else st->overflow = 1;
+    if (k < EX_MAXC) { cont[k].start = i; cont[k].ed = 0; } else st->overflow = 1;
   }
 }
 // a foreground component that directly encloses a background region (a hole): flag its root
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(1024) sort_roots_kernel(Contour* __restrict__ 
       }
       __syncthreads();
     }
-  for (int i = threadIdx.x; i < n; i += 1024) cont[i].start = keys[i];
+  for (int i = threadIdx.x; i < n; i += 1024) { cont[i].start = keys[i]; cont[i].ed = 0; }
 }
 
 // ----------------------------------------------------------------------------------------- tracing ----
@@ -171,10 +171,11 @@ __device__ __forceinline__ int dir_index(int dx, int dy) {
 }
 // Suzuki-Abe steps 3.1-3.5 (oracle/contours.py::_trace); WRITE=false only counts.
 template <bool WRITE>
-__device__ int trace_border(const uint8_t* img, int W, int H, int x0, int y0, int2* out, Contour* c) {
+__device__ int trace_border(const uint8_t* img, int W, int H, int x0, int y0, int2* out, Contour* c, int ed = 0) {
   int fx = -1, fy = -1;
-  for (int k = 1; k < 8; ++k) {            // 3.1 clockwise from the west entry pixel
-    if (fg_at(img, W, H, x0 + c_dx[k], y0 + c_dy[k])) { fx = x0 + c_dx[k]; fy = y0 + c_dy[k]; break; }
+  for (int k = 1; k < 8; ++k) {            // 3.1 clockwise from the (zero) entry pixel: west for outer, east for hole borders
+    const int d = (ed + k) & 7;
+    if (fg_at(img, W, H, x0 + c_dx[d], y0 + c_dy[d])) { fx = x0 + c_dx[d]; fy = y0 + c_dy[d]; break; }
   }
   int minx = x0, maxx = x0, miny = y0, maxy = y0, n = 0;
   if (fx < 0) {
@@ -205,14 +206,14 @@ __device__ int trace_border(const uint8_t* img, int W, int H, int x0, int y0, in
 __global__ void trace_kernel(const uint8_t* __restrict__ img, int W, int H, Contour* __restrict__ cont, int2* __restrict__ chain,
                              int cap, ExState* st, int mode, const uint8_t* __restrict__ hashole) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= st->n_cont) return;
+  if (c >= st->n_cont || c >= gridDim.x * blockDim.x) return;
   const int s = cont[c].start, y0 = s / W, x0 = s - y0 * W;
   if ((mode == 1 && st->n_cont <= 1) || (mode == 2 && hashole[s])) { cont[c].off = 0; cont[c].len = 0; return; }
-  const int n = trace_border<false>(img, W, H, x0, y0, nullptr, nullptr);
+  const int n = trace_border<false>(img, W, H, x0, y0, nullptr, nullptr, cont[c].ed);
   const int off = atomicAdd(&st->cursor, n);
   if (off + n > cap) { st->overflow = 1; cont[c].off = 0; cont[c].len = 0; return; }
   cont[c].off = off; cont[c].len = n;
-  trace_border<true>(img, W, H, x0, y0, chain + off, &cont[c]);
+  trace_border<true>(img, W, H, x0, y0, chain + off, &cont[c], cont[c].ed);
 }
 
 // CHAIN_APPROX_SIMPLE: point i of a chain is kept iff the step into it differs from the step out of it
@@ -707,6 +708,85 @@ __global__ void frontier_kernel(const Contour* __restrict__ cont, const int2* __
   }
 }
 
+// ---------------------------------------------------------------- fill_small_holes (img_utils.py:361-390) ----
+__global__ void zero_mask_kernel(const float* __restrict__ depth, uint8_t* __restrict__ mask, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mask[i] = depth[i] == 0.f ? 1 : 0;
+}
+// RETR_TREE: the outer border of EVERY component and the border of every hole
+__global__ void collect_all_kernel(const int* __restrict__ Lfg, const int* __restrict__ Lbg, const uint8_t* __restrict__ outer, int W, int H,
+                                   Contour* __restrict__ cont, int maxc, ExState* st) {
+  const int n = W * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int start = -1, ed = 0;
+    if (Lfg[i] == i) { start = i; ed = 0; }
+    else if (Lbg[i] == i && !outer[i]) { start = i - 1; ed = 4; }     // hole: the pixel west of its raster-first cell, entered from the east
+    if (start < 0) continue;
+    const int k = atomicAdd(&st->n_cont, 1);
+    if (k < maxc) { cont[k].start = start; cont[k].ed = ed; } else st->overflow = 1;
+  }
+}
+// one block per contour: contourArea < thresh -> drawContours(filled, [cnt], 0, 1, -1); bounding-box scan conversion in
+// shared memory, processed in row bands when the box is tall
+__global__ void __launch_bounds__(256)
+fill_small_contours_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, uint8_t* __restrict__ filled, int W, int H,
+                           double area_thresh, int smem_words, const ExState* st) {
+  extern __shared__ uint32_t fs_smem[];
+  const int ci = blockIdx.x;
+  if (ci >= st->n_cont) return;
+  const Contour c = cont[ci];
+  if (c.len == 0) return;
+  const int2* p = chain + c.off;
+  __shared__ long long s_a2;
+  if (threadIdx.x == 0) s_a2 = 0;
+  __syncthreads();
+  long long acc = 0;
+  for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
+    const int2 q = p[i == 0 ? c.len - 1 : i - 1], b = p[i];
+    acc += (long long)q.x * b.y - (long long)b.x * q.y;
+  }
+  atomicAdd(reinterpret_cast<unsigned long long*>(&s_a2), (unsigned long long)acc);
+  __syncthreads();
+  if (!(fabs((double)s_a2 * 0.5) < area_thresh)) return;
+  const int bw = c.x1 - c.x0 + 2, pw = (bw + 31) / 32;           // +1 column for the toggle right of the last cell
+  const int band = smem_words / (2 * pw);
+  for (int r0 = c.y0; r0 <= c.y1; r0 += band) {
+    const int rows = min(band, c.y1 - r0 + 1);
+    uint32_t* tog = fs_smem; uint32_t* orb = fs_smem + rows * pw;
+    for (int i = threadIdx.x; i < 2 * rows * pw; i += blockDim.x) fs_smem[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
+      const int2 a = p[i], b = p[i + 1 == c.len ? 0 : i + 1];
+      if (a.y >= r0 && a.y < r0 + rows) atomicOr(&orb[(a.y - r0) * pw + ((a.x - c.x0) >> 5)], 1u << ((a.x - c.x0) & 31));
+      if (a.y != b.y) {
+        const int xa = (a.y < b.y ? a.x : b.x) - c.x0, ya = min(a.y, b.y);
+        if (ya >= r0 && ya < r0 + rows) {
+          atomicXor(&tog[(ya - r0) * pw + ((xa + 1) >> 5)], 1u << ((xa + 1) & 31));
+          atomicOr(&orb[(ya - r0) * pw + (xa >> 5)], 1u << (xa & 31));
+        }
+      }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+      uint32_t carry = 0;
+      for (int w = 0; w < pw; ++w) {
+        const uint32_t t = tog[r * pw + w];
+        uint32_t x = t;
+        x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+        x ^= carry;
+        if (__popc(t) & 1) carry = ~carry;
+        uint32_t f = x | orb[r * pw + w];
+        while (f) {
+          const int bq = __ffs(f) - 1; f &= f - 1;
+          const int col = c.x0 + w * 32 + bq;
+          if (col <= c.x1) filled[(size_t)(r0 + r) * W + col] = 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void sticky_status_kernel(const ExState* st, int32_t* status) { if (st->overflow) *status |= 1; }
 __global__ void reset_state_kernel(ExState* st, int keep_fog) {
   st->n_cont = 0; st->cursor = 0; st->n_rays = 0; st->chosen = -1;
   if (!keep_fog) { st->skip_fog = 0; st->overflow = 0; st->n_front = 0; }
@@ -731,7 +811,8 @@ struct Ws {       // carved from the caller's workspace
 constexpr int WIN_MAX = 512;
 constexpr int CHAIN_CAP = 1 << 20, RAYS_CAP = 1 << 16, MAXF = 4096;
 
-size_t carve(Ws* w, uint8_t* base, int G) {
+constexpr int HOLES_MAXC = 1 << 16;   // fill_small_holes sees sensor speckle: many more (tiny) contours than a map does
+size_t carve(Ws* w, uint8_t* base, int G, int maxc = EX_MAXC) {
   size_t o = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base ? base + o : nullptr; o += (bytes + 255) & ~(size_t)255; return p; };
   const size_t n = (size_t)G * G, wn = (size_t)WIN_MAX * WIN_MAX;
@@ -748,7 +829,7 @@ size_t carve(Ws* w, uint8_t* base, int G) {
   p = take(n); if (w) w->hashole = p;
   p = take(n * 4); if (w) w->Lfg = (int*)p;
   p = take(n * 4); if (w) w->Lbg = (int*)p;
-  p = take(sizeof(Contour) * EX_MAXC); if (w) w->cont = (Contour*)p;
+  p = take(sizeof(Contour) * (size_t)maxc); if (w) w->cont = (Contour*)p;
   p = take(sizeof(int2) * (size_t)CHAIN_CAP); if (w) w->chain = (int2*)p;
   p = take(sizeof(int4) * (size_t)RAYS_CAP); if (w) w->rays = (int4*)p;
   p = take(sizeof(double) * EX_MAXC); if (w) w->dist = (double*)p;
@@ -895,5 +976,47 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   if (rc) return rc;
   VLFM_CHECK_LAUNCH("vlfm_explore_update");
   count_launch(40);
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_holes_workspace_bytes(int H, int W, size_t* bytes) {
+  if (!bytes || H < 1 || W < 1) { set_error("vlfm_holes_workspace_bytes: bad argument"); return VLFM_E_INVALID; }
+  int G = H > W ? H : W;
+  *bytes = carve(nullptr, nullptr, G, HOLES_MAXC);
+  return VLFM_OK;
+}
+
+// fill_small_holes (vlfm/utils/img_utils.py:361-390): d_filled[H,W] := 1 where the reference would write depth 1.0
+extern "C" int vlfm_fill_small_holes(const float* d_depth, int H, int W, double area_thresh, uint8_t* d_filled, void* d_workspace,
+                                     int32_t* d_status, void* stream) {
+  if (!d_depth || !d_filled || !d_workspace || !d_status || H < 1 || W < 1) { set_error("vlfm_fill_small_holes: bad argument"); return VLFM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Ws w;
+  carve(&w, (uint8_t*)d_workspace, H > W ? H : W, HOLES_MAXC);
+  const int n = H * W;
+  uint8_t* mask = w.unexp;                       // scratch planes of the explore workspace layout
+  zero_mask_kernel<<<nblk(n), 256, 0, st>>>(d_depth, mask, n);
+  clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(d_filled, n);
+  reset_state_kernel<<<1, 1, 0, st>>>(w.st, 0);
+  ccl_init_kernel<true><<<nblk(H, 64), 64, 0, st>>>(mask, w.Lfg, W, H);
+  ccl_init_kernel<false><<<nblk(H, 64), 64, 0, st>>>(mask, w.Lbg, W, H);
+  ccl_merge_kernel<true><<<nblk(n), 256, 0, st>>>(mask, w.Lfg, W, H);
+  ccl_merge_kernel<false><<<nblk(n), 256, 0, st>>>(mask, w.Lbg, W, H);
+  ccl_flatten_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, n);
+  ccl_flatten_kernel<<<nblk(n), 256, 0, st>>>(w.Lbg, n);
+  clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(w.outer, n);
+  bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
+  collect_all_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, HOLES_MAXC, w.st);
+  trace_kernel<<<HOLES_MAXC / 64, 64, 0, st>>>(mask, W, H, w.cont, w.chain, w.chain_cap, w.st, 0, w.hashole);
+  static bool cfg = false;
+  const int smem_words = 24 * 1024;             // 96 KB of toggle / outline bit planes per block
+  if (!cfg) {
+    int rc = check_cuda(cudaFuncSetAttribute(fill_small_contours_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_words * 4), "attr(fill_small_contours)");
+    if (rc) return rc; cfg = true;
+  }
+  fill_small_contours_kernel<<<HOLES_MAXC, 256, smem_words * 4, st>>>(w.cont, w.chain, d_filled, W, H, area_thresh, smem_words, w.st);
+  sticky_status_kernel<<<1, 1, 0, st>>>(w.st, d_status);      // sticky: the host may poll it many steps later
+  VLFM_CHECK_LAUNCH("vlfm_fill_small_holes");
+  count_launch(16);
   return VLFM_OK;
 }

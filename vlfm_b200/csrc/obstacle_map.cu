@@ -32,8 +32,9 @@ struct ObstDev {
 };
 
 __device__ __forceinline__ void obst_point(const ObstDev& p, const double* T, uint8_t* obst, int* status,
-                                           int b, int u, int v, float d) {
-  if (d == 0.f) d = 1.f;                                         // :88-89
+                                           int b, int u, int v, float d, const uint8_t* fill) {
+  if (fill) { if (fill[v * p.W + u]) d = 1.f; }                  // fill_small_holes mask (:91, img_utils.py:388)
+  else if (d == 0.f) d = 1.f;                                    // hole_area_thresh == -1 (:88-89)
   float z32 = __fadd_rn(__fmul_rn(d, p.dscale), p.doff);         // :92 float32
   if (!(z32 < p.maxd)) return;                                   // :93
   // get_point_cloud: int64 * float32 -> float64, then / fx  (geometry_utils.py:230-234)
@@ -63,8 +64,9 @@ __device__ __forceinline__ void obst_point(const ObstDev& p, const double* T, ui
 __global__ void __launch_bounds__(256)
 obstacle_scatter_kernel(ObstDev p, const int* __restrict__ slot, uint8_t* __restrict__ obstAll,
                         const float* __restrict__ depth, const double* __restrict__ tf,
-                        int* __restrict__ status) {
+                        int* __restrict__ status, const uint8_t* __restrict__ fillAll) {
   const int b = blockIdx.y;
+  const uint8_t* fill = fillAll ? fillAll + (size_t)b * p.H * p.W : nullptr;
   __shared__ double T[16];
   if (threadIdx.x < 16) T[threadIdx.x] = tf[(size_t)b * 16 + threadIdx.x];
   __syncthreads();
@@ -77,15 +79,15 @@ obstacle_scatter_kernel(ObstDev p, const int* __restrict__ slot, uint8_t* __rest
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
       float4 d = __ldg(reinterpret_cast<const float4*>(img) + i);
       int pix = i << 2, v = pix / p.W, u = pix - v * p.W;
-      obst_point(p, T, obst, status, b, u + 0, v, d.x);
-      obst_point(p, T, obst, status, b, u + 1, v, d.y);
-      obst_point(p, T, obst, status, b, u + 2, v, d.z);
-      obst_point(p, T, obst, status, b, u + 3, v, d.w);
+      obst_point(p, T, obst, status, b, u + 0, v, d.x, fill);
+      obst_point(p, T, obst, status, b, u + 1, v, d.y, fill);
+      obst_point(p, T, obst, status, b, u + 2, v, d.z, fill);
+      obst_point(p, T, obst, status, b, u + 3, v, d.w, fill);
     }
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       int v = i / p.W, u = i - v * p.W;
-      obst_point(p, T, obst, status, b, u, v, __ldg(img + i));
+      obst_point(p, T, obst, status, b, u, v, __ldg(img + i), fill);
     }
   }
 }
@@ -159,7 +161,7 @@ using namespace vlfm;
 
 extern "C" int vlfm_obstacle_update(const VlfmObstacleParams* p, int batch, const int32_t* d_slot,
                                     uint8_t* d_obst, uint8_t* d_nav, const float* d_depth,
-                                    const double* d_tf, int32_t* d_status, void* stream) {
+                                    const double* d_tf, const uint8_t* d_hole_fill, int32_t* d_status, void* stream) {
   if (!p || !d_obst || !d_nav || !d_depth || !d_tf || !d_status) { set_error("vlfm_obstacle_update: null argument"); return VLFM_E_INVALID; }
   if (batch <= 0) return VLFM_OK;
   if (p->kernel < 1 || p->kernel > DT_MAXK || (p->kernel & 1) == 0 || batch > 65535) {
@@ -173,7 +175,7 @@ extern "C" int vlfm_obstacle_update(const VlfmObstacleParams* p, int batch, cons
   int n4 = (p->H * p->W + 3) / 4;
   int bx = (n4 + 255) / 256;
   if (bx > 1184) bx = 1184;
-  obstacle_scatter_kernel<<<dim3(bx, batch), 256, 0, st>>>(d, d_slot, d_obst, d_depth, d_tf, d_status);
+  obstacle_scatter_kernel<<<dim3(bx, batch), 256, 0, st>>>(d, d_slot, d_obst, d_depth, d_tf, d_status, d_hole_fill);
   VLFM_CHECK_LAUNCH("obstacle_scatter_kernel");
   int side = d.full ? d.G : (2 * d.half + 1 + 16);
   int tiles = ((side + DT_COLS - 1) / DT_COLS) * ((side + DT_ROWS - 1) / DT_ROWS);

@@ -46,14 +46,24 @@ class ObstacleMap(BaseMap):
         self._dev_tf = torch.empty((16,), dtype=torch.float64, device=self.device)
         self._ev: Optional[torch.cuda.Event] = None
         self._explore_impl = None
+        self._fill = None
+
+    def _check_fill(self) -> None:
+        # fill_small_holes reports scratch exhaustion (> 65536 borders or > 1M border points in one depth image) through a
+        # sticky device flag; it is read wherever the host synchronises anyway
+        if self._fill is not None and int(self._fill_status.item()) != 0:
+            self._fill_status.zero_()
+            raise _lib.VlfmError("fill_small_holes: a device scratch buffer overflowed (too many contours in the depth image)")
 
     # ---- numpy views
     @property
     def _map(self) -> np.ndarray:
+        self._check_fill()
         return self._obst[0].cpu().numpy().astype(bool)
 
     @property
     def _navigable_map(self) -> np.ndarray:
+        self._check_fill()
         return self._nav[0].cpu().numpy().astype(np.int64)  # the reference's is int64 0/1 (:105-109)
 
     @property
@@ -64,6 +74,7 @@ class ObstacleMap(BaseMap):
     @property
     def _frontiers_px(self) -> np.ndarray:
         if self._front_cache is None:
+            self._check_fill()
             self._front_cache = self._explore_impl.fetch_frontiers_px()
         return self._front_cache
 
@@ -104,10 +115,6 @@ class ObstacleMap(BaseMap):
         """obstacle_map.py:55-153."""
         with torch.cuda.device(self.device):
             if update_obstacles:
-                if self._hole_area_thresh != -1:
-                    raise NotImplementedError(
-                        "fill_small_holes with a finite hole_area_thresh (img_utils.py:361-390) is not on the GPU "
-                        "path yet; construct ObstacleMap(hole_area_thresh=-1) (see DESIGN.md, out-of-scope list)")
                 if depth.ndim == 3:
                     depth = depth.squeeze(2)
                 self._upload(depth, tf_camera_to_episodic)
@@ -119,8 +126,20 @@ class ObstacleMap(BaseMap):
                                         float(np.float32(max_depth)), float(fx), float(fy),
                                         float(self._min_height), float(self._max_height), self._kernel,
                                         0 if self._nav_valid else 1, half)
+                fill = None
+                if self._hole_area_thresh != -1:          # fill_small_holes (img_utils.py:361-390) on the device
+                    if self._fill is None or self._fill.shape != (1, h, w):
+                        nb = ctypes.c_size_t(0)
+                        _lib.check(self.lib.vlfm_holes_workspace_bytes(h, w, ctypes.byref(nb)), "vlfm_holes_workspace_bytes")
+                        self._fill = torch.zeros((1, h, w), dtype=torch.uint8, device=self.device)
+                        self._fill_ws = torch.zeros((nb.value + 3) // 4, dtype=torch.int32, device=self.device)
+                        self._fill_status = torch.zeros(1, dtype=torch.int32, device=self.device)
+                    rc = self.lib.vlfm_fill_small_holes(_lib.ptr(self._dev_depth), h, w, float(self._hole_area_thresh), _lib.ptr(self._fill),
+                                                        _lib.ptr(self._fill_ws), _lib.ptr(self._fill_status), _lib.stream_ptr())
+                    _lib.check(rc, "vlfm_fill_small_holes")
+                    fill = self._fill
                 rc = self.lib.vlfm_obstacle_update(ctypes.byref(p), 1, None, _lib.ptr(self._obst), _lib.ptr(self._nav),
-                                                   _lib.ptr(self._dev_depth), _lib.ptr(self._dev_tf),
+                                                   _lib.ptr(self._dev_depth), _lib.ptr(self._dev_tf), _lib.ptr(fill),
                                                    _lib.ptr(self._status), _lib.stream_ptr())
                 _lib.check(rc, "vlfm_obstacle_update")
                 self._nav_valid = True
