@@ -200,6 +200,17 @@ int vlfm_swin_window_attention(const void* d_qkv, const float* d_qkv_bias, const
                                int H, int W, int C, int heads, int shift, void* stream);
 int vlfm_swin_patch_merge(const float* d_x, float* d_out, int B, int H, int W, int C, void* stream);
 
+/* ------------------------------------- GroundingDINO feature enhancer / decoder ---- */
+/* Multi-scale deformable attention sampling (replaces groundingdino's third-party ms_deform_attn_cuda.cu, reached from
+ * vlfm/vlm/grounding_dino.py:61-67).  d_value [B,S,heads,hd] fp32 or fp16 (S = sum H_l*W_l, levels concatenated),
+ * d_loc [B,Q,heads,levels,points,2] fp32 normalised (x,y), d_attw [B,Q,heads,levels,points] fp32 (already soft-maxed)
+ * -> d_out [B,Q,heads*hd] fp32.  Bilinear taps with zero padding, align_corners=False.  h_shapes_hw: HOST int32
+ * [levels*2] = (H_l, W_l). */
+int vlfm_msda_forward(const void* d_value, int value_is_f16, const float* d_loc, const float* d_attw, float* d_out, int B, int S,
+                      int Q, int heads, int hd, int levels, int points, const int32_t* h_shapes_hw, void* stream);
+/* fp32 -> fp16 (round to nearest even) staging of GEMM operands. */
+int vlfm_cast_f32_f16(const float* d_in, void* d_out16, long n, void* stream);
+
 /* ------------------------------------------------------------- explore half ---- */
 /* Replaces ObstacleMap.update_map's explore half (vlfm/mapping/obstacle_map.py:114-153) and _get_frontiers
  * (:155-169) including the two third-party frontier_exploration functions they call (spec:

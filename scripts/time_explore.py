@@ -5,8 +5,8 @@ from vlfm_b200.mapping.obstacle_map import ObstacleMap
 from vlfm_b200.utils.synthetic import focal_from_hfov, trajectory
 from oracle.obstacle_map_oracle import ObstacleMapOracle
 fx = focal_from_hfov(640)
-g = ObstacleMap(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=-1, size=1000)
-o = ObstacleMapOracle(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=-1, size=1000)
+g = ObstacleMap(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=int(os.environ.get("HOLE", "100000")), size=1000)
+o = ObstacleMapOracle(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=int(os.environ.get("HOLE", "100000")), size=1000)
 fr = trajectory(5, 40, bound_m=12.0)
 for f in fr[:8]: g.update_map(f.depth, f.tf, 0.5, 5.0, fx, fx, np.deg2rad(79))
 torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -59,3 +59,50 @@ def test_predict_surface_and_outputs(pair):
 
     back = ObjectDetections.from_json(j, image_source=img)
     assert back.num_detections == det.num_detections
+
+
+@pytest.mark.parametrize("f16", [False, True])
+def test_msda_kernel_vs_torch_grid_sample(f16):
+    """vlfm_msda_forward against transformers' pure-PyTorch MultiScaleDeformableAttention (fp32 grid_sample).
+    Tolerance 2e-5 for fp32 values (same taps, different summation order), 2e-3 for fp16 values."""
+    from transformers.models.grounding_dino.modeling_grounding_dino import MultiScaleDeformableAttention
+    from vlfm_b200.vlm.gdino_accel import TcMSDA
+
+    torch.manual_seed(0)
+    shapes = [(60, 80), (30, 40), (15, 20), (8, 10)]
+    b, heads, hd, q, pts = 2, 8, 32, 777, 4
+    s = sum(h * w for h, w in shapes)
+    value = torch.randn(b, s, heads, hd, device="cuda")
+    loc = torch.rand(b, q, heads, len(shapes), pts, 2, device="cuda") * 1.3 - 0.15      # some samples fall outside: zero padding
+    loc[0, 0, 0, 0, 0] = torch.tensor([0.5 / 80, 0.5 / 60])                             # exact pixel centre
+    attw = torch.softmax(torch.randn(b, q, heads, len(shapes) * pts, device="cuda"), -1).view(b, q, heads, len(shapes), pts)
+    sp = torch.tensor(shapes, device="cuda")
+    start = torch.cat([sp.new_zeros(1), (sp[:, 0] * sp[:, 1]).cumsum(0)[:-1]])
+    ref = MultiScaleDeformableAttention()(value, sp, shapes, start, loc, attw, 64)
+    got = TcMSDA()(value.half() if f16 else value, sp, shapes, start, loc, attw, 64)
+    torch.cuda.synchronize()
+    err = float((got - ref).abs().max())
+    print("msda max abs err", err)
+    assert got.shape == ref.shape and err <= (2e-3 if f16 else 2e-5)
+
+
+def test_tc_linear_and_cast_vs_torch():
+    from vlfm_b200.vlm.gdino_accel import TcLinear, cast_f16
+
+    torch.manual_seed(1)
+    x = torch.randn(3, 1001, 256, device="cuda")
+    assert torch.equal(cast_f16(x.reshape(-1)[:1001 * 3 + 2].contiguous()), x.reshape(-1)[:1001 * 3 + 2].half())   # tail path
+    for n_out in (384, 2048, 128):
+        lin = torch.nn.Linear(256, n_out).cuda()
+        ref = lin(x)
+        got = TcLinear(lin)(x)
+        torch.cuda.synchronize()
+        # fp16 operands (11-bit mantissa), fp32 accumulate over K=256: |err| <~ 2^-11 * sum|x_k w_k|
+        err = float((got - ref).abs().max())
+        print("TcLinear", n_out, "max abs err", err)
+        assert got.shape == ref.shape and err <= 5e-3
+
+
+def test_accelerated_primitives_are_installed(pair):
+    _, g = pair
+    assert g.accel["msda"] == 12 and g.accel["linear"] > 150, g.accel      # 6 encoder + 6 decoder deformable attentions

@@ -63,42 +63,65 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
-// init: every pixel of the set points at the first pixel of its horizontal run (one thread per row), so that the
-// union phase only has to stitch runs of adjacent rows instead of every pixel pair.
-template <bool FG>
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int* __restrict__ L, int W, int H) {
-  for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < H; y += gridDim.x * blockDim.x) {
-    int run = -1;
+// init: every pixel points at the first pixel of its horizontal run, for the foreground (8-connected) and the background
+// (4-connected) label arrays at once, so that the union phase only has to stitch runs of adjacent rows.  One warp per
+// row, 32 cells per ballot; the ballot word doubles as the packed bitmap the border tracer reads.  Block 0 also resets
+// the per-image bookkeeping.
+__global__ void __launch_bounds__(256)
+ccl_init2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __restrict__ Lbg, uint32_t* __restrict__ bits, int W, int H,
+                 int pw, ExState* st, int keep_fog) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->n_cont = 0; st->cursor = 0; st->n_rays = 0; st->chosen = -1;
+    if (!keep_fog) { st->skip_fog = 0; st->overflow = 0; st->n_front = 0; }
+  }
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < H; y += gridDim.x * wpb) {
     const uint8_t* row = img + (size_t)y * W;
-    int* lr = L + (size_t)y * W;
-    for (int x = 0; x < W; ++x) {
-      const bool in = (row[x] != 0) == FG;
-      if (in) { if (run < 0) run = y * W + x; lr[x] = run; } else { run = -1; lr[x] = -1; }
+    const int base = y * W;
+    int carry_fg = -1, carry_bg = -1;                 // column where a run that reaches the chunk boundary started
+    const unsigned below = (1u << lane) - 1;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+      const int x = x0 + lane;
+      const bool valid = x < W;
+      const bool fg = valid && row[x] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, fg);
+      if (lane == 0) bits[y * pw + (x0 >> 5)] = m;
+      const unsigned zf = ~m & below, zb = m & below;  // cells below this lane that end a fg / bg run
+      const int sf = zf ? x0 + 32 - __clz(zf) : (carry_fg >= 0 ? carry_fg : x0);
+      const int sb = zb ? x0 + 32 - __clz(zb) : (carry_bg >= 0 ? carry_bg : x0);
+      if (valid) { Lfg[base + x] = fg ? base + sf : -1; Lbg[base + x] = fg ? -1 : base + sb; }
+      const int sf31 = __shfl_sync(0xffffffffu, sf, 31), sb31 = __shfl_sync(0xffffffffu, sb, 31);
+      carry_fg = (m >> 31) ? sf31 : -1;
+      carry_bg = (m >> 31) ? -1 : sb31;
     }
   }
 }
-// stitch: a pixel unions with the row above only where a NEW overlap between runs begins
-template <bool FG>
-__global__ void ccl_merge_kernel(const uint8_t* __restrict__ img, int* __restrict__ L, int W, int H) {
+// stitch: a pixel unions with the row above only where a NEW overlap between runs begins; also clears the per-label flags
+__global__ void ccl_merge2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __restrict__ Lbg, uint8_t* __restrict__ outer,
+                                  uint8_t* __restrict__ hashole, int W, int H) {
   const int n = W * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (((img[i] != 0) == FG) == false) continue;
+    outer[i] = 0;
+    if (hashole) hashole[i] = 0;
     const int y = i / W, x = i - y * W;
     if (y == 0) continue;
-    const bool west = x > 0 && ((img[i - 1] != 0) == FG);
-    const bool north = (img[i - W] != 0) == FG;
-    const bool nwest = x > 0 && ((img[i - W - 1] != 0) == FG);
+    const bool c = img[i] != 0;
+    const bool west = x > 0 && ((img[i - 1] != 0) == c);
+    const bool north = (img[i - W] != 0) == c;
+    const bool nwest = x > 0 && ((img[i - W - 1] != 0) == c);
+    int* L = c ? Lfg : Lbg;
     if (north && (!west || !nwest)) uf_union(L, i, i - W);
-    if (FG) {   // foreground is 8-connected: diagonal contacts not already implied by a north contact
+    if (c) {   // foreground is 8-connected: diagonal contacts not already implied by a north contact
       const bool neast = x + 1 < W && img[i - W + 1] != 0;
       if (nwest && !north && !west) uf_union(L, i, i - W - 1);
       if (neast && !north) uf_union(L, i, i - W + 1);
     }
   }
 }
-__global__ void ccl_flatten_kernel(int* __restrict__ L, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    if (L[i] >= 0) L[i] = uf_find(L, i);
+__global__ void ccl_flatten2_kernel(int* __restrict__ Lfg, int* __restrict__ Lbg, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (Lfg[i] >= 0) Lfg[i] = uf_find(Lfg, i); else Lbg[i] = uf_find(Lbg, i);
+  }
 }
 // background components touching the image frame are the "outer" background (the frame is background for Suzuki)
 __global__ void bg_outer_kernel(const int* __restrict__ Lbg, uint8_t* __restrict__ outer, int W, int H) {
@@ -139,12 +162,15 @@ __global__ void __launch_bounds__(1024) sort_roots_kernel(Contour* __restrict__ 
   __shared__ int keys[EX_MAXC];
   int n = st->n_cont;
   if (n > EX_MAXC) n = EX_MAXC;
-  if (threadIdx.x == 0) st->n_cont = n;
-  for (int i = threadIdx.x; i < EX_MAXC; i += 1024) keys[i] = i < n ? cont[i].start : -1;
   __syncthreads();
-  for (int k = 2; k <= EX_MAXC; k <<= 1)
+  if (threadIdx.x == 0) st->n_cont = n;
+  int P = 2;
+  while (P < n) P <<= 1;                              // bitonic network over the next power of two only
+  for (int i = threadIdx.x; i < P; i += 1024) keys[i] = i < n ? cont[i].start : -1;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < EX_MAXC; i += 1024) {
+      for (int i = threadIdx.x; i < P; i += 1024) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const int a = keys[i], b = keys[ixj];
@@ -164,18 +190,38 @@ __constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 __device__ __forceinline__ bool fg_at(const uint8_t* img, int W, int H, int x, int y) {
   return (unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H && img[y * W + x] != 0;
 }
-__device__ __forceinline__ int dir_index(int dx, int dy) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) if (c_dx[i] == dx && c_dy[i] == dy) return i;
-  return 0;
+// three-cell window (x-1, x, x+1) of bitmap row y as bits 0..2; cells outside the image are background
+__device__ __forceinline__ unsigned row3(const uint32_t* __restrict__ bits, int pw, int W, int H, int x, int y) {
+  if ((unsigned)y >= (unsigned)H) return 0;
+  const uint32_t* r = bits + (size_t)y * pw;
+  const int wi = x >> 5, b = x & 31;
+  const uint32_t w = __ldg(r + wi);
+  unsigned out = ((w >> b) & 1u) << 1;
+  if (b > 0) out |= (w >> (b - 1)) & 1u; else if (wi > 0) out |= __ldg(r + wi - 1) >> 31;
+  if (b < 31) out |= ((w >> (b + 1)) & 1u) << 2; else if (x + 1 < W) out |= (__ldg(r + wi + 1) & 1u) << 2;
+  return (x + 1 < W) ? out : (out & 3u);
 }
-// Suzuki-Abe steps 3.1-3.5 (oracle/contours.py::_trace); WRITE=false only counts.
+// 8-neighbourhood of (x, y) as a mask indexed like c_dx / c_dy (clockwise from west)
+__device__ __forceinline__ unsigned nb8(const uint32_t* __restrict__ bits, int pw, int W, int H, int x, int y) {
+  const unsigned up = row3(bits, pw, W, H, x, y - 1), mid = row3(bits, pw, W, H, x, y), dn = row3(bits, pw, W, H, x, y + 1);
+  return (mid & 1u) | ((up & 1u) << 1) | (((up >> 1) & 1u) << 2) | (((up >> 2) & 1u) << 3) | (((mid >> 2) & 1u) << 4) |
+         (((dn >> 2) & 1u) << 5) | (((dn >> 1) & 1u) << 6) | ((dn & 1u) << 7);
+}
+__device__ __forceinline__ int dir_index(int dx, int dy) {
+  // inverse of c_dx / c_dy for unit steps: (-1,0)->0 (-1,-1)->1 (0,-1)->2 (1,-1)->3 (1,0)->4 (1,1)->5 (0,1)->6 (-1,1)->7
+  const int t = (dy + 1) * 3 + (dx + 1);               // 0..8, row-major over dy, dx
+  return (0x56740321 >> ((t > 4 ? t - 1 : t) * 4)) & 7;
+}
+// Suzuki-Abe steps 3.1-3.5 (oracle/contours.py::_trace) on the packed bitmap; WRITE=false only counts.
 template <bool WRITE>
-__device__ int trace_border(const uint8_t* img, int W, int H, int x0, int y0, int2* out, Contour* c, int ed = 0) {
+__device__ int trace_border(const uint32_t* __restrict__ bits, int pw, int W, int H, int x0, int y0, int2* out, Contour* c, int ed = 0) {
   int fx = -1, fy = -1;
-  for (int k = 1; k < 8; ++k) {            // 3.1 clockwise from the (zero) entry pixel: west for outer, east for hole borders
-    const int d = (ed + k) & 7;
-    if (fg_at(img, W, H, x0 + c_dx[d], y0 + c_dy[d])) { fx = x0 + c_dx[d]; fy = y0 + c_dy[d]; break; }
+  {
+    const unsigned nb = nb8(bits, pw, W, H, x0, y0);
+    for (int k = 1; k < 8; ++k) {          // 3.1 clockwise from the (zero) entry pixel: west for outer, east for hole borders
+      const int d = (ed + k) & 7;
+      if ((nb >> d) & 1u) { fx = x0 + c_dx[d]; fy = y0 + c_dy[d]; break; }
+    }
   }
   int minx = x0, maxx = x0, miny = y0, maxy = y0, n = 0;
   if (fx < 0) {
@@ -185,10 +231,12 @@ __device__ int trace_border(const uint8_t* img, int W, int H, int x0, int y0, in
     int x2 = fx, y2 = fy, x3 = x0, y3 = y0;
     while (true) {
       const int d0 = dir_index(x2 - x3, y2 - y3);
+      const unsigned nb = nb8(bits, pw, W, H, x3, y3);
+      // 3.3 counter-clockwise, starting after (x2,y2): first set bit of nb rotated so that d0-1 is bit 7 ... d0-8 is bit 0
       int x4 = x3, y4 = y3;
-      for (int k = 1; k <= 8; ++k) {       // 3.3 counter-clockwise, starting after (x2,y2)
+      for (int k = 1; k <= 8; ++k) {
         const int di = (d0 - k) & 7;
-        if (fg_at(img, W, H, x3 + c_dx[di], y3 + c_dy[di])) { x4 = x3 + c_dx[di]; y4 = y3 + c_dy[di]; break; }
+        if ((nb >> di) & 1u) { x4 = x3 + c_dx[di]; y4 = y3 + c_dy[di]; break; }
       }
       if (WRITE) out[n] = make_int2(x3, y3);
       ++n;
@@ -203,17 +251,17 @@ __device__ int trace_border(const uint8_t* img, int W, int H, int x0, int y0, in
 }
 // mode 0: trace every contour; 1: only when more than one contour exists (component selection); 2: skip components
 // that enclose a hole (their filled polygon contains a zero cell, so F1 can never absorb them)
-__global__ void trace_kernel(const uint8_t* __restrict__ img, int W, int H, Contour* __restrict__ cont, int2* __restrict__ chain,
+__global__ void trace_kernel(const uint32_t* __restrict__ bits, int pw, int W, int H, Contour* __restrict__ cont, int2* __restrict__ chain,
                              int cap, ExState* st, int mode, const uint8_t* __restrict__ hashole) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st->n_cont || c >= gridDim.x * blockDim.x) return;
   const int s = cont[c].start, y0 = s / W, x0 = s - y0 * W;
   if ((mode == 1 && st->n_cont <= 1) || (mode == 2 && hashole[s])) { cont[c].off = 0; cont[c].len = 0; return; }
-  const int n = trace_border<false>(img, W, H, x0, y0, nullptr, nullptr, cont[c].ed);
+  const int n = trace_border<false>(bits, pw, W, H, x0, y0, nullptr, nullptr, cont[c].ed);
   const int off = atomicAdd(&st->cursor, n);
   if (off + n > cap) { st->overflow = 1; cont[c].off = 0; cont[c].len = 0; return; }
   cont[c].off = off; cont[c].len = n;
-  trace_border<true>(img, W, H, x0, y0, chain + off, &cont[c], cont[c].ed);
+  trace_border<true>(bits, pw, W, H, x0, y0, chain + off, &cont[c], cont[c].ed);
 }
 
 // CHAIN_APPROX_SIMPLE: point i of a chain is kept iff the step into it differs from the step out of it
@@ -346,33 +394,41 @@ __global__ void fog_masks_kernel(const uint8_t* __restrict__ cone, const uint8_t
   }
 }
 
-// R3/R4: obstacle contours -> ray list (x0,y0,x1,y1 in window coordinates)
-__global__ void rays_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, int4* __restrict__ rays, int cap, int sx, int sy,
-                            int ox, int oy, double heading_deg, double ray_len, ExState* st) {
-  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+// CHAIN_APPROX_SIMPLE vertex list of every contour, compacted in order (one warp per contour)
+__global__ void simple_vertices_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, int2* __restrict__ sv,
+                                       int* __restrict__ nsv, const ExState* st) {
+  const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (ci >= st->n_cont) return;
   const Contour c = cont[ci];
   const int2* p = chain + c.off;
-  const int n = c.len;
-  // cv2.isContourConvex on the SIMPLE vertices (oracle/contours.py::is_convex)
-  int nv = 0, i_last = -1, i_prev = -1;
-  for (int i = 0; i < n; ++i) if (simple_vertex(p, n, i)) { ++nv; i_prev = i_last; i_last = i; }
-  bool convex = nv > 0;
-  if (convex) {
-    if (nv == 1) i_prev = i_last;
-    long long px_ = p[i_prev].x, py_ = p[i_prev].y, cx = p[i_last].x, cy = p[i_last].y;   // p[n-2], p[n-1] of the vertex list
-    long long dx0 = cx - px_, dy0 = cy - py_;
-    int orient = 0;
-    for (int i = 0; i < n && convex; ++i) {
-      if (!simple_vertex(p, n, i)) continue;
-      px_ = cx; py_ = cy; cx = p[i].x; cy = p[i].y;
-      const long long dx = cx - px_, dy = cy - py_;
-      const long long dxdy0 = dx * dy0, dydx0 = dy * dx0;
-      orient |= dydx0 > dxdy0 ? 1 : (dydx0 < dxdy0 ? 2 : 3);
-      if (orient == 3) convex = false;
-      dx0 = dx; dy0 = dy;
-    }
+  int2* o = sv + c.off;
+  int cnt = 0;
+  for (int b = 0; b < c.len; b += 32) {
+    const int i = b + lane;
+    const bool keep = i < c.len && simple_vertex(p, c.len, i);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) o[cnt + __popc(m & ((1u << lane) - 1))] = p[i];
+    cnt += __popc(m);
   }
+  if (lane == 0) nsv[ci] = cnt;
+}
+// R3/R4: obstacle contours -> ray list (x0,y0,x1,y1 in window coordinates); one warp per contour
+__global__ void rays_kernel(const Contour* __restrict__ cont, const int2* __restrict__ sv, const int* __restrict__ nsv, int4* __restrict__ rays,
+                            int cap, int sx, int sy, int ox, int oy, double heading_deg, double ray_len, ExState* st) {
+  const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (ci >= st->n_cont) return;
+  const int2* v = sv + cont[ci].off;
+  const int nv = nsv[ci];
+  // cv2.isContourConvex on the SIMPLE vertices (oracle/contours.py::is_convex): every turn has the same strict sign
+  int orient = 0;
+  for (int j = lane; j < nv; j += 32) {
+    const int2 a = v[(j + 2 * nv - 2) % nv], b = v[(j + nv - 1) % nv], c = v[j];
+    const long long dx0 = b.x - a.x, dy0 = b.y - a.y, dx = c.x - b.x, dy = c.y - b.y;
+    const long long dxdy0 = dx * dy0, dydx0 = dy * dx0;
+    orient |= dydx0 > dxdy0 ? 1 : (dydx0 < dxdy0 ? 2 : 3);
+  }
+  orient = __reduce_or_sync(0xffffffffu, orient);
+  const bool convex = nv > 0 && orient != 3;
   auto emit = [&](int qx, int qy) {
     const double ang = atan2((double)(qy - sy), (double)(qx - sx));
     // astype(np.int32) truncates toward zero in GRID coordinates (the window origin is subtracted afterwards)
@@ -381,21 +437,26 @@ __global__ void rays_kernel(const Contour* __restrict__ cont, const int2* __rest
     if (k < cap) rays[k] = make_int4(qx, qy, ex, ey); else st->overflow = 1;
   };
   if (convex) {
-    // _extreme_bearing_points: the heading in DEGREES is used as radians, as in the restated package
+    // _extreme_bearing_points: the heading in DEGREES is used as radians, as in the restated package; np.argmin /
+    // np.argmax return the FIRST extreme vertex
     const double cs = cos(-heading_deg), sn = sin(-heading_deg);
-    double amin = 1e300, amax = -1e300; int imin = -1, imax = -1;
-    for (int i = 0; i < n; ++i) {
-      if (!simple_vertex(p, n, i)) continue;
-      const double qx = (double)(p[i].x - sx), qy = (double)(p[i].y - sy);
+    double amin = 1e300, amax = -1e300; int imin = 0x7fffffff, imax = 0x7fffffff;
+    for (int j = lane; j < nv; j += 32) {
+      const double qx = (double)(v[j].x - sx), qy = (double)(v[j].y - sy);
       const double rx = qx * cs + qy * sn, ry = qx * (-sn) + qy * cs;
       const double a = atan2(ry, rx);
-      if (a < amin) { amin = a; imin = i; }
-      if (a > amax) { amax = a; imax = i; }
+      if (a < amin) { amin = a; imin = j; }
+      if (a > amax) { amax = a; imax = j; }
     }
-    emit(p[imin].x, p[imin].y);
-    emit(p[imax].x, p[imax].y);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double a1 = __shfl_xor_sync(0xffffffffu, amin, o), a2 = __shfl_xor_sync(0xffffffffu, amax, o);
+      const int i1 = __shfl_xor_sync(0xffffffffu, imin, o), i2 = __shfl_xor_sync(0xffffffffu, imax, o);
+      if (a1 < amin || (a1 == amin && i1 < imin)) { amin = a1; imin = i1; }
+      if (a2 > amax || (a2 == amax && i2 < imax)) { amax = a2; imax = i2; }
+    }
+    if (lane == 0) { emit(v[imin].x, v[imin].y); emit(v[imax].x, v[imax].y); }
   } else {
-    for (int i = 0; i < n; ++i) if (simple_vertex(p, n, i)) emit(p[i].x, p[i].y);
+    for (int j = lane; j < nv; j += 32) emit(v[j].x, v[j].y);
   }
 }
 
@@ -654,14 +715,23 @@ __device__ void emit_midpoint(const int2* p, int n, int a, int b, int a2, int b2
   const int k = st->n_front;
   if (k < maxf) { out[2 * k] = u.x + t * (v.x - u.x); out[2 * k + 1] = u.y + t * (v.y - u.y); st->n_front = k + 1; } else st->overflow = 1;
 }
-__global__ void frontier_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, const uint8_t* __restrict__ nav,
-                                const uint8_t* __restrict__ ex2, int W, int H, double* __restrict__ out, int maxf, ExState* st) {
+// F3 "bad" test of every traced border point at once (the serial walk below only reads the flags)
+__global__ void bad_flags_kernel(const int2* __restrict__ chain, const uint8_t* __restrict__ nav, const uint8_t* __restrict__ ex2, int W, int H,
+                                 uint8_t* __restrict__ flags, const ExState* st) {
+  const int n = st->cursor;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    flags[i] = blur_zero(nav, ex2, W, H, chain[i].x, chain[i].y) ? 1 : 0;
+}
+__global__ void frontier_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, const uint8_t* __restrict__ flags,
+                                double* __restrict__ out, int maxf, ExState* st) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   st->n_front = 0;
   for (int ci = 0; ci < st->n_cont; ++ci) {
     const int2* p = chain + cont[ci].off;
+    const uint8_t* fl = flags + cont[ci].off;
     const int n = cont[ci].len, m = 2 * n;              // interpolated sequence q has 2n entries
-    auto bad = [&](int k) { const int2 q = p[((k + 1) >> 1) % n]; return blur_zero(nav, ex2, W, H, q.x, q.y); };
+    if (n == 0) continue;
+    auto bad = [&](int k) { return fl[((k + 1) >> 1) % n] != 0; };
     // bad indices split q; piece 0 = [0, b0), piece j = [b_{j-1}, b_j) minus its first element, last = [b_last, m)
     int nbad = 0, first_bad = -1, last_bad = -1;
     for (int k = 0; k < m; ++k) if (bad(k)) { if (first_bad < 0) first_bad = k; last_bad = k; ++nbad; }
@@ -729,60 +799,63 @@ __global__ void collect_all_kernel(const int* __restrict__ Lfg, const int* __res
 // shared memory, processed in row bands when the box is tall
 __global__ void __launch_bounds__(256)
 fill_small_contours_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, uint8_t* __restrict__ filled, int W, int H,
-                           double area_thresh, int smem_words, const ExState* st) {
+                           double area_thresh, int smem_words, int maxc, const ExState* st) {
   extern __shared__ uint32_t fs_smem[];
-  const int ci = blockIdx.x;
-  if (ci >= st->n_cont) return;
-  const Contour c = cont[ci];
-  if (c.len == 0) return;
-  const int2* p = chain + c.off;
   __shared__ long long s_a2;
-  if (threadIdx.x == 0) s_a2 = 0;
-  __syncthreads();
-  long long acc = 0;
-  for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
-    const int2 q = p[i == 0 ? c.len - 1 : i - 1], b = p[i];
-    acc += (long long)q.x * b.y - (long long)b.x * q.y;
-  }
-  atomicAdd(reinterpret_cast<unsigned long long*>(&s_a2), (unsigned long long)acc);
-  __syncthreads();
-  if (!(fabs((double)s_a2 * 0.5) < area_thresh)) return;
-  const int bw = c.x1 - c.x0 + 2, pw = (bw + 31) / 32;           // +1 column for the toggle right of the last cell
-  const int band = smem_words / (2 * pw);
-  for (int r0 = c.y0; r0 <= c.y1; r0 += band) {
-    const int rows = min(band, c.y1 - r0 + 1);
-    uint32_t* tog = fs_smem; uint32_t* orb = fs_smem + rows * pw;
-    for (int i = threadIdx.x; i < 2 * rows * pw; i += blockDim.x) fs_smem[i] = 0;
+  const int nc = min(st->n_cont, maxc);
+  for (int ci = blockIdx.x; ci < nc; ci += gridDim.x) {
+    const Contour c = cont[ci];
+    if (c.len == 0) continue;
+    const int2* p = chain + c.off;
     __syncthreads();
+    if (threadIdx.x == 0) s_a2 = 0;
+    __syncthreads();
+    long long acc = 0;
     for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
-      const int2 a = p[i], b = p[i + 1 == c.len ? 0 : i + 1];
-      if (a.y >= r0 && a.y < r0 + rows) atomicOr(&orb[(a.y - r0) * pw + ((a.x - c.x0) >> 5)], 1u << ((a.x - c.x0) & 31));
-      if (a.y != b.y) {
-        const int xa = (a.y < b.y ? a.x : b.x) - c.x0, ya = min(a.y, b.y);
-        if (ya >= r0 && ya < r0 + rows) {
-          atomicXor(&tog[(ya - r0) * pw + ((xa + 1) >> 5)], 1u << ((xa + 1) & 31));
-          atomicOr(&orb[(ya - r0) * pw + (xa >> 5)], 1u << (xa & 31));
+      const int2 q = p[i == 0 ? c.len - 1 : i - 1], b = p[i];
+      acc += (long long)q.x * b.y - (long long)b.x * q.y;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_a2), (unsigned long long)acc);
+    __syncthreads();
+    if (!(fabs((double)s_a2 * 0.5) < area_thresh)) continue;
+    if (c.len == 1) { if (threadIdx.x == 0) filled[(size_t)c.y0 * W + c.x0] = 1; continue; }   // speckle: the common case
+    const int bw = c.x1 - c.x0 + 2, pw = (bw + 31) / 32;           // +1 column for the toggle right of the last cell
+    const int band = smem_words / (2 * pw);
+    for (int r0 = c.y0; r0 <= c.y1; r0 += band) {
+      const int rows = min(band, c.y1 - r0 + 1);
+      uint32_t* tog = fs_smem; uint32_t* orb = fs_smem + rows * pw;
+      for (int i = threadIdx.x; i < 2 * rows * pw; i += blockDim.x) fs_smem[i] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
+        const int2 a = p[i], b = p[i + 1 == c.len ? 0 : i + 1];
+        if (a.y >= r0 && a.y < r0 + rows) atomicOr(&orb[(a.y - r0) * pw + ((a.x - c.x0) >> 5)], 1u << ((a.x - c.x0) & 31));
+        if (a.y != b.y) {
+          const int xa = (a.y < b.y ? a.x : b.x) - c.x0, ya = min(a.y, b.y);
+          if (ya >= r0 && ya < r0 + rows) {
+            atomicXor(&tog[(ya - r0) * pw + ((xa + 1) >> 5)], 1u << ((xa + 1) & 31));
+            atomicOr(&orb[(ya - r0) * pw + (xa >> 5)], 1u << (xa & 31));
+          }
         }
       }
-    }
-    __syncthreads();
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-      uint32_t carry = 0;
-      for (int w = 0; w < pw; ++w) {
-        const uint32_t t = tog[r * pw + w];
-        uint32_t x = t;
-        x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
-        x ^= carry;
-        if (__popc(t) & 1) carry = ~carry;
-        uint32_t f = x | orb[r * pw + w];
-        while (f) {
-          const int bq = __ffs(f) - 1; f &= f - 1;
-          const int col = c.x0 + w * 32 + bq;
-          if (col <= c.x1) filled[(size_t)(r0 + r) * W + col] = 1;
+      __syncthreads();
+      for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        uint32_t carry = 0;
+        for (int w = 0; w < pw; ++w) {
+          const uint32_t t = tog[r * pw + w];
+          uint32_t x = t;
+          x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+          x ^= carry;
+          if (__popc(t) & 1) carry = ~carry;
+          uint32_t f = x | orb[r * pw + w];
+          while (f) {
+            const int bq = __ffs(f) - 1; f &= f - 1;
+            const int col = c.x0 + w * 32 + bq;
+            if (col <= c.x1) filled[(size_t)(r0 + r) * W + col] = 1;
+          }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -805,7 +878,8 @@ namespace {
 struct Ws {       // carved from the caller's workspace
   uint8_t *cone, *blocked, *visible, *cut, *newexp, *outer, *grown, *unexp, *ex2, *hashole;
   int *Lfg, *Lbg, *which;
-  Contour* cont; int2* chain; int4* rays; double* dist; uint32_t *tog, *orb; long long* verts; ExState* st;
+  Contour* cont; int2 *chain, *sv; int4* rays; double* dist; uint32_t *tog, *orb, *bits; long long* verts; ExState* st;
+  int* nsv; uint8_t* flags;
   int chain_cap, rays_cap;
 };
 constexpr int WIN_MAX = 512;
@@ -831,11 +905,15 @@ size_t carve(Ws* w, uint8_t* base, int G, int maxc = EX_MAXC) {
   p = take(n * 4); if (w) w->Lbg = (int*)p;
   p = take(sizeof(Contour) * (size_t)maxc); if (w) w->cont = (Contour*)p;
   p = take(sizeof(int2) * (size_t)CHAIN_CAP); if (w) w->chain = (int2*)p;
+  p = take(sizeof(int2) * (size_t)CHAIN_CAP); if (w) w->sv = (int2*)p;
+  p = take((size_t)CHAIN_CAP); if (w) w->flags = p;
+  p = take(sizeof(int) * (size_t)maxc); if (w) w->nsv = (int*)p;
   p = take(sizeof(int4) * (size_t)RAYS_CAP); if (w) w->rays = (int4*)p;
   p = take(sizeof(double) * EX_MAXC); if (w) w->dist = (double*)p;
   const size_t pw = ((size_t)G + 31) / 32;
   p = take(pw * G * 4); if (w) w->tog = (uint32_t*)p;
   p = take(pw * G * 4); if (w) w->orb = (uint32_t*)p;
+  p = take(pw * G * 4); if (w) w->bits = (uint32_t*)p;
   p = take(64 * 2 * 8); if (w) w->verts = (long long*)p;
   p = take(sizeof(ExState)); if (w) w->st = (ExState*)p;
   p = take(64); if (w) w->which = (int*)p;
@@ -847,24 +925,16 @@ inline int nblk(long n, int t = 256) { long b = (n + t - 1) / t; return (int)(b 
 
 // external contours of `img` (W x H): CCL fg/bg, top-level roots in cv2 order, traced chains
 void contours(const Ws& w, const uint8_t* img, int W, int H, cudaStream_t st, int keep_fog, int mode = 0) {
-  const int n = W * H;
-  reset_state_kernel<<<1, 1, 0, st>>>(w.st, keep_fog);
-  ccl_init_kernel<true><<<nblk(H, 64), 64, 0, st>>>(img, w.Lfg, W, H);
-  ccl_init_kernel<false><<<nblk(H, 64), 64, 0, st>>>(img, w.Lbg, W, H);
-  ccl_merge_kernel<true><<<nblk(n), 256, 0, st>>>(img, w.Lfg, W, H);
-  ccl_merge_kernel<false><<<nblk(n), 256, 0, st>>>(img, w.Lbg, W, H);
-  ccl_flatten_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, n);
-  ccl_flatten_kernel<<<nblk(n), 256, 0, st>>>(w.Lbg, n);
-  clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(w.outer, n);
+  const int n = W * H, pw = (W + 31) / 32;
+  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(img, w.Lfg, w.Lbg, w.bits, W, H, pw, w.st, keep_fog);
+  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(img, w.Lfg, w.Lbg, w.outer, mode == 2 ? w.hashole : nullptr, W, H);
+  ccl_flatten2_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, n);
   bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
   collect_roots_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, w.st);
   sort_roots_kernel<<<1, 1024, 0, st>>>(w.cont, w.st);
-  if (mode == 2) {
-    clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(w.hashole, n);
-    mark_holes_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, w.hashole, W, H);
-  }
-  trace_kernel<<<EX_MAXC / 64, 64, 0, st>>>(img, W, H, w.cont, w.chain, w.chain_cap, w.st, mode, w.hashole);
-  count_launch(12);
+  if (mode == 2) mark_holes_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, w.hashole, W, H);
+  trace_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.bits, pw, W, H, w.cont, w.chain, w.chain_cap, w.st, mode, w.hashole);
+  count_launch(mode == 2 ? 8 : 7);
 }
 
 // cv2.ellipse sector polygon (oracle/cv_draw.py::ellipse_sector), vertices in grid coordinates, 16.16
@@ -928,7 +998,6 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   const int nv = sector_polygon(agent_col, agent_row, L, heading_deg - fov_deg / 2, heading_deg + fov_deg / 2, hv);
   int rc = check_cuda(cudaMemcpyAsync(w.verts, hv, sizeof(long long) * 2 * nv, cudaMemcpyHostToDevice, st), "explore: vertex upload");
   if (rc) return rc;
-  reset_state_kernel<<<1, 1, 0, st>>>(w.st, 0);
   zero_planes_kernel<<<nblk(pw0 * W0), 256, 0, st>>>(w.tog, w.orb, pw0 * W0);
   sector_edges_kernel<<<1, 64, 0, st>>>(w.verts, nv, ox, oy, w.tog, w.orb, W0, W0, pw0);
   planes_to_image_kernel<<<nblk(W0, 64), 64, 0, st>>>(w.tog, w.orb, w.cone, W0, W0, pw0, 1, 1, nullptr);
@@ -936,7 +1005,8 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   // ---- R2/R3/R4: obstacle contours -> rays -> cut
   contours(w, w.blocked, W0, W0, st, 0);
   fog_gate_kernel<<<1, 1, 0, st>>>(w.st);
-  rays_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.cont, w.chain, w.rays, w.rays_cap, sx, sy, ox, oy, heading_deg, max_line_len * 1.05, w.st);
+  simple_vertices_kernel<<<EX_MAXC / 8, 256, 0, st>>>(w.cont, w.chain, w.sv, w.nsv, w.st);
+  rays_kernel<<<EX_MAXC / 8, 256, 0, st>>>(w.cont, w.sv, w.nsv, w.rays, w.rays_cap, sx, sy, ox, oy, heading_deg, max_line_len * 1.05, w.st);
   clear_bytes_kernel<<<nblk(wn), 256, 0, st>>>(w.cut, wn);
   thick_rays_kernel<<<RAYS_CAP / 64, 64, 0, st>>>(w.rays, w.cut, W0, W0, w.st);
   apply_cut_kernel<<<nblk(wn), 256, 0, st>>>(w.visible, w.cut, wn, w.st);
@@ -969,7 +1039,8 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   contours(w, w.unexp, G, G, st, 1, 2);
   absorb_small_kernel<<<EX_MAXC, 128, 0, st>>>(w.cont, w.chain, w.unexp, w.ex2, G, G, area_thresh_px, w.st);
   contours(w, w.ex2, G, G, st, 1);
-  frontier_kernel<<<1, 32, 0, st>>>(w.cont, w.chain, d_nav, w.ex2, G, G, d_frontiers, MAXF, w.st);
+  bad_flags_kernel<<<nblk(CHAIN_CAP / 64), 256, 0, st>>>(w.chain, d_nav, w.ex2, G, G, w.flags, w.st);
+  frontier_kernel<<<1, 32, 0, st>>>(w.cont, w.chain, w.flags, d_frontiers, MAXF, w.st);
   rc = check_cuda(cudaMemcpyAsync(d_count, &w.st->n_front, sizeof(int), cudaMemcpyDeviceToDevice, st), "explore: count");
   if (rc) return rc;
   rc = check_cuda(cudaMemcpyAsync(d_status, &w.st->overflow, sizeof(int), cudaMemcpyDeviceToDevice, st), "explore: status");
@@ -997,26 +1068,22 @@ extern "C" int vlfm_fill_small_holes(const float* d_depth, int H, int W, double 
   uint8_t* mask = w.unexp;                       // scratch planes of the explore workspace layout
   zero_mask_kernel<<<nblk(n), 256, 0, st>>>(d_depth, mask, n);
   clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(d_filled, n);
-  reset_state_kernel<<<1, 1, 0, st>>>(w.st, 0);
-  ccl_init_kernel<true><<<nblk(H, 64), 64, 0, st>>>(mask, w.Lfg, W, H);
-  ccl_init_kernel<false><<<nblk(H, 64), 64, 0, st>>>(mask, w.Lbg, W, H);
-  ccl_merge_kernel<true><<<nblk(n), 256, 0, st>>>(mask, w.Lfg, W, H);
-  ccl_merge_kernel<false><<<nblk(n), 256, 0, st>>>(mask, w.Lbg, W, H);
-  ccl_flatten_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, n);
-  ccl_flatten_kernel<<<nblk(n), 256, 0, st>>>(w.Lbg, n);
-  clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(w.outer, n);
+  const int pw = (W + 31) / 32;
+  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(mask, w.Lfg, w.Lbg, w.bits, W, H, pw, w.st, 0);
+  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(mask, w.Lfg, w.Lbg, w.outer, nullptr, W, H);
+  ccl_flatten2_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, n);
   bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
   collect_all_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, HOLES_MAXC, w.st);
-  trace_kernel<<<HOLES_MAXC / 64, 64, 0, st>>>(mask, W, H, w.cont, w.chain, w.chain_cap, w.st, 0, w.hashole);
+  trace_kernel<<<HOLES_MAXC / 64, 64, 0, st>>>(w.bits, pw, W, H, w.cont, w.chain, w.chain_cap, w.st, 0, w.hashole);
   static bool cfg = false;
   const int smem_words = 24 * 1024;             // 96 KB of toggle / outline bit planes per block
   if (!cfg) {
     int rc = check_cuda(cudaFuncSetAttribute(fill_small_contours_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_words * 4), "attr(fill_small_contours)");
     if (rc) return rc; cfg = true;
   }
-  fill_small_contours_kernel<<<HOLES_MAXC, 256, smem_words * 4, st>>>(w.cont, w.chain, d_filled, W, H, area_thresh, smem_words, w.st);
+  fill_small_contours_kernel<<<148 * 2, 256, smem_words * 4, st>>>(w.cont, w.chain, d_filled, W, H, area_thresh, smem_words, HOLES_MAXC, w.st);
   sticky_status_kernel<<<1, 1, 0, st>>>(w.st, d_status);      // sticky: the host may poll it many steps later
   VLFM_CHECK_LAUNCH("vlfm_fill_small_holes");
-  count_launch(16);
+  count_launch(11);
   return VLFM_OK;
 }

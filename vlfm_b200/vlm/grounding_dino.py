@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from .detections import ObjectDetections
+from .gdino_accel import accelerate
 from .swin_engine import SwinBackboneEngine
 
 GROUNDING_DINO_CONFIG = "GroundingDINO/groundingdino/config/GroundingDINO_SwinT_OGC.py"
@@ -87,6 +88,8 @@ class GroundingDINO:
         self._features = _Features()
         model.model.backbone.conv_encoder.model = self._features
         self.model = model.to(device).eval()
+        # feature enhancer / decoder: nn.Linear -> tcgen05 GEMM, deformable-attention sampling -> vlfm_msda_forward
+        self.accel = accelerate(self.model) if os.environ.get("VLFM_GDINO_ACCEL", "1") != "0" else {}
         self.caption = caption
         self.box_threshold = box_threshold
         self.text_threshold = text_threshold
@@ -95,6 +98,16 @@ class GroundingDINO:
         self._dev: Optional[torch.Tensor] = None
 
     @torch.inference_mode()
+    def raw_outputs_device(self, images: torch.Tensor, input_ids: List[int]):
+        """images [B,H,W,3] uint8 on the device -> (sigmoid logits [B,900,256], boxes [B,900,4] cxcywh)."""
+        self._features.maps = self.backbone.forward(images)
+        b, h, w = images.shape[:3]
+        ids = torch.tensor([input_ids], dtype=torch.long, device=self.device).expand(b, -1).contiguous()
+        dummy = torch.zeros(b, 3, h, w, device=self.device)  # only its shape is used (pixel mask); features come from our engine
+        out = self.model(pixel_values=dummy, input_ids=ids, token_type_ids=torch.zeros_like(ids), attention_mask=torch.ones_like(ids),
+                         pixel_mask=torch.ones(b, h, w, dtype=torch.long, device=self.device))
+        return out.logits.sigmoid(), out.pred_boxes
+
     def raw_outputs(self, image: np.ndarray, input_ids: List[int]):
         """-> (sigmoid logits [900,256], boxes [900,4] cxcywh) on the device."""
         image = np.ascontiguousarray(image, dtype=np.uint8)
@@ -103,13 +116,8 @@ class GroundingDINO:
             self._dev = torch.empty((1,) + image.shape, dtype=torch.uint8, device=self.device)
         self._pin[0].numpy()[...] = image
         self._dev.copy_(self._pin, non_blocking=True)
-        self._features.maps = self.backbone.forward(self._dev)
-        h, w = image.shape[:2]
-        ids = torch.tensor([input_ids], dtype=torch.long, device=self.device)
-        dummy = torch.zeros(1, 3, h, w, device=self.device)  # only its shape is used (pixel mask); features come from our engine
-        out = self.model(pixel_values=dummy, input_ids=ids, token_type_ids=torch.zeros_like(ids), attention_mask=torch.ones_like(ids),
-                         pixel_mask=torch.ones(1, h, w, dtype=torch.long, device=self.device))
-        return out.logits[0].sigmoid(), out.pred_boxes[0]
+        logits, boxes = self.raw_outputs_device(self._dev, input_ids)
+        return logits[0], boxes[0]
 
     def predict(self, image: np.ndarray, caption: Optional[str] = None) -> ObjectDetections:
         """grounding_dino.py:38-74."""
