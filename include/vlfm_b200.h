@@ -141,13 +141,14 @@ int vlfm_fill_small_holes(const float* d_depth, int H, int W, double area_thresh
  * A, W row-major fp16 (K contiguous, K % 8 == 0).
  * epilogue: 0 = bias -> fp16 out; 1 = bias + GELU(erf) -> fp16 out;
  *           2 = bias + residual: resid_f32[M,N] += result (fp32 stream, in place)
- *           3 = bias -> fp32 out
+ *           3 = bias -> fp32 out; 4 = bias + ReLU -> fp16 out (GroundingDINO FFNs)
  * These replace the nn.Linear calls inside lavis' Blip2 ITM forward
  * (reference call site vlfm/vlm/blip2itm.py:52).                                     */
 #define VLFM_EPI_BIAS_F16 0
 #define VLFM_EPI_BIAS_GELU_F16 1
 #define VLFM_EPI_BIAS_RESID_F32 2
 #define VLFM_EPI_BIAS_F32 3
+#define VLFM_EPI_BIAS_RELU_F16 4
 /* development aid: CTA (0,0,0) of every later GEMM launch writes clock64() at its phase boundaries
  * (start, setup done, dependency wait done, first stage landed, last MMA issued, accumulator ready,
  * epilogue done) and %globaltimer into d_buf8[0..7]; NULL disables. */
@@ -208,8 +209,18 @@ int vlfm_swin_patch_merge(const float* d_x, float* d_out, int B, int H, int W, i
  * [levels*2] = (H_l, W_l). */
 int vlfm_msda_forward(const void* d_value, int value_is_f16, const float* d_loc, const float* d_attw, float* d_out, int B, int S,
                       int Q, int heads, int hd, int levels, int points, const int32_t* h_shapes_hw, void* stream);
+/* Fused form used by the deformable layers: softmax over the levels*points logits, sampling-location arithmetic
+ * (MSDeformAttn.forward: loc = ref + off / (W_l, H_l) for 2-d reference points, ref_xy + off / points * ref_wh * 0.5 for
+ * 4-d boxes) and the bilinear gather in one kernel.  d_value16 [B,S,heads,32] fp16; d_offlog [B*Q, ld] fp32 rows holding
+ * the sampling-offset projection at column 0 (heads*levels*points*2) and the attention logits at column `logit_col`
+ * (heads*levels*points); d_ref [B,Q,levels,ref_dim] fp32; d_out16 [B*Q, heads*32] fp16.  head_dim 32, levels*points <= 16. */
+int vlfm_msda_fused(const void* d_value16, const float* d_offlog, int ld, int logit_col, const float* d_ref, int ref_dim,
+                    void* d_out16, int B, int S, int Q, int heads, int levels, int points, const int32_t* h_shapes_hw,
+                    void* stream);
 /* fp32 -> fp16 (round to nearest even) staging of GEMM operands. */
 int vlfm_cast_f32_f16(const float* d_in, void* d_out16, long n, void* stream);
+/* out_x16 = fp16(x), out_xp16 = fp16(x + pos) (query/key = hidden + position embedding); n % 4 == 0; either output may be NULL. */
+int vlfm_cast_addpos_f16(const float* d_x, const float* d_pos, void* d_out_x16, void* d_out_xp16, long n, void* stream);
 
 /* ------------------------------------------------------------- explore half ---- */
 /* Replaces ObstacleMap.update_map's explore half (vlfm/mapping/obstacle_map.py:114-153) and _get_frontiers

@@ -105,4 +105,42 @@ def test_tc_linear_and_cast_vs_torch():
 
 def test_accelerated_primitives_are_installed(pair):
     _, g = pair
-    assert g.accel["msda"] == 12 and g.accel["linear"] > 150, g.accel      # 6 encoder + 6 decoder deformable attentions
+    # 6 encoder deformable layers rewritten whole, 6 decoder cross-attentions, every other nn.Linear on the tcgen05 GEMM
+    assert g.accel["deformable_layers"] == 6 and g.accel["deformable_attn"] == 6 and g.accel["linear"] > 100, g.accel
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_fused_deformable_attention_vs_hf_module(ref_dim):
+    """TcDeformAttn (cast+pos, value / offsets|logits GEMMs, fused softmax+locations+gather, output GEMM) against the HF
+    fp32 module it replaces.  fp16 GEMM operands and fp16 values: |err| <= 2e-2 absolute on O(1) outputs, mean <= 2e-3."""
+    from transformers import GroundingDinoConfig
+    from transformers.models.grounding_dino.modeling_grounding_dino import GroundingDinoMultiscaleDeformableAttention
+    from vlfm_b200.vlm.gdino_accel import TcDeformAttn
+
+    torch.manual_seed(2)
+    cfg = GroundingDinoConfig()
+    m = GroundingDinoMultiscaleDeformableAttention(cfg, num_heads=8, n_points=4).cuda().eval()
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.05); m.sampling_offsets.bias.normal_(0, 1.0)
+        m.attention_weights.weight.normal_(0, 0.05); m.attention_weights.bias.normal_(0, 0.5)
+    shapes = [(60, 80), (30, 40), (15, 20), (8, 10)]
+    s = sum(h * w for h, w in shapes)
+    b = 2
+    q = s if ref_dim == 2 else 900
+    enc = torch.randn(b, s, 256, device="cuda")
+    hid = enc if ref_dim == 2 else torch.randn(b, q, 256, device="cuda")
+    pos = torch.randn(b, q, 256, device="cuda") * 0.5
+    ref = torch.rand(b, q, 4, ref_dim, device="cuda")
+    if ref_dim == 4:
+        ref[..., 2:] *= 0.3
+    sp = torch.tensor(shapes, device="cuda")
+    start = torch.cat([sp.new_zeros(1), (sp[:, 0] * sp[:, 1]).cumsum(0)[:-1]])
+    with torch.no_grad():
+        want, _ = m(hid, attention_mask=None, encoder_hidden_states=enc, position_embeddings=pos, reference_points=ref, spatial_shapes=sp,
+                    spatial_shapes_list=shapes, level_start_index=start)
+        got, _ = TcDeformAttn(m)(hid, attention_mask=None, encoder_hidden_states=enc, position_embeddings=pos, reference_points=ref,
+                                 spatial_shapes=sp, spatial_shapes_list=shapes, level_start_index=start)
+    torch.cuda.synchronize()
+    err = (got - want).abs()
+    print("deform attn ref_dim", ref_dim, "max", float(err.max()), "mean", float(err.mean()), "ref scale", float(want.abs().mean()))
+    assert float(err.max()) <= 2e-2 and float(err.mean()) <= 2e-3

@@ -212,16 +212,18 @@ __device__ __forceinline__ int dir_index(int dx, int dy) {
   const int t = (dy + 1) * 3 + (dx + 1);               // 0..8, row-major over dy, dx
   return (0x56740321 >> ((t > 4 ? t - 1 : t) * 4)) & 7;
 }
+// direction tables packed into registers (a dynamically indexed __constant__ array costs a dependent LDC per probe)
+__device__ __forceinline__ int dir_dx(int d) { return (int)((0x01222100u >> (d * 4)) & 0xFu) - 1; }
+__device__ __forceinline__ int dir_dy(int d) { return (int)((0x22210001u >> (d * 4)) & 0xFu) - 1; }
+__device__ __forceinline__ unsigned rotr8(unsigned v, int r) { return ((v >> r) | (v << (8 - r))) & 0xFFu; }
 // Suzuki-Abe steps 3.1-3.5 (oracle/contours.py::_trace) on the packed bitmap; WRITE=false only counts.
 template <bool WRITE>
 __device__ int trace_border(const uint32_t* __restrict__ bits, int pw, int W, int H, int x0, int y0, int2* out, Contour* c, int ed = 0) {
   int fx = -1, fy = -1;
   {
-    const unsigned nb = nb8(bits, pw, W, H, x0, y0);
-    for (int k = 1; k < 8; ++k) {          // 3.1 clockwise from the (zero) entry pixel: west for outer, east for hole borders
-      const int d = (ed + k) & 7;
-      if ((nb >> d) & 1u) { fx = x0 + c_dx[d]; fy = y0 + c_dy[d]; break; }
-    }
+    // 3.1 clockwise from the (zero) entry pixel (west for outer, east for hole borders): first set bit among ed+1 .. ed+7
+    const unsigned r = rotr8(nb8(bits, pw, W, H, x0, y0), ed) & 0xFEu;
+    if (r) { const int d = (ed + __ffs(r) - 1) & 7; fx = x0 + dir_dx(d); fy = y0 + dir_dy(d); }
   }
   int minx = x0, maxx = x0, miny = y0, maxy = y0, n = 0;
   if (fx < 0) {
@@ -231,13 +233,11 @@ __device__ int trace_border(const uint32_t* __restrict__ bits, int pw, int W, in
     int x2 = fx, y2 = fy, x3 = x0, y3 = y0;
     while (true) {
       const int d0 = dir_index(x2 - x3, y2 - y3);
-      const unsigned nb = nb8(bits, pw, W, H, x3, y3);
-      // 3.3 counter-clockwise, starting after (x2,y2): first set bit of nb rotated so that d0-1 is bit 7 ... d0-8 is bit 0
-      int x4 = x3, y4 = y3;
-      for (int k = 1; k <= 8; ++k) {
-        const int di = (d0 - k) & 7;
-        if ((nb >> di) & 1u) { x4 = x3 + c_dx[di]; y4 = y3 + c_dy[di]; break; }
-      }
+      // 3.3 counter-clockwise, starting after (x2,y2): probes d0-1, d0-2, ..., d0-8; after rotating right by d0 they are
+      // bits 7, 6, ..., 0, so the first hit is the highest set bit (bit 0 = (x2,y2) itself is always set)
+      const unsigned r = rotr8(nb8(bits, pw, W, H, x3, y3), d0);
+      const int di = (d0 + (31 - __clz(r))) & 7;
+      const int x4 = x3 + dir_dx(di), y4 = y3 + dir_dy(di);
       if (WRITE) out[n] = make_int2(x3, y3);
       ++n;
       minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);

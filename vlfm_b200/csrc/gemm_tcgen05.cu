@@ -133,10 +133,13 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
         v[j] = __uint_as_float(r[j]) + b;
       }
     }
-    if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16) {
+    if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16 || g.epi == VLFM_EPI_BIAS_RELU_F16) {
       if (g.epi == VLFM_EPI_BIAS_GELU_F16) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (g.epi == VLFM_EPI_BIAS_RELU_F16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       __half* o = reinterpret_cast<__half*>(g.out) + (size_t)row * g.ldo + n0;
       if (fullw) {
@@ -659,7 +662,7 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   if (!d_A || !d_W || !d_out || M < 1 || N < 1 || K < 1) { set_error("vlfm_gemm_f16: bad argument"); return VLFM_E_INVALID; }
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
     set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
-  if (epilogue < 0 || epilogue > 3) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
+  if (epilogue < 0 || epilogue > 4) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
   GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
   return gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, nullptr);
 }

@@ -69,11 +69,116 @@ class TcMSDA(torch.nn.Module):
         return out
 
 
+def _w16(lin: torch.nn.Linear):
+    return lin.weight.detach().to(torch.float16).contiguous(), lin.bias.detach().float().contiguous()
+
+
+def _shapes(spatial_shapes_list):
+    flat = [int(v) for hw in spatial_shapes_list for v in hw]
+    return (ctypes.c_int32 * len(flat))(*flat)
+
+
+class TcDeformAttn(torch.nn.Module):
+    """``GroundingDinoMultiscaleDeformableAttention`` (groundingdino MSDeformAttn.forward) on the library's kernels:
+    cast(+pos) -> value GEMM (fp16 out) -> offsets|logits GEMM (one launch, fp32 out) -> fused softmax + sampling
+    locations + bilinear gather (``vlfm_msda_fused``) -> output GEMM.  Padding masks are not supported on this path
+    (the detector is always fed unpadded, equally sized frames: grounding_dino.py:52-54 passes one native-size image)."""
+
+    def __init__(self, m):
+        super().__init__()
+        self.heads, self.levels, self.points, self.d = m.n_heads, m.n_levels, m.n_points, m.d_model
+        assert self.d // self.heads == 32 and self.levels * self.points <= 16
+        wv, bv = _w16(m.value_proj); wo, bo = _w16(m.output_proj)
+        ws, bs = _w16(m.sampling_offsets); wa, ba = _w16(m.attention_weights)
+        for n, t in (("wv", wv), ("bv", bv), ("wo", wo), ("bo", bo), ("wc", torch.cat([ws, wa]).contiguous()), ("bc", torch.cat([bs, ba]).contiguous())):
+            self.register_buffer(n, t, persistent=False)
+        self.logit_col = ws.shape[0]
+        self.orig = [m]                                    # keeps the parameters reachable without registering them twice
+
+    def sample(self, hidden: torch.Tensor, pos, enc, ref: torch.Tensor, shapes_list) -> torch.Tensor:
+        """-> fp16 [B*Q, d] attention output before the output projection."""
+        from .dense import gemm_f16
+
+        lib = _lib.load()
+        b, q, d = hidden.shape
+        same = enc is None or enc is hidden
+        x = hidden.contiguous()
+        xp16 = torch.empty((b * q, d), dtype=torch.float16, device=x.device)
+        x16 = torch.empty((b * q, d), dtype=torch.float16, device=x.device) if same else None
+        p = None if pos is None else pos.expand_as(x).contiguous()
+        _lib.check(lib.vlfm_cast_addpos_f16(x.data_ptr(), _lib.ptr(p), _lib.ptr(x16), xp16.data_ptr(), x.numel(), _lib.stream_ptr()),
+                   "vlfm_cast_addpos_f16")
+        if not same:
+            s = enc.shape[1]
+            x16 = cast_f16(enc.contiguous()).view(b * s, d)
+        else:
+            s = q
+        value16 = gemm_f16(x16, self.wv, self.bv, _lib.EPI_BIAS_F16)
+        offlog = gemm_f16(xp16, self.wc, self.bc, _lib.EPI_BIAS_F32)
+        ref = ref.float().contiguous()
+        out16 = torch.empty((b * q, d), dtype=torch.float16, device=x.device)
+        rc = lib.vlfm_msda_fused(value16.data_ptr(), offlog.data_ptr(), offlog.stride(0), self.logit_col, ref.data_ptr(), ref.shape[-1],
+                                 out16.data_ptr(), b, s, q, self.heads, self.levels, self.points,
+                                 ctypes.cast(_shapes(shapes_list), ctypes.c_void_p), _lib.stream_ptr())
+        _lib.check(rc, "vlfm_msda_fused")
+        return out16
+
+    def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None, position_embeddings=None,
+                reference_points=None, spatial_shapes=None, spatial_shapes_list=None, level_start_index=None, output_attentions=False):
+        from .dense import gemm_f16
+
+        b, q, d = hidden_states.shape
+        out16 = self.sample(hidden_states, position_embeddings, encoder_hidden_states, reference_points, spatial_shapes_list)
+        return gemm_f16(out16, self.wo, self.bo, _lib.EPI_BIAS_F32).view(b, q, d), None
+
+
+class TcDeformableLayer(torch.nn.Module):
+    """``GroundingDinoDeformableLayer.forward`` (deformable self-attention + FFN, post-LN) entirely on the library's
+    kernels: residual adds fused into the GEMM epilogues (fp32 stream), ReLU fused into fc1, LayerNorms on
+    ``vlfm_layernorm``."""
+
+    def __init__(self, m):
+        super().__init__()
+        self.attn = TcDeformAttn(m.self_attn)
+        w1, b1 = _w16(m.fc1); w2, b2 = _w16(m.fc2)
+        for n, t in (("w1", w1), ("b1", b1), ("w2", w2), ("b2", b2),
+                     ("g1", m.self_attn_layer_norm.weight.detach().float().contiguous()), ("be1", m.self_attn_layer_norm.bias.detach().float().contiguous()),
+                     ("g2", m.final_layer_norm.weight.detach().float().contiguous()), ("be2", m.final_layer_norm.bias.detach().float().contiguous())):
+            self.register_buffer(n, t, persistent=False)
+        self.eps1, self.eps2 = m.self_attn_layer_norm.eps, m.final_layer_norm.eps
+        self.orig = [m]
+
+    def forward(self, hidden_states, attention_mask=None, position_embeddings=None, reference_points=None, spatial_shapes=None,
+                spatial_shapes_list=None, level_start_index=None, output_attentions=False):
+        from .dense import gemm_f16, layernorm
+
+        b, s, d = hidden_states.shape
+        x = hidden_states.reshape(b * s, d).clone()                                   # fp32 residual stream
+        out16 = self.attn.sample(hidden_states, position_embeddings, None, reference_points, spatial_shapes_list)
+        gemm_f16(out16, self.attn.wo, self.attn.bo, _lib.EPI_BIAS_RESID_F32, out=x)   # x += out_proj(attn)
+        x16, x32 = layernorm(x, self.g1, self.be1, self.eps1, want16=True, want32=True)
+        h16 = gemm_f16(x16, self.w1, self.b1, _lib.EPI_BIAS_RELU_F16)
+        gemm_f16(h16, self.w2, self.b2, _lib.EPI_BIAS_RESID_F32, out=x32)             # x32 += fc2(relu(fc1(x)))
+        _, y = layernorm(x32, self.g2, self.be2, self.eps2, want16=False, want32=True)
+        return y.view(b, s, d), None
+
+
 def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
     """Swap the primitives in place (model already on the GPU).  Returns counts for the log / tests."""
-    from transformers.models.grounding_dino.modeling_grounding_dino import MultiScaleDeformableAttention
+    from transformers.models.grounding_dino.modeling_grounding_dino import (GroundingDinoDeformableLayer,
+                                                                           GroundingDinoMultiscaleDeformableAttention,
+                                                                           MultiScaleDeformableAttention)
 
-    n_lin = n_msda = n_skip = 0
+    n_lin = n_msda = n_skip = n_layer = n_attn = 0
+    assert getattr(model.config, "activation_function", "relu") == "relu"
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            if isinstance(child, GroundingDinoDeformableLayer):
+                setattr(parent, name, TcDeformableLayer(child)); n_layer += 1
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            if isinstance(child, GroundingDinoMultiscaleDeformableAttention):
+                setattr(parent, name, TcDeformAttn(child)); n_attn += 1
     for parent in list(model.modules()):
         for name, child in list(parent.named_children()):
             if isinstance(child, torch.nn.Linear):
@@ -83,4 +188,4 @@ def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
                     n_skip += 1
             elif isinstance(child, MultiScaleDeformableAttention):
                 setattr(parent, name, TcMSDA()); n_msda += 1
-    return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda}
+    return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda, "deformable_layers": n_layer, "deformable_attn": n_attn}
