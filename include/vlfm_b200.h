@@ -201,6 +201,13 @@ int vlfm_swin_window_attention(const void* d_qkv, const float* d_qkv_bias, const
                                int H, int W, int C, int heads, int shift, void* stream);
 int vlfm_swin_patch_merge(const float* d_x, float* d_out, int B, int H, int W, int C, void* stream);
 
+/* Confidence-cone template of ValueMap (`_get_confidence_mask` / `_get_blank_cone_mask`, value_map.py:321-355): the
+ * cv2.ellipse filled sector (+-fov/2 about +row, integer degrees, OpenCV's sine table and 16.16 edge scan) times
+ * remap(cos^2(remap(atan2(|dcol|,|drow|), 0, fov/2, 0, pi/2)), 0, 1, min_conf, 1).  d_out [R,R] f32, R = 2*int(max_depth*ppm)+1.
+ * d_scratch needs R*R + 8*R*ceil(R/32) + 2304 bytes.  Configuration-time constant (synchronises the stream). */
+int vlfm_value_cone_template(double fov, double max_depth, int ppm, double min_conf, float* d_out, void* d_scratch,
+                             size_t scratch_bytes, void* stream);
+
 /* ------------------------------------- GroundingDINO feature enhancer / decoder ---- */
 /* Multi-scale deformable attention sampling (replaces groundingdino's third-party ms_deform_attn_cuda.cu, reached from
  * vlfm/vlm/grounding_dino.py:61-67).  d_value [B,S,heads,hd] fp32 or fp16 (S = sum H_l*W_l, levels concatenated),

@@ -169,3 +169,21 @@ def test_other_resolution_ppm40():
         g.update_map(v, f.depth, f.tf, 0.5, 5.0, FOV)
     assert np.array_equal(g._map, o._map)
     assert np.abs(g._value_map - o._value_map).max() <= VAL_TOL
+
+
+@pytest.mark.parametrize("cfg", [(79.0, 5.0, 20), (79.0, 5.0, 40), (79.0, 5.0, 50), (90.0, 3.5, 20), (60.0, 10.0, 20), (120.0, 2.0, 20)])
+def test_cone_template_built_on_device_is_bit_exact(cfg):
+    """vlfm_value_cone_template (device) against the reference's construction (cv2.ellipse sector x python-float cos^2
+    falloff, value_map.py:321-355) as restated in oracle.value_map_oracle.cone_template: every float32 identical."""
+    import torch
+
+    from oracle.value_map_oracle import cone_template
+    from vlfm_b200.mapping.value_map import build_cone_template
+
+    fov_deg, max_depth, ppm = cfg
+    fov = float(np.deg2rad(fov_deg))
+    got = build_cone_template(fov, max_depth, ppm, torch.device("cuda")).cpu().numpy()
+    want = cone_template(fov, max_depth, ppm)
+    assert got.shape == want.shape and got.dtype == np.float32
+    bad = np.flatnonzero(got.view(np.uint32) != np.asarray(want, dtype=np.float32).view(np.uint32))
+    assert bad.size == 0, f"{bad.size} of {got.size} template cells differ (first at {np.unravel_index(bad[0], got.shape)})"

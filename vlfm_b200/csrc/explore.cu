@@ -383,6 +383,19 @@ __global__ void sector_edges_kernel(const long long* __restrict__ v, int nv, int
   }
 }
 
+// ValueMap confidence cone (value_map.py:321-355): sector(0/1 byte image) x remap(cos^2(remap(atan2(|dc|,|dr|), 0, fov/2, 0, pi/2)),
+// 0, 1, min_conf, 1) in float64 with numpy's operation order, cast to float32.
+__global__ void cone_template_kernel(const uint8_t* __restrict__ sector, float* __restrict__ out, int R, double fov, double min_conf) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R * R; i += gridDim.x * blockDim.x) {
+    const int r = i / R, c = i - r * R;
+    const double dr = fabs((double)(r - R / 2)), dc = fabs((double)(c - R / 2));
+    const double ang = __ddiv_rn(__dmul_rn(atan2(dc, dr), 3.14159265358979323846 / 2), fov / 2);
+    const double cs = cos(ang);
+    const double conf = __dadd_rn(__dmul_rn(__dmul_rn(cs, cs), 1.0 - min_conf), min_conf);
+    out[i] = sector[i] ? (float)conf : 0.f;
+  }
+}
+
 // --------------------------------------------------------------------------------- window images ----
 // blocked = cone & !nav ; visible = cone & nav   (window W0 x W0 at grid origin (ox, oy))
 __global__ void fog_masks_kernel(const uint8_t* __restrict__ cone, const uint8_t* __restrict__ nav, int G, int ox, int oy, int W0,
@@ -1085,5 +1098,34 @@ extern "C" int vlfm_fill_small_holes(const float* d_depth, int H, int W, double 
   sticky_status_kernel<<<1, 1, 0, st>>>(w.st, d_status);      // sticky: the host may poll it many steps later
   VLFM_CHECK_LAUNCH("vlfm_fill_small_holes");
   count_launch(11);
+  return VLFM_OK;
+}
+
+// Confidence-cone template of ValueMap (vlfm/mapping/value_map.py:321-355 `_get_confidence_mask` / `_get_blank_cone_mask`):
+// cv2.ellipse filled sector (+-fov/2 about +row) x cos^2 falloff.  d_out [R,R] float32, R = 2*int(max_depth*ppm)+1;
+// d_scratch: R*R bytes + 2*R*ceil(R/32) uint32 + 2 KB.
+extern "C" int vlfm_value_cone_template(double fov, double max_depth, int ppm, double min_conf, float* d_out, void* d_scratch,
+                                        size_t scratch_bytes, void* stream) {
+  const int half = (int)(max_depth * ppm), R = 2 * half + 1, pw = (R + 31) / 32;
+  const size_t need = (((size_t)R * R + 255) & ~(size_t)255) + (size_t)2 * R * pw * 4 + 2048;
+  if (!d_out || !d_scratch || half < 1 || scratch_bytes < need) { set_error("vlfm_value_cone_template: bad argument (scratch %zu < %zu)", scratch_bytes, need); return VLFM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* sector = (uint8_t*)d_scratch;
+  uint32_t* tog = (uint32_t*)(sector + (((size_t)R * R + 255) & ~(size_t)255));
+  uint32_t* orb = tog + (size_t)R * pw;
+  long long* verts = (long long*)(orb + (size_t)R * pw);
+  const double deg = fov * 180.0 / 3.14159265358979323846;       // np.rad2deg
+  long long hv[128];
+  const int nv = sector_polygon(half, half, half, -deg / 2 + 90, deg / 2 + 90, hv);
+  int rc = check_cuda(cudaMemcpyAsync(verts, hv, sizeof(long long) * 2 * nv, cudaMemcpyHostToDevice, st), "cone template: vertex upload");
+  if (rc) return rc;
+  zero_planes_kernel<<<nblk((long)pw * R), 256, 0, st>>>(tog, orb, pw * R);
+  sector_edges_kernel<<<1, 64, 0, st>>>(verts, nv, 0, 0, tog, orb, R, R, pw);
+  planes_to_image_kernel<<<nblk(R, 64), 64, 0, st>>>(tog, orb, sector, R, R, pw, 1, 1, nullptr);
+  cone_template_kernel<<<nblk((long)R * R), 256, 0, st>>>(sector, d_out, R, fov, min_conf);
+  rc = check_cuda(cudaStreamSynchronize(st), "cone template");   // hv is a stack buffer: the upload must finish before returning
+  if (rc) return rc;
+  VLFM_CHECK_LAUNCH("vlfm_value_cone_template");
+  count_launch(4);
   return VLFM_OK;
 }

@@ -26,26 +26,26 @@ _TANS: Dict[Tuple[float, int, str], torch.Tensor] = {}
 _DISCS: Dict[Tuple[int, str], torch.Tensor] = {}
 
 
-def build_cone_template(fov: float, max_depth: float, ppm: int) -> np.ndarray:
-    """Confidence cone (value_map.py:321-355): filled +-fov/2 sector (cv2.ellipse, as the
-    reference) times cos^2 falloff remapped to [0.25, 1], float32.  Configuration-time
-    constant per (fov, max_depth, ppm); computed once on the host and cached in HBM."""
-    import cv2
-
+def build_cone_template(fov: float, max_depth: float, ppm: int, device: torch.device) -> torch.Tensor:
+    """Confidence cone (value_map.py:321-355): filled +-fov/2 sector (cv2.ellipse's rasterisation rules) times the cos^2
+    falloff remapped to [0.25, 1], float32 -- built on the device by ``vlfm_value_cone_template``.  Configuration-time
+    constant per (fov, max_depth, ppm), cached in HBM like the reference's class-level ``_confidence_masks``."""
     half = int(max_depth * ppm)
     side = 2 * half + 1
-    deg = float(np.rad2deg(fov))
-    sector = cv2.ellipse(np.zeros((side, side)), (half, half), (half, half), 0, -deg / 2 + 90, deg / 2 + 90, 1, -1)
-    off = np.abs(np.arange(side) - side // 2).astype(np.float64)
-    ang = np.arctan2(off[None, :], off[:, None]) * (np.pi / 2) / (fov / 2)
-    conf = np.cos(ang) ** 2 * (1.0 - MIN_CONFIDENCE) + MIN_CONFIDENCE
-    return (conf.astype(np.float32) * sector).astype(np.float32)
+    out = torch.empty((side, side), dtype=torch.float32, device=device)
+    nbytes = side * side + 8 * side * ((side + 31) // 32) + 2304
+    scratch = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        rc = _lib.load().vlfm_value_cone_template(float(fov), float(max_depth), int(ppm), MIN_CONFIDENCE, _lib.ptr(out), _lib.ptr(scratch),
+                                                  scratch.numel() * 4, _lib.stream_ptr())
+    _lib.check(rc, "vlfm_value_cone_template")
+    return out
 
 
 def _template(fov: float, max_depth: float, ppm: int, device: torch.device) -> torch.Tensor:
     key = (float(fov), float(max_depth), int(ppm), str(device))
     if key not in _TEMPLATES:
-        _TEMPLATES[key] = torch.from_numpy(build_cone_template(fov, max_depth, ppm)).to(device).contiguous()
+        _TEMPLATES[key] = build_cone_template(fov, max_depth, ppm, torch.device(device))
     return _TEMPLATES[key]
 
 
