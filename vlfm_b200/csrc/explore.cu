@@ -65,11 +65,10 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 
 // init: every pixel points at the first pixel of its horizontal run, for the foreground (8-connected) and the background
 // (4-connected) label arrays at once, so that the union phase only has to stitch runs of adjacent rows.  One warp per
-// row, 32 cells per ballot; the ballot word doubles as the packed bitmap the border tracer reads.  Block 0 also resets
+// row, 32 cells per ballot.  Block 0 also resets
 // the per-image bookkeeping.
 __global__ void __launch_bounds__(256)
-ccl_init2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __restrict__ Lbg, uint32_t* __restrict__ bits, int W, int H,
-                 int pw, ExState* st, int keep_fog) {
+ccl_init2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __restrict__ Lbg, int W, int H, ExState* st, int keep_fog) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->n_cont = 0; st->cursor = 0; st->n_rays = 0; st->chosen = -1;
     if (!keep_fog) { st->skip_fog = 0; st->overflow = 0; st->n_front = 0; }
@@ -85,7 +84,6 @@ ccl_init2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __
       const bool valid = x < W;
       const bool fg = valid && row[x] != 0;
       const unsigned m = __ballot_sync(0xffffffffu, fg);
-      if (lane == 0) bits[y * pw + (x0 >> 5)] = m;
       const unsigned zf = ~m & below, zb = m & below;  // cells below this lane that end a fg / bg run
       const int sf = zf ? x0 + 32 - __clz(zf) : (carry_fg >= 0 ? carry_fg : x0);
       const int sb = zb ? x0 + 32 - __clz(zb) : (carry_bg >= 0 ? carry_bg : x0);
@@ -98,14 +96,27 @@ ccl_init2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __
 }
 // stitch: a pixel unions with the row above only where a NEW overlap between runs begins; also clears the per-label flags
 __global__ void ccl_merge2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __restrict__ Lbg, uint8_t* __restrict__ outer,
-                                  uint8_t* __restrict__ hashole, int W, int H) {
+                                  uint8_t* __restrict__ hashole, uint8_t* __restrict__ nbm, int W, int H) {
   const int n = W * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     outer[i] = 0;
     if (hashole) hashole[i] = 0;
     const int y = i / W, x = i - y * W;
-    if (y == 0) continue;
     const bool c = img[i] != 0;
+    if (c) {   // 8-neighbourhood mask for the border tracer, bit d = neighbour in direction d (clockwise from west)
+      const bool l = x > 0, r = x + 1 < W, u = y > 0, d = y + 1 < H;
+      unsigned m = 0;
+      if (l && img[i - 1]) m |= 1u;
+      if (l && u && img[i - W - 1]) m |= 2u;
+      if (u && img[i - W]) m |= 4u;
+      if (r && u && img[i - W + 1]) m |= 8u;
+      if (r && img[i + 1]) m |= 16u;
+      if (r && d && img[i + W + 1]) m |= 32u;
+      if (d && img[i + W]) m |= 64u;
+      if (l && d && img[i + W - 1]) m |= 128u;
+      nbm[i] = (uint8_t)m;
+    }
+    if (y == 0) continue;
     const bool west = x > 0 && ((img[i - 1] != 0) == c);
     const bool north = (img[i - W] != 0) == c;
     const bool nwest = x > 0 && ((img[i - W - 1] != 0) == c);
@@ -184,66 +195,37 @@ __global__ void __launch_bounds__(1024) sort_roots_kernel(Contour* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------------------- tracing ----
-__constant__ int c_dx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};   // clockwise from west (image coordinates, y down)
-__constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+// directions 0..7: clockwise from west (image coordinates, y down): dx = {-1,-1,0,1,1,1,0,-1}, dy = {0,-1,-1,-1,0,1,1,1}
 
-__device__ __forceinline__ bool fg_at(const uint8_t* img, int W, int H, int x, int y) {
-  return (unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H && img[y * W + x] != 0;
-}
-// three-cell window (x-1, x, x+1) of bitmap row y as bits 0..2; cells outside the image are background
-__device__ __forceinline__ unsigned row3(const uint32_t* __restrict__ bits, int pw, int W, int H, int x, int y) {
-  if ((unsigned)y >= (unsigned)H) return 0;
-  const uint32_t* r = bits + (size_t)y * pw;
-  const int wi = x >> 5, b = x & 31;
-  const uint32_t w = __ldg(r + wi);
-  unsigned out = ((w >> b) & 1u) << 1;
-  if (b > 0) out |= (w >> (b - 1)) & 1u; else if (wi > 0) out |= __ldg(r + wi - 1) >> 31;
-  if (b < 31) out |= ((w >> (b + 1)) & 1u) << 2; else if (x + 1 < W) out |= (__ldg(r + wi + 1) & 1u) << 2;
-  return (x + 1 < W) ? out : (out & 3u);
-}
-// 8-neighbourhood of (x, y) as a mask indexed like c_dx / c_dy (clockwise from west)
-__device__ __forceinline__ unsigned nb8(const uint32_t* __restrict__ bits, int pw, int W, int H, int x, int y) {
-  const unsigned up = row3(bits, pw, W, H, x, y - 1), mid = row3(bits, pw, W, H, x, y), dn = row3(bits, pw, W, H, x, y + 1);
-  return (mid & 1u) | ((up & 1u) << 1) | (((up >> 1) & 1u) << 2) | (((up >> 2) & 1u) << 3) | (((mid >> 2) & 1u) << 4) |
-         (((dn >> 2) & 1u) << 5) | (((dn >> 1) & 1u) << 6) | ((dn & 1u) << 7);
-}
-__device__ __forceinline__ int dir_index(int dx, int dy) {
-  // inverse of c_dx / c_dy for unit steps: (-1,0)->0 (-1,-1)->1 (0,-1)->2 (1,-1)->3 (1,0)->4 (1,1)->5 (0,1)->6 (-1,1)->7
-  const int t = (dy + 1) * 3 + (dx + 1);               // 0..8, row-major over dy, dx
-  return (0x56740321 >> ((t > 4 ? t - 1 : t) * 4)) & 7;
-}
 // direction tables packed into registers (a dynamically indexed __constant__ array costs a dependent LDC per probe)
 __device__ __forceinline__ int dir_dx(int d) { return (int)((0x01222100u >> (d * 4)) & 0xFu) - 1; }
 __device__ __forceinline__ int dir_dy(int d) { return (int)((0x22210001u >> (d * 4)) & 0xFu) - 1; }
 __device__ __forceinline__ unsigned rotr8(unsigned v, int r) { return ((v >> r) | (v << (8 - r))) & 0xFFu; }
-// Suzuki-Abe steps 3.1-3.5 (oracle/contours.py::_trace) on the packed bitmap; WRITE=false only counts.
+// Suzuki-Abe steps 3.1-3.5 (oracle/contours.py::_trace) on the per-pixel neighbour masks written by ccl_merge2_kernel: one
+// byte load per step; the clockwise / counter-clockwise probe loops are a byte rotation + ffs / clz.  WRITE=false only counts.
 template <bool WRITE>
-__device__ int trace_border(const uint32_t* __restrict__ bits, int pw, int W, int H, int x0, int y0, int2* out, Contour* c, int ed = 0) {
-  int fx = -1, fy = -1;
-  {
-    // 3.1 clockwise from the (zero) entry pixel (west for outer, east for hole borders): first set bit among ed+1 .. ed+7
-    const unsigned r = rotr8(nb8(bits, pw, W, H, x0, y0), ed) & 0xFEu;
-    if (r) { const int d = (ed + __ffs(r) - 1) & 7; fx = x0 + dir_dx(d); fy = y0 + dir_dy(d); }
-  }
-  int minx = x0, maxx = x0, miny = y0, maxy = y0, n = 0;
-  if (fx < 0) {
+__device__ int trace_border(const uint8_t* __restrict__ nbm, int W, int x0, int y0, int2* out, Contour* c, int ed = 0) {
+  int n = 0, minx = x0, maxx = x0, miny = y0, maxy = y0;
+  // 3.1 clockwise from the (zero) entry pixel (west for outer, east for hole borders): first set bit among ed+1 .. ed+7
+  const unsigned r0 = rotr8(nbm[y0 * W + x0], ed) & 0xFEu;
+  if (!r0) {
     if (WRITE) out[0] = make_int2(x0, y0);
     n = 1;
   } else {
-    int x2 = fx, y2 = fy, x3 = x0, y3 = y0;
+    const int df = (ed + __ffs(r0) - 1) & 7;
+    const int fx = x0 + dir_dx(df), fy = y0 + dir_dy(df);
+    int x3 = x0, y3 = y0, d0 = df;                   // d0: direction from (x3,y3) to the previously examined pixel (x2,y2)
     while (true) {
-      const int d0 = dir_index(x2 - x3, y2 - y3);
-      // 3.3 counter-clockwise, starting after (x2,y2): probes d0-1, d0-2, ..., d0-8; after rotating right by d0 they are
-      // bits 7, 6, ..., 0, so the first hit is the highest set bit (bit 0 = (x2,y2) itself is always set)
-      const unsigned r = rotr8(nb8(bits, pw, W, H, x3, y3), d0);
+      // 3.3 counter-clockwise, starting after (x2,y2): probes d0-1, ..., d0-8 are bits 7..0 after rotating right by d0, so the
+      // first hit is the highest set bit (bit 0 = (x2,y2) itself is always set)
+      const unsigned r = rotr8(nbm[y3 * W + x3], d0);
       const int di = (d0 + (31 - __clz(r))) & 7;
       const int x4 = x3 + dir_dx(di), y4 = y3 + dir_dy(di);
-      if (WRITE) out[n] = make_int2(x3, y3);
+      if (WRITE) { out[n] = make_int2(x3, y3); minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3); }
       ++n;
-      minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
       if (x4 == x0 && y4 == y0 && x3 == fx && y3 == fy) break;   // 3.5
-      x2 = x3; y2 = y3; x3 = x4; y3 = y4;
-      if (n > (1 << 22)) break;            // safety
+      x3 = x4; y3 = y4; d0 = (di + 4) & 7;          // seen from the new pixel, the old one lies in the opposite direction
+      if (n > (1 << 22)) break;                      // safety
     }
   }
   if (WRITE) { c->x0 = minx; c->x1 = maxx; c->y0 = miny; c->y1 = maxy; }
@@ -251,17 +233,17 @@ __device__ int trace_border(const uint32_t* __restrict__ bits, int pw, int W, in
 }
 // mode 0: trace every contour; 1: only when more than one contour exists (component selection); 2: skip components
 // that enclose a hole (their filled polygon contains a zero cell, so F1 can never absorb them)
-__global__ void trace_kernel(const uint32_t* __restrict__ bits, int pw, int W, int H, Contour* __restrict__ cont, int2* __restrict__ chain,
+__global__ void trace_kernel(const uint8_t* __restrict__ nbm, int W, int H, Contour* __restrict__ cont, int2* __restrict__ chain,
                              int cap, ExState* st, int mode, const uint8_t* __restrict__ hashole) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st->n_cont || c >= gridDim.x * blockDim.x) return;
   const int s = cont[c].start, y0 = s / W, x0 = s - y0 * W;
   if ((mode == 1 && st->n_cont <= 1) || (mode == 2 && hashole[s])) { cont[c].off = 0; cont[c].len = 0; return; }
-  const int n = trace_border<false>(bits, pw, W, H, x0, y0, nullptr, nullptr, cont[c].ed);
+  const int n = trace_border<false>(nbm, W, x0, y0, nullptr, nullptr, cont[c].ed);
   const int off = atomicAdd(&st->cursor, n);
   if (off + n > cap) { st->overflow = 1; cont[c].off = 0; cont[c].len = 0; return; }
   cont[c].off = off; cont[c].len = n;
-  trace_border<true>(bits, pw, W, H, x0, y0, chain + off, &cont[c], cont[c].ed);
+  trace_border<true>(nbm, W, x0, y0, chain + off, &cont[c], cont[c].ed);
 }
 
 // CHAIN_APPROX_SIMPLE: point i of a chain is kept iff the step into it differs from the step out of it
@@ -889,9 +871,9 @@ using namespace vlfm;
 namespace {
 
 struct Ws {       // carved from the caller's workspace
-  uint8_t *cone, *blocked, *visible, *cut, *newexp, *outer, *grown, *unexp, *ex2, *hashole;
+  uint8_t *cone, *blocked, *visible, *cut, *newexp, *outer, *grown, *unexp, *ex2, *hashole, *nbm;
   int *Lfg, *Lbg, *which;
-  Contour* cont; int2 *chain, *sv; int4* rays; double* dist; uint32_t *tog, *orb, *bits; long long* verts; ExState* st;
+  Contour* cont; int2 *chain, *sv; int4* rays; double* dist; uint32_t *tog, *orb; long long* verts; ExState* st;
   int* nsv; uint8_t* flags;
   int chain_cap, rays_cap;
 };
@@ -914,6 +896,7 @@ size_t carve(Ws* w, uint8_t* base, int G, int maxc = EX_MAXC) {
   p = take(n); if (w) w->unexp = p;
   p = take(n); if (w) w->ex2 = p;
   p = take(n); if (w) w->hashole = p;
+  p = take(n); if (w) w->nbm = p;
   p = take(n * 4); if (w) w->Lfg = (int*)p;
   p = take(n * 4); if (w) w->Lbg = (int*)p;
   p = take(sizeof(Contour) * (size_t)maxc); if (w) w->cont = (Contour*)p;
@@ -926,7 +909,6 @@ size_t carve(Ws* w, uint8_t* base, int G, int maxc = EX_MAXC) {
   const size_t pw = ((size_t)G + 31) / 32;
   p = take(pw * G * 4); if (w) w->tog = (uint32_t*)p;
   p = take(pw * G * 4); if (w) w->orb = (uint32_t*)p;
-  p = take(pw * G * 4); if (w) w->bits = (uint32_t*)p;
   p = take(64 * 2 * 8); if (w) w->verts = (long long*)p;
   p = take(sizeof(ExState)); if (w) w->st = (ExState*)p;
   p = take(64); if (w) w->which = (int*)p;
@@ -938,15 +920,15 @@ inline int nblk(long n, int t = 256) { long b = (n + t - 1) / t; return (int)(b 
 
 // external contours of `img` (W x H): CCL fg/bg, top-level roots in cv2 order, traced chains
 void contours(const Ws& w, const uint8_t* img, int W, int H, cudaStream_t st, int keep_fog, int mode = 0) {
-  const int n = W * H, pw = (W + 31) / 32;
-  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(img, w.Lfg, w.Lbg, w.bits, W, H, pw, w.st, keep_fog);
-  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(img, w.Lfg, w.Lbg, w.outer, mode == 2 ? w.hashole : nullptr, W, H);
+  const int n = W * H;
+  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(img, w.Lfg, w.Lbg, W, H, w.st, keep_fog);
+  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(img, w.Lfg, w.Lbg, w.outer, mode == 2 ? w.hashole : nullptr, w.nbm, W, H);
   ccl_flatten2_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, n);
   bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
   collect_roots_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, w.st);
   sort_roots_kernel<<<1, 1024, 0, st>>>(w.cont, w.st);
   if (mode == 2) mark_holes_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, w.hashole, W, H);
-  trace_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.bits, pw, W, H, w.cont, w.chain, w.chain_cap, w.st, mode, w.hashole);
+  trace_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.nbm, W, H, w.cont, w.chain, w.chain_cap, w.st, mode, w.hashole);
   count_launch(mode == 2 ? 8 : 7);
 }
 
@@ -1081,13 +1063,12 @@ extern "C" int vlfm_fill_small_holes(const float* d_depth, int H, int W, double 
   uint8_t* mask = w.unexp;                       // scratch planes of the explore workspace layout
   zero_mask_kernel<<<nblk(n), 256, 0, st>>>(d_depth, mask, n);
   clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(d_filled, n);
-  const int pw = (W + 31) / 32;
-  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(mask, w.Lfg, w.Lbg, w.bits, W, H, pw, w.st, 0);
-  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(mask, w.Lfg, w.Lbg, w.outer, nullptr, W, H);
+  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(mask, w.Lfg, w.Lbg, W, H, w.st, 0);
+  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(mask, w.Lfg, w.Lbg, w.outer, nullptr, w.nbm, W, H);
   ccl_flatten2_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, n);
   bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
   collect_all_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, HOLES_MAXC, w.st);
-  trace_kernel<<<HOLES_MAXC / 64, 64, 0, st>>>(w.bits, pw, W, H, w.cont, w.chain, w.chain_cap, w.st, 0, w.hashole);
+  trace_kernel<<<HOLES_MAXC / 64, 64, 0, st>>>(w.nbm, W, H, w.cont, w.chain, w.chain_cap, w.st, 0, w.hashole);
   static bool cfg = false;
   const int smem_words = 24 * 1024;             // 96 KB of toggle / outline bit planes per block
   if (!cfg) {
