@@ -106,7 +106,8 @@ def test_tc_linear_and_cast_vs_torch():
 def test_accelerated_primitives_are_installed(pair):
     _, g = pair
     # 6 encoder deformable layers rewritten whole, 6 decoder cross-attentions, every other nn.Linear on the tcgen05 GEMM
-    assert g.accel["deformable_layers"] == 6 and g.accel["deformable_attn"] == 6 and g.accel["linear"] > 100, g.accel
+    assert g.accel["deformable_layers"] == 6 and g.accel["deformable_attn"] == 6 and g.accel["fusion_layers"] == 6, g.accel
+    assert g.accel["linear"] > 60, g.accel
 
 
 @pytest.mark.parametrize("ref_dim", [2, 4])
@@ -144,3 +145,49 @@ def test_fused_deformable_attention_vs_hf_module(ref_dim):
     err = (got - want).abs()
     print("deform attn ref_dim", ref_dim, "max", float(err.max()), "mean", float(err.mean()), "ref scale", float(want.abs().mean()))
     assert float(err.max()) <= 2e-2 and float(err.mean()) <= 2e-3
+
+
+@pytest.mark.parametrize("nq,nk", [(777, 10), (10, 777), (64, 130), (3, 6380), (130, 48)])
+def test_biattn_kernel_vs_torch(nq, nk):
+    """vlfm_biattn_f16 (head_dim 256; key chunks merged by log-sum-exp) against fp32 torch attention on the same fp16
+    inputs.  Tolerance 3e-3 (fp16 probabilities and outputs)."""
+    from vlfm_b200.vlm.gdino_accel import biattn_f16
+
+    torch.manual_seed(nq * 1000 + nk)
+    b, heads = 2, 4
+    q = (torch.randn(b * nq, heads * 256, device="cuda") * 0.5).half()
+    kv = (torch.randn(b * nk, 2 * heads * 256, device="cuda") * 0.5).half()       # keys | values interleaved like the fused projection
+    k, v = kv[:, : heads * 256], kv[:, heads * 256 :]
+    scale = 256 ** -0.5
+    got = biattn_f16(q, k, v, b, heads, nq, nk, scale)
+    qf = q.float().view(b, nq, heads, 256).transpose(1, 2)
+    kf = k.float().reshape(b, nk, heads, 256).transpose(1, 2)
+    vf = v.float().reshape(b, nk, heads, 256).transpose(1, 2)
+    want = (torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf).transpose(1, 2).reshape(b * nq, heads * 256)
+    torch.cuda.synchronize()
+    err = float((got.float() - want).abs().max())
+    print("biattn", nq, nk, "max abs err", err)
+    assert err <= 3e-3
+
+
+def test_fusion_layer_vs_hf_module():
+    """TcFusionLayer against the HF fp32 GroundingDinoFusionLayer it replaces (layer scale set to O(1) so that the attention
+    path is visible in the output).  fp16 operands: max |err| <= 3e-2, mean <= 3e-3 on O(1) outputs."""
+    from transformers import GroundingDinoConfig
+    from transformers.models.grounding_dino.modeling_grounding_dino import GroundingDinoFusionLayer
+    from vlfm_b200.vlm.gdino_accel import TcFusionLayer
+
+    torch.manual_seed(3)
+    m = GroundingDinoFusionLayer(GroundingDinoConfig()).cuda().eval()
+    with torch.no_grad():
+        m.vision_param.fill_(0.7); m.text_param.fill_(0.9)
+    b, nv, t = 2, 1500, 12
+    vis = torch.randn(b, nv, 256, device="cuda")
+    txt = torch.randn(b, t, 256, device="cuda")
+    with torch.no_grad():
+        (wv, _), (wt, _) = m(vis, txt, attention_mask_vision=None, attention_mask_text=None)
+        (gv, _), (gt, _) = TcFusionLayer(m)(vis, txt)
+    torch.cuda.synchronize()
+    ev, et = (gv - wv).abs(), (gt - wt).abs()
+    print("fusion vision max", float(ev.max()), "mean", float(ev.mean()), "text max", float(et.max()), "mean", float(et.mean()))
+    assert float(ev.max()) <= 3e-2 and float(ev.mean()) <= 3e-3 and float(et.max()) <= 3e-2 and float(et.mean()) <= 3e-3

@@ -180,6 +180,173 @@ __global__ void cast_f32_f16_kernel(const float4* __restrict__ in, uint2* __rest
   if (blockIdx.x == 0 && threadIdx.x < tail) out_tail[threadIdx.x] = __float2half_rn(in_tail[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------ bi-directional fusion attention ----
+// GroundingDinoBiMultiHeadAttention (groundingdino BiMultiHeadAttention, reached from vlfm/vlm/grounding_dino.py:61-67):
+// head_dim 256, 4 heads.  Both directions are plain softmax attentions over the SAME logits S = scale * q_img . k_txt:
+//   image <- text : queries = image tokens (thousands), keys/values = text tokens (tens)           -> chunks == 1
+//   text <- image : queries = text tokens, keys = the image QUERY projection, values = image values -> keys split into
+//                   chunks over CTAs, partial (m, l, O) merged by biattn_merge_kernel.
+// Flash-style on mma.sync m16n8k16.  8 warps = 4 row groups of 16 queries x 2 channel halves (128 channels each): the two
+// warps of a row group both compute S (tensor cores are idle anyway) so that each keeps only 64 accumulator registers.
+struct BiAttnArgs {
+  const __half *q, *k, *v;   // rows b*N + i, head h at column h*256
+  __half* o16;               // chunks == 1: [B*Nq, ldo]
+  float* part;               // chunks > 1: [B, H, chunks, NqP, 258] unnormalised channels, then m, l
+  int B, H, Nq, Nk, ldq, ldk, ldv, ldo, KC, chunks, NqP;
+  float scale_log2;
+};
+__device__ __forceinline__ void bi_mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t bi_pack(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ void bi_ldm_x2t(uint32_t& r0, uint32_t& r1, const __half* p) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+constexpr int BI_HD = 256, BI_KS = BI_HD + 8;
+
+__global__ void __launch_bounds__(256)
+biattn_kernel(BiAttnArgs a) {
+  extern __shared__ __align__(16) uint8_t bi_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int rg = warp >> 1, half = warp & 1;
+  const int qb = blockIdx.x / a.chunks, ch = blockIdx.x - qb * a.chunks, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = ch * a.KC, nk = min(a.KC, a.Nk - k0), nkp = (nk + 15) & ~15;
+  __half* sK = reinterpret_cast<__half*>(bi_smem);
+  __half* sV = sK + (size_t)((a.KC + 15) & ~15) * BI_KS;
+  const __half* kbase = a.k + ((size_t)b * a.Nk + k0) * a.ldk + (size_t)h * BI_HD;
+  const __half* vbase = a.v + ((size_t)b * a.Nk + k0) * a.ldv + (size_t)h * BI_HD;
+  for (int i = tid; i < nkp * (BI_HD / 8); i += 256) {
+    const int key = i >> 5, c = (i & 31) * 8;
+    const bool ok = key < nk;
+    const __half* ks = ok ? kbase + (size_t)key * a.ldk + c : kbase;
+    const __half* vs = ok ? vbase + (size_t)key * a.ldv + c : vbase;
+    const uint32_t kd = (uint32_t)__cvta_generic_to_shared(sK + key * BI_KS + c), vd = (uint32_t)__cvta_generic_to_shared(sV + key * BI_KS + c);
+    const int nb = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(kd), "l"(ks), "r"(nb) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vd), "l"(vs), "r"(nb) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int row0 = qb * 64 + rg * 16, r_lo = row0 + g, r_hi = row0 + g + 8;
+  const __half* qlo = a.q + ((size_t)b * a.Nq + r_lo) * a.ldq + (size_t)h * BI_HD;
+  const __half* qhi = a.q + ((size_t)b * a.Nq + r_hi) * a.ldq + (size_t)h * BI_HD;
+  uint32_t qf[BI_HD / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < BI_HD / 16; ++kk) {
+    const int c0 = kk * 16 + 2 * t, c1 = c0 + 8;
+    qf[kk][0] = r_lo < a.Nq ? *reinterpret_cast<const uint32_t*>(qlo + c0) : 0u;
+    qf[kk][1] = r_hi < a.Nq ? *reinterpret_cast<const uint32_t*>(qhi + c0) : 0u;
+    qf[kk][2] = r_lo < a.Nq ? *reinterpret_cast<const uint32_t*>(qlo + c1) : 0u;
+    qf[kk][3] = r_hi < a.Nq ? *reinterpret_cast<const uint32_t*>(qhi + c1) : 0u;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (row0 >= a.Nq) return;                        // row group past the last query (no block-wide barrier follows)
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  for (int kb = 0; kb < nkp; kb += 64) {
+    const int ntiles = min(8, (nkp - kb) >> 3);
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      if (j < ntiles) {
+        const __half* kr = sK + (kb + j * 8 + g) * BI_KS + 2 * t;
+#pragma unroll
+        for (int kk = 0; kk < BI_HD / 16; ++kk)
+          bi_mma_16816(s[j], qf[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16), *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+      }
+    }
+    float bm_lo = -INFINITY, bm_hi = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = kb + j * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (j < ntiles) && (key + (e & 1) < nk);
+        s[j][e] = ok ? s[j][e] * a.scale_log2 : -INFINITY;
+      }
+      bm_lo = fmaxf(bm_lo, fmaxf(s[j][0], s[j][1])); bm_hi = fmaxf(bm_hi, fmaxf(s[j][2], s[j][3]));
+    }
+    bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1)); bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
+    bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1)); bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+    const float mn_lo = fmaxf(m_lo, bm_lo), mn_hi = fmaxf(m_hi, bm_hi);
+    const float ref_lo = mn_lo == -INFINITY ? 0.f : mn_lo, ref_hi = mn_hi == -INFINITY ? 0.f : mn_hi;
+    const float al_lo = exp2f(m_lo - ref_lo), al_hi = exp2f(m_hi - ref_hi);
+    m_lo = mn_lo; m_hi = mn_hi;
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f(s[j][0] - ref_lo); s[j][1] = exp2f(s[j][1] - ref_lo);
+      s[j][2] = exp2f(s[j][2] - ref_hi); s[j][3] = exp2f(s[j][3] - ref_hi);
+      sum_lo += s[j][0] + s[j][1]; sum_hi += s[j][2] + s[j][3];
+    }
+    l_lo = l_lo * al_lo + sum_lo; l_hi = l_hi * al_hi + sum_hi;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { o[i][0] *= al_lo; o[i][1] *= al_lo; o[i][2] *= al_hi; o[i][3] *= al_hi; }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (2 * p < ntiles) {
+        uint32_t pa[4];
+        pa[0] = bi_pack(s[2 * p][0], s[2 * p][1]); pa[1] = bi_pack(s[2 * p][2], s[2 * p][3]);
+        pa[2] = bi_pack(s[2 * p + 1][0], s[2 * p + 1][1]); pa[3] = bi_pack(s[2 * p + 1][2], s[2 * p + 1][3]);
+        const __half* vr = sV + (kb + p * 16 + (lane & 15)) * BI_KS + half * 128;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          uint32_t b0, b1;
+          bi_ldm_x2t(b0, b1, vr + i * 8);
+          bi_mma_16816(o[i], pa, b0, b1);
+        }
+      }
+    }
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  if (a.chunks == 1) {
+    const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+    __half* olo = a.o16 + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * BI_HD + half * 128;
+    __half* ohi = a.o16 + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * BI_HD + half * 128;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = i * 8 + 2 * t;
+      if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = bi_pack(o[i][0] * inv_lo, o[i][1] * inv_lo);
+      if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = bi_pack(o[i][2] * inv_hi, o[i][3] * inv_hi);
+    }
+  } else {
+    float* plo = a.part + ((((size_t)b * a.H + h) * a.chunks + ch) * a.NqP + r_lo) * 258;
+    float* phi = a.part + ((((size_t)b * a.H + h) * a.chunks + ch) * a.NqP + r_hi) * 258;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = half * 128 + i * 8 + 2 * t;
+      if (r_lo < a.Nq) *reinterpret_cast<float2*>(plo + c) = make_float2(o[i][0], o[i][1]);
+      if (r_hi < a.Nq) *reinterpret_cast<float2*>(phi + c) = make_float2(o[i][2], o[i][3]);
+    }
+    if (half == 0 && t == 0) {
+      if (r_lo < a.Nq) { plo[256] = m_lo; plo[257] = l_lo; }
+      if (r_hi < a.Nq) { phi[256] = m_hi; phi[257] = l_hi; }
+    }
+  }
+}
+// log-sum-exp merge of the key chunks: one block per (b, h, query row), thread = channel
+__global__ void __launch_bounds__(256)
+biattn_merge_kernel(const float* __restrict__ part, __half* __restrict__ o16, int H, int Nq, int NqP, int chunks, int ldo) {
+  const int row = blockIdx.x, h = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
+  const float* p = part + (((size_t)b * H + h) * chunks * NqP + row) * 258;
+  const size_t cs = (size_t)NqP * 258;
+  float M = -INFINITY;
+  for (int k = 0; k < chunks; ++k) M = fmaxf(M, p[k * cs + 256]);
+  float L = 0.f, acc = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    const float w = exp2f(p[k * cs + 256] - M);
+    L += p[k * cs + 257] * w;
+    acc += p[k * cs + c] * w;
+  }
+  o16[((size_t)b * Nq + row) * ldo + (size_t)h * 256 + c] = __float2half_rn(acc / L);
+}
+
 }  // namespace vlfm
 
 using namespace vlfm;
@@ -256,5 +423,42 @@ extern "C" int vlfm_cast_addpos_f16(const float* d_x, const float* d_pos, void* 
   cast_addpos_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)d_x, (const float4*)d_pos, (uint2*)d_out_x16, (uint2*)d_out_xp16, n4);
   VLFM_CHECK_LAUNCH("vlfm_cast_addpos_f16");
   count_launch();
+  return VLFM_OK;
+}
+
+// softmax(scale * q k^T) v per (batch, head) for head_dim 256 (GroundingDINO fusion layers).  q [B*Nq, ldq], k [B*Nk, ldk],
+// v [B*Nk, ldv] fp16 with head h at column h*256; out fp16 [B*Nq, ldo].  Keys are split into chunks of `key_chunk`
+// (multiple of 16, <= 192) over CTAs when Nk exceeds it; d_part then needs B*heads*chunks*ceil64(Nq)*258 floats.
+extern "C" int vlfm_biattn_f16(const void* d_q, const void* d_k, const void* d_v, void* d_out16, float* d_part, size_t part_floats, int B,
+                               int heads, int Nq, int Nk, int ldq, int ldk, int ldv, int ldo, int key_chunk, float scale, void* stream) {
+  if (!d_q || !d_k || !d_v || !d_out16 || B < 1 || heads < 1 || Nq < 1 || Nk < 1 || key_chunk < 16 || key_chunk > 192 || (key_chunk & 15) ||
+      (ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 1)) { set_error("vlfm_biattn_f16: bad argument"); return VLFM_E_INVALID; }
+  BiAttnArgs a{};
+  a.q = (const __half*)d_q; a.k = (const __half*)d_k; a.v = (const __half*)d_v; a.o16 = (__half*)d_out16; a.part = d_part;
+  a.B = B; a.H = heads; a.Nq = Nq; a.Nk = Nk; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.KC = Nk <= key_chunk ? ((Nk + 15) & ~15) : key_chunk;
+  a.chunks = (Nk + a.KC - 1) / a.KC;
+  const int qblocks = (Nq + 63) / 64;
+  a.NqP = qblocks * 64;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  if (a.chunks > 1 && (!d_part || part_floats < (size_t)B * heads * a.chunks * a.NqP * 258)) {
+    set_error("vlfm_biattn_f16: partial buffer too small (%zu floats needed)", (size_t)B * heads * a.chunks * a.NqP * 258); return VLFM_E_INVALID;
+  }
+  const size_t smem = (size_t)2 * a.KC * BI_KS * 2;
+  static bool cfg = false;
+  if (!cfg) {
+    int rc = check_cuda(cudaFuncSetAttribute(biattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 192 * BI_KS * 2), "attr(biattn)");
+    if (rc) return rc; cfg = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((long)qblocks * a.chunks > 0x7fffffffL || heads > 65535 || B > 65535) { set_error("vlfm_biattn_f16: grid too large"); return VLFM_E_INVALID; }
+  biattn_kernel<<<dim3((unsigned)(qblocks * a.chunks), heads, B), 256, smem, st>>>(a);
+  VLFM_CHECK_LAUNCH("biattn_kernel");
+  count_launch();
+  if (a.chunks > 1) {
+    biattn_merge_kernel<<<dim3(Nq, heads, B), 256, 0, st>>>(d_part, (__half*)d_out16, heads, Nq, a.NqP, a.chunks, ldo);
+    VLFM_CHECK_LAUNCH("biattn_merge_kernel");
+    count_launch();
+  }
   return VLFM_OK;
 }

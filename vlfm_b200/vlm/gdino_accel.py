@@ -163,18 +163,87 @@ class TcDeformableLayer(torch.nn.Module):
         return y.view(b, s, d), None
 
 
+def biattn_f16(q, k, v, b: int, heads: int, nq: int, nk: int, scale: float, key_chunk: int = 128) -> torch.Tensor:
+    """softmax(scale q k^T) v per (batch, head), head_dim 256; q/k/v are fp16 2-D (strided column views allowed)."""
+    out = torch.empty((b * nq, heads * 256), dtype=torch.float16, device=q.device)
+    part = None
+    if nk > key_chunk:
+        chunks = (nk + key_chunk - 1) // key_chunk
+        part = torch.empty(b * heads * chunks * ((nq + 63) // 64 * 64) * 258, dtype=torch.float32, device=q.device)
+    rc = _lib.load().vlfm_biattn_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _lib.ptr(part), 0 if part is None else part.numel(),
+                                    b, heads, nq, nk, q.stride(0), k.stride(0), v.stride(0), out.stride(0), key_chunk, float(scale),
+                                    _lib.stream_ptr())
+    _lib.check(rc, "vlfm_biattn_f16")
+    return out
+
+
+class TcFusionLayer(torch.nn.Module):
+    """``GroundingDinoFusionLayer.forward`` (groundingdino BiAttentionBlock: pre-LN, bi-directional image<->text attention,
+    layer-scaled residuals) on the library's kernels: ``vlfm_layernorm`` -> ONE GEMM per modality for (query|value) resp.
+    (key|value) projections with fp16 out -> ``vlfm_biattn_f16`` in both directions -> output GEMMs with the layer scale
+    folded into the weights and the residual add in the epilogue.  The reference's global-max subtraction and +-50000 clamp
+    are softmax-invariant for finite logits and are not reproduced.  No padding masks (see TcDeformAttn); captions longer
+    than 128 tokens fall back to the original module."""
+
+    MAX_TEXT = 128
+
+    def __init__(self, m):
+        super().__init__()
+        at = m.attn
+        assert at.head_dim == 256
+        self.heads, self.scale = at.num_heads, at.scale
+        wq, bq = _w16(at.vision_proj); wvv, bvv = _w16(at.values_vision_proj)
+        wk, bk = _w16(at.text_proj); wvt, bvt = _w16(at.values_text_proj)
+        gv, gt = m.vision_param.detach().float(), m.text_param.detach().float()
+        wov = (at.out_vision_proj.weight.detach().float() * gv[:, None]).to(torch.float16).contiguous()
+        wot = (at.out_text_proj.weight.detach().float() * gt[:, None]).to(torch.float16).contiguous()
+        bufs = {"wv": torch.cat([wq, wvv]).contiguous(), "bv": torch.cat([bq, bvv]).contiguous(),
+                "wt": torch.cat([wk, wvt]).contiguous(), "bt": torch.cat([bk, bvt]).contiguous(),
+                "wov": wov, "bov": (at.out_vision_proj.bias.detach().float() * gv).contiguous(),
+                "wot": wot, "bot": (at.out_text_proj.bias.detach().float() * gt).contiguous(),
+                "gv": m.layer_norm_vision.weight.detach().float().contiguous(), "bev": m.layer_norm_vision.bias.detach().float().contiguous(),
+                "gt": m.layer_norm_text.weight.detach().float().contiguous(), "bet": m.layer_norm_text.bias.detach().float().contiguous()}
+        for n, t in bufs.items():
+            self.register_buffer(n, t, persistent=False)
+        self.epsv, self.epst = m.layer_norm_vision.eps, m.layer_norm_text.eps
+        self.e = self.heads * 256
+        self.orig = [m]
+
+    def forward(self, vision_features, text_features, attention_mask_vision=None, attention_mask_text=None):
+        from .dense import gemm_f16, layernorm
+
+        b, nv, d = vision_features.shape
+        t = text_features.shape[1]
+        if t > self.MAX_TEXT:
+            return self.orig[0](vision_features, text_features, attention_mask_vision, attention_mask_text)
+        v16, v32 = layernorm(vision_features.reshape(b * nv, d).contiguous(), self.gv, self.bev, self.epsv, want16=True, want32=True)
+        t16, t32 = layernorm(text_features.reshape(b * t, d).contiguous(), self.gt, self.bet, self.epst, want16=True, want32=True)
+        qv = gemm_f16(v16, self.wv, self.bv, _lib.EPI_BIAS_F16)            # [b*nv, 2e]: image queries | image values
+        kt = gemm_f16(t16, self.wt, self.bt, _lib.EPI_BIAS_F16)            # [b*t, 2e]: text keys | text values
+        e = self.e
+        ov = biattn_f16(qv[:, :e], kt[:, :e], kt[:, e:], b, self.heads, nv, t, self.scale)      # image <- text
+        ot = biattn_f16(kt[:, :e], qv[:, :e], qv[:, e:], b, self.heads, t, nv, self.scale)      # text <- image
+        gemm_f16(ov, self.wov, self.bov, _lib.EPI_BIAS_RESID_F32, out=v32)  # LN(x) + gamma * out_proj(attn)
+        gemm_f16(ot, self.wot, self.bot, _lib.EPI_BIAS_RESID_F32, out=t32)
+        return (v32.view(b, nv, d), None), (t32.view(b, t, d), None)
+
+
 def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
     """Swap the primitives in place (model already on the GPU).  Returns counts for the log / tests."""
     from transformers.models.grounding_dino.modeling_grounding_dino import (GroundingDinoDeformableLayer,
                                                                            GroundingDinoMultiscaleDeformableAttention,
                                                                            MultiScaleDeformableAttention)
 
-    n_lin = n_msda = n_skip = n_layer = n_attn = 0
+    from transformers.models.grounding_dino.modeling_grounding_dino import GroundingDinoFusionLayer
+
+    n_lin = n_msda = n_skip = n_layer = n_attn = n_fuse = 0
     assert getattr(model.config, "activation_function", "relu") == "relu"
     for parent in list(model.modules()):
         for name, child in list(parent.named_children()):
             if isinstance(child, GroundingDinoDeformableLayer):
                 setattr(parent, name, TcDeformableLayer(child)); n_layer += 1
+            elif isinstance(child, GroundingDinoFusionLayer) and child.attn.head_dim == 256:
+                setattr(parent, name, TcFusionLayer(child)); n_fuse += 1
     for parent in list(model.modules()):
         for name, child in list(parent.named_children()):
             if isinstance(child, GroundingDinoMultiscaleDeformableAttention):
@@ -188,4 +257,4 @@ def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
                     n_skip += 1
             elif isinstance(child, MultiScaleDeformableAttention):
                 setattr(parent, name, TcMSDA()); n_msda += 1
-    return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda, "deformable_layers": n_layer, "deformable_attn": n_attn}
+    return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda, "deformable_layers": n_layer, "deformable_attn": n_attn, "fusion_layers": n_fuse}
