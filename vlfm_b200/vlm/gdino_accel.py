@@ -228,6 +228,27 @@ class TcFusionLayer(torch.nn.Module):
         return (v32.view(b, nv, d), None), (t32.view(b, t, d), None)
 
 
+class CachedTextBackbone(torch.nn.Module):
+    """The BERT text tower depends only on the caption: its output is computed once per (caption ids, batch) and reused
+    (the reference re-runs it for every frame: groundingdino ... predict -> model(image, captions=[caption]))."""
+
+    def __init__(self, inner: torch.nn.Module, max_entries: int = 8):
+        super().__init__()
+        self.inner = inner
+        self.key = None                  # set by GroundingDINO.raw_outputs_device before every forward
+        self.cache: dict = {}
+        self.max_entries = max_entries
+
+    def forward(self, *args, **kwargs):
+        if self.key is None:
+            return self.inner(*args, **kwargs)
+        if self.key not in self.cache:
+            if len(self.cache) >= self.max_entries:
+                self.cache.pop(next(iter(self.cache)))
+            self.cache[self.key] = self.inner(*args, **kwargs)
+        return self.cache[self.key]
+
+
 def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
     """Swap the primitives in place (model already on the GPU).  Returns counts for the log / tests."""
     from transformers.models.grounding_dino.modeling_grounding_dino import (GroundingDinoDeformableLayer,
@@ -257,4 +278,6 @@ def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
                     n_skip += 1
             elif isinstance(child, MultiScaleDeformableAttention):
                 setattr(parent, name, TcMSDA()); n_msda += 1
+    if hasattr(model, "model") and hasattr(model.model, "text_backbone"):
+        model.model.text_backbone = CachedTextBackbone(model.model.text_backbone)
     return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda, "deformable_layers": n_layer, "deformable_attn": n_attn, "fusion_layers": n_fuse}

@@ -102,6 +102,9 @@ class GroundingDINO:
         """images [B,H,W,3] uint8 on the device -> (sigmoid logits [B,900,256], boxes [B,900,4] cxcywh)."""
         self._features.maps = self.backbone.forward(images)
         b, h, w = images.shape[:3]
+        tb = self.model.model.text_backbone
+        if hasattr(tb, "key"):
+            tb.key = (tuple(int(i) for i in input_ids), int(b))
         ids = torch.tensor([input_ids], dtype=torch.long, device=self.device).expand(b, -1).contiguous()
         dummy = torch.zeros(b, 3, h, w, device=self.device)  # only its shape is used (pixel mask); features come from our engine
         out = self.model(pixel_values=dummy, input_ids=ids, token_type_ids=torch.zeros_like(ids), attention_mask=torch.ones_like(ids),
