@@ -224,12 +224,15 @@ int vlfm_msda_forward(const void* d_value, int value_is_f16, const float* d_loc,
 int vlfm_msda_fused(const void* d_value16, const float* d_offlog, int ld, int logit_col, const float* d_ref, int ref_dim,
                     void* d_out16, int B, int S, int Q, int heads, int levels, int points, const int32_t* h_shapes_hw,
                     void* stream);
-/* softmax(scale * q k^T) v per (batch, head), head_dim 256: both directions of GroundingDINO's fusion-layer
+/* softmax(scale * q k^T) v per (batch, head) for head_dim 256 -- both directions of GroundingDINO's fusion-layer
  * BiMultiHeadAttention (image<-text: few keys, one chunk; text<-image: thousands of keys split into `key_chunk`-sized chunks over
- * CTAs and merged).  q [B*Nq, ldq], k [B*Nk, ldk], v [B*Nk, ldv] fp16, head h at column h*256; d_out16 [B*Nq, ldo] fp16.
- * d_part (needed when Nk > key_chunk): B*heads*ceil(Nk/key_chunk)*ceil64(Nq)*258 floats. */
+ * CTAs and merged) -- or head_dim 32 (decoder self-attention over the 900 queries and text cross-attention).
+ * q [B*Nq, ldq], k [B*Nk, ldk], v [B*Nk, ldv] fp16, head h at column h*head_dim; d_out16 [B*Nq, ldo] fp16.  key_chunk: multiple
+ * of 16, <= 192 (head_dim 256) / <= 1024 (32).  d_part (needed when Nk > key_chunk):
+ * B*heads*ceil(Nk/key_chunk)*ceilR(Nq)*(head_dim+2) floats, R = 64 / 128. */
 int vlfm_biattn_f16(const void* d_q, const void* d_k, const void* d_v, void* d_out16, float* d_part, size_t part_floats, int B,
-                    int heads, int Nq, int Nk, int ldq, int ldk, int ldv, int ldo, int key_chunk, float scale, void* stream);
+                    int heads, int head_dim, int Nq, int Nk, int ldq, int ldk, int ldv, int ldo, int key_chunk, float scale,
+                    void* stream);
 /* fp32 -> fp16 (round to nearest even) staging of GEMM operands. */
 int vlfm_cast_f32_f16(const float* d_in, void* d_out16, long n, void* stream);
 /* out_x16 = fp16(x), out_xp16 = fp16(x + pos) (query/key = hidden + position embedding); n % 4 == 0; either output may be NULL. */

@@ -106,7 +106,7 @@ def test_tc_linear_and_cast_vs_torch():
 def test_accelerated_primitives_are_installed(pair):
     _, g = pair
     # 6 encoder deformable layers rewritten whole, 6 decoder cross-attentions, every other nn.Linear on the tcgen05 GEMM
-    assert g.accel["deformable_layers"] == 6 and g.accel["deformable_attn"] == 6 and g.accel["fusion_layers"] == 6, g.accel
+    assert g.accel["deformable_layers"] == 6 and g.accel["decoder_layers"] == 6 and g.accel["fusion_layers"] == 6, g.accel
     assert g.accel["linear"] > 60, g.accel
 
 
@@ -191,3 +191,60 @@ def test_fusion_layer_vs_hf_module():
     ev, et = (gv - wv).abs(), (gt - wt).abs()
     print("fusion vision max", float(ev.max()), "mean", float(ev.mean()), "text max", float(et.max()), "mean", float(et.mean()))
     assert float(ev.max()) <= 3e-2 and float(ev.mean()) <= 3e-3 and float(et.max()) <= 3e-2 and float(et.mean()) <= 3e-3
+
+
+@pytest.mark.parametrize("nq,nk,kc", [(900, 900, 0), (900, 12, 0), (130, 2000, 512), (7, 33, 0)])
+def test_biattn_head_dim_32_vs_torch(nq, nk, kc):
+    """Decoder-shaped attention (8 heads x 32) on vlfm_biattn_f16 against fp32 torch attention; tolerance 3e-3."""
+    from vlfm_b200.vlm.gdino_accel import biattn_f16
+
+    torch.manual_seed(nq + nk)
+    b, heads = 3, 8
+    qk = (torch.randn(b * nq, 2 * heads * 32, device="cuda")).half()
+    q = qk[:, : heads * 32]
+    kv = (torch.randn(b * nk, 2 * heads * 32, device="cuda")).half()
+    k, v = kv[:, : heads * 32], kv[:, heads * 32 :]
+    scale = 32 ** -0.5
+    got = biattn_f16(q, k, v, b, heads, nq, nk, scale, key_chunk=kc, head_dim=32)
+    qf = q.float().reshape(b, nq, heads, 32).transpose(1, 2)
+    kf = k.float().reshape(b, nk, heads, 32).transpose(1, 2)
+    vf = v.float().reshape(b, nk, heads, 32).transpose(1, 2)
+    want = (torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf).transpose(1, 2).reshape(b * nq, heads * 32)
+    torch.cuda.synchronize()
+    err = float((got.float() - want).abs().max())
+    print("biattn32", nq, nk, "max abs err", err)
+    assert err <= 3e-3
+
+
+def test_decoder_layer_vs_hf_module():
+    """TcDecoderLayer against the HF fp32 GroundingDinoDecoderLayer it replaces; fp16 operands: max <= 5e-2, mean <= 5e-3 on
+    LayerNorm-scaled (O(1)) outputs."""
+    from transformers import GroundingDinoConfig
+    from transformers.models.grounding_dino.modeling_grounding_dino import GroundingDinoDecoderLayer
+    from vlfm_b200.vlm.gdino_accel import TcDecoderLayer
+
+    torch.manual_seed(4)
+    m = GroundingDinoDecoderLayer(GroundingDinoConfig()).cuda().eval()
+    with torch.no_grad():
+        m.encoder_attn.sampling_offsets.weight.normal_(0, 0.05); m.encoder_attn.sampling_offsets.bias.normal_(0, 1.0)
+        m.encoder_attn.attention_weights.weight.normal_(0, 0.05); m.encoder_attn.attention_weights.bias.normal_(0, 0.5)
+    shapes = [(30, 40), (15, 20), (8, 10), (4, 5)]
+    s = sum(h * w for h, w in shapes)
+    b, nq, t = 2, 900, 11
+    hid = torch.randn(b, nq, 256, device="cuda")
+    pos = torch.randn(b, nq, 256, device="cuda") * 0.5
+    enc = torch.randn(b, s, 256, device="cuda")
+    txt = torch.randn(b, t, 256, device="cuda")
+    ref = torch.rand(b, nq, 4, 4, device="cuda"); ref[..., 2:] *= 0.3
+    sp = torch.tensor(shapes, device="cuda")
+    start = torch.cat([sp.new_zeros(1), (sp[:, 0] * sp[:, 1]).cumsum(0)[:-1]])
+    kw = dict(position_embeddings=pos, reference_points=ref, spatial_shapes=sp, spatial_shapes_list=shapes, level_start_index=start,
+              vision_encoder_hidden_states=enc, vision_encoder_attention_mask=None, text_encoder_hidden_states=txt,
+              text_encoder_attention_mask=None, self_attn_mask=None)
+    with torch.no_grad():
+        want = m(hid, **kw)[0]
+        got = TcDecoderLayer(m)(hid, **kw)[0]
+    torch.cuda.synchronize()
+    err = (got - want).abs()
+    print("decoder layer max", float(err.max()), "mean", float(err.mean()))
+    assert float(err.max()) <= 5e-2 and float(err.mean()) <= 5e-3

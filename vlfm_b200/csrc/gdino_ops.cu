@@ -204,13 +204,15 @@ __device__ __forceinline__ void bi_ldm_x2t(uint32_t& r0, uint32_t& r1, const __h
   uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
-constexpr int BI_HD = 256, BI_KS = BI_HD + 8;
 
+// HD = head_dim, NS = channel splits per row group: 8 warps = (8 / NS) row groups of 16 queries x NS channel slices of HD / NS
+template <int HD, int NS>
 __global__ void __launch_bounds__(256)
 biattn_kernel(BiAttnArgs a) {
+  constexpr int BI_HD = HD, BI_KS = HD + 8, CW = HD / NS, RPB = 16 * (8 / NS);
   extern __shared__ __align__(16) uint8_t bi_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int rg = warp >> 1, half = warp & 1;
+  const int rg = warp / NS, half = warp % NS;
   const int qb = blockIdx.x / a.chunks, ch = blockIdx.x - qb * a.chunks, h = blockIdx.y, b = blockIdx.z;
   const int k0 = ch * a.KC, nk = min(a.KC, a.Nk - k0), nkp = (nk + 15) & ~15;
   __half* sK = reinterpret_cast<__half*>(bi_smem);
@@ -218,7 +220,7 @@ biattn_kernel(BiAttnArgs a) {
   const __half* kbase = a.k + ((size_t)b * a.Nk + k0) * a.ldk + (size_t)h * BI_HD;
   const __half* vbase = a.v + ((size_t)b * a.Nk + k0) * a.ldv + (size_t)h * BI_HD;
   for (int i = tid; i < nkp * (BI_HD / 8); i += 256) {
-    const int key = i >> 5, c = (i & 31) * 8;
+    const int key = i / (BI_HD / 8), c = (i % (BI_HD / 8)) * 8;
     const bool ok = key < nk;
     const __half* ks = ok ? kbase + (size_t)key * a.ldk + c : kbase;
     const __half* vs = ok ? vbase + (size_t)key * a.ldv + c : vbase;
@@ -228,7 +230,7 @@ biattn_kernel(BiAttnArgs a) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vd), "l"(vs), "r"(nb) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  const int row0 = qb * 64 + rg * 16, r_lo = row0 + g, r_hi = row0 + g + 8;
+  const int row0 = qb * RPB + rg * 16, r_lo = row0 + g, r_hi = row0 + g + 8;
   const __half* qlo = a.q + ((size_t)b * a.Nq + r_lo) * a.ldq + (size_t)h * BI_HD;
   const __half* qhi = a.q + ((size_t)b * a.Nq + r_hi) * a.ldq + (size_t)h * BI_HD;
   uint32_t qf[BI_HD / 16][4];
@@ -243,9 +245,9 @@ biattn_kernel(BiAttnArgs a) {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (row0 >= a.Nq) return;                        // row group past the last query (no block-wide barrier follows)
-  float o[16][4];
+  float o[CW / 8][4];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  for (int i = 0; i < CW / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
   for (int kb = 0; kb < nkp; kb += 64) {
     const int ntiles = min(8, (nkp - kb) >> 3);
@@ -286,16 +288,16 @@ biattn_kernel(BiAttnArgs a) {
     }
     l_lo = l_lo * al_lo + sum_lo; l_hi = l_hi * al_hi + sum_hi;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { o[i][0] *= al_lo; o[i][1] *= al_lo; o[i][2] *= al_hi; o[i][3] *= al_hi; }
+    for (int i = 0; i < CW / 8; ++i) { o[i][0] *= al_lo; o[i][1] *= al_lo; o[i][2] *= al_hi; o[i][3] *= al_hi; }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       if (2 * p < ntiles) {
         uint32_t pa[4];
         pa[0] = bi_pack(s[2 * p][0], s[2 * p][1]); pa[1] = bi_pack(s[2 * p][2], s[2 * p][3]);
         pa[2] = bi_pack(s[2 * p + 1][0], s[2 * p + 1][1]); pa[3] = bi_pack(s[2 * p + 1][2], s[2 * p + 1][3]);
-        const __half* vr = sV + (kb + p * 16 + (lane & 15)) * BI_KS + half * 128;
+        const __half* vr = sV + (kb + p * 16 + (lane & 15)) * BI_KS + half * CW;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < CW / 8; ++i) {
           uint32_t b0, b1;
           bi_ldm_x2t(b0, b1, vr + i * 8);
           bi_mma_16816(o[i], pa, b0, b1);
@@ -307,44 +309,44 @@ biattn_kernel(BiAttnArgs a) {
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
   if (a.chunks == 1) {
     const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
-    __half* olo = a.o16 + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * BI_HD + half * 128;
-    __half* ohi = a.o16 + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * BI_HD + half * 128;
+    __half* olo = a.o16 + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * BI_HD + half * CW;
+    __half* ohi = a.o16 + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * BI_HD + half * CW;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < CW / 8; ++i) {
       const int c = i * 8 + 2 * t;
       if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = bi_pack(o[i][0] * inv_lo, o[i][1] * inv_lo);
       if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = bi_pack(o[i][2] * inv_hi, o[i][3] * inv_hi);
     }
   } else {
-    float* plo = a.part + ((((size_t)b * a.H + h) * a.chunks + ch) * a.NqP + r_lo) * 258;
-    float* phi = a.part + ((((size_t)b * a.H + h) * a.chunks + ch) * a.NqP + r_hi) * 258;
+    float* plo = a.part + ((((size_t)b * a.H + h) * a.chunks + ch) * a.NqP + r_lo) * (HD + 2);
+    float* phi = a.part + ((((size_t)b * a.H + h) * a.chunks + ch) * a.NqP + r_hi) * (HD + 2);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int c = half * 128 + i * 8 + 2 * t;
+    for (int i = 0; i < CW / 8; ++i) {
+      const int c = half * CW + i * 8 + 2 * t;
       if (r_lo < a.Nq) *reinterpret_cast<float2*>(plo + c) = make_float2(o[i][0], o[i][1]);
       if (r_hi < a.Nq) *reinterpret_cast<float2*>(phi + c) = make_float2(o[i][2], o[i][3]);
     }
     if (half == 0 && t == 0) {
-      if (r_lo < a.Nq) { plo[256] = m_lo; plo[257] = l_lo; }
-      if (r_hi < a.Nq) { phi[256] = m_hi; phi[257] = l_hi; }
+      if (r_lo < a.Nq) { plo[HD] = m_lo; plo[HD + 1] = l_lo; }
+      if (r_hi < a.Nq) { phi[HD] = m_hi; phi[HD + 1] = l_hi; }
     }
   }
 }
 // log-sum-exp merge of the key chunks: one block per (b, h, query row), thread = channel
-__global__ void __launch_bounds__(256)
-biattn_merge_kernel(const float* __restrict__ part, __half* __restrict__ o16, int H, int Nq, int NqP, int chunks, int ldo) {
+__global__ void biattn_merge_kernel(const float* __restrict__ part, __half* __restrict__ o16, int H, int Nq, int NqP, int chunks, int ldo, int HD) {
   const int row = blockIdx.x, h = blockIdx.y, b = blockIdx.z, c = threadIdx.x;
-  const float* p = part + (((size_t)b * H + h) * chunks * NqP + row) * 258;
-  const size_t cs = (size_t)NqP * 258;
+  const int PW = HD + 2;
+  const float* p = part + (((size_t)b * H + h) * chunks * NqP + row) * PW;
+  const size_t cs = (size_t)NqP * PW;
   float M = -INFINITY;
-  for (int k = 0; k < chunks; ++k) M = fmaxf(M, p[k * cs + 256]);
+  for (int k = 0; k < chunks; ++k) M = fmaxf(M, p[k * cs + HD]);
   float L = 0.f, acc = 0.f;
   for (int k = 0; k < chunks; ++k) {
-    const float w = exp2f(p[k * cs + 256] - M);
-    L += p[k * cs + 257] * w;
+    const float w = exp2f(p[k * cs + HD] - M);
+    L += p[k * cs + HD + 1] * w;
     acc += p[k * cs + c] * w;
   }
-  o16[((size_t)b * Nq + row) * ldo + (size_t)h * 256 + c] = __float2half_rn(acc / L);
+  o16[((size_t)b * Nq + row) * ldo + (size_t)h * HD + c] = __float2half_rn(acc / L);
 }
 
 }  // namespace vlfm
@@ -426,37 +428,47 @@ extern "C" int vlfm_cast_addpos_f16(const float* d_x, const float* d_pos, void* 
   return VLFM_OK;
 }
 
-// softmax(scale * q k^T) v per (batch, head) for head_dim 256 (GroundingDINO fusion layers).  q [B*Nq, ldq], k [B*Nk, ldk],
-// v [B*Nk, ldv] fp16 with head h at column h*256; out fp16 [B*Nq, ldo].  Keys are split into chunks of `key_chunk`
-// (multiple of 16, <= 192) over CTAs when Nk exceeds it; d_part then needs B*heads*chunks*ceil64(Nq)*258 floats.
+// softmax(scale * q k^T) v per (batch, head) for head_dim 256 (GroundingDINO fusion layers) or 32 (decoder self / text
+// cross attention).  q [B*Nq, ldq], k [B*Nk, ldk], v [B*Nk, ldv] fp16 with head h at column h*head_dim; out fp16 [B*Nq, ldo].
+// Keys are split into chunks of `key_chunk` (multiple of 16; <= 192 for head_dim 256, <= 1024 for 32) over CTAs when Nk
+// exceeds it; d_part then needs B*heads*chunks*ceilR(Nq)*(head_dim+2) floats (R = 64 resp. 128 query rows per CTA).
 extern "C" int vlfm_biattn_f16(const void* d_q, const void* d_k, const void* d_v, void* d_out16, float* d_part, size_t part_floats, int B,
-                               int heads, int Nq, int Nk, int ldq, int ldk, int ldv, int ldo, int key_chunk, float scale, void* stream) {
-  if (!d_q || !d_k || !d_v || !d_out16 || B < 1 || heads < 1 || Nq < 1 || Nk < 1 || key_chunk < 16 || key_chunk > 192 || (key_chunk & 15) ||
-      (ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 1)) { set_error("vlfm_biattn_f16: bad argument"); return VLFM_E_INVALID; }
+                               int heads, int head_dim, int Nq, int Nk, int ldq, int ldk, int ldv, int ldo, int key_chunk, float scale,
+                               void* stream) {
+  const int kc_max = head_dim == 256 ? 192 : 1024;
+  if (!d_q || !d_k || !d_v || !d_out16 || B < 1 || heads < 1 || Nq < 1 || Nk < 1 || (head_dim != 256 && head_dim != 32) || key_chunk < 16 ||
+      key_chunk > kc_max || (key_chunk & 15) || (ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 1)) {
+    set_error("vlfm_biattn_f16: bad argument"); return VLFM_E_INVALID;
+  }
   BiAttnArgs a{};
   a.q = (const __half*)d_q; a.k = (const __half*)d_k; a.v = (const __half*)d_v; a.o16 = (__half*)d_out16; a.part = d_part;
   a.B = B; a.H = heads; a.Nq = Nq; a.Nk = Nk; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
   a.KC = Nk <= key_chunk ? ((Nk + 15) & ~15) : key_chunk;
   a.chunks = (Nk + a.KC - 1) / a.KC;
-  const int qblocks = (Nq + 63) / 64;
-  a.NqP = qblocks * 64;
+  const int rpb = head_dim == 256 ? 64 : 128;
+  const int qblocks = (Nq + rpb - 1) / rpb;
+  a.NqP = qblocks * rpb;
   a.scale_log2 = scale * 1.4426950408889634f;
-  if (a.chunks > 1 && (!d_part || part_floats < (size_t)B * heads * a.chunks * a.NqP * 258)) {
-    set_error("vlfm_biattn_f16: partial buffer too small (%zu floats needed)", (size_t)B * heads * a.chunks * a.NqP * 258); return VLFM_E_INVALID;
+  const size_t need = (size_t)B * heads * a.chunks * a.NqP * (head_dim + 2);
+  if (a.chunks > 1 && (!d_part || part_floats < need)) {
+    set_error("vlfm_biattn_f16: partial buffer too small (%zu floats needed)", need); return VLFM_E_INVALID;
   }
-  const size_t smem = (size_t)2 * a.KC * BI_KS * 2;
+  const size_t smem = (size_t)2 * a.KC * (head_dim + 8) * 2;
   static bool cfg = false;
   if (!cfg) {
-    int rc = check_cuda(cudaFuncSetAttribute(biattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 192 * BI_KS * 2), "attr(biattn)");
+    int rc = check_cuda(cudaFuncSetAttribute(biattn_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 192 * 264 * 2), "attr(biattn256)");
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(biattn_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 1024 * 40 * 2), "attr(biattn32)");
     if (rc) return rc; cfg = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if ((long)qblocks * a.chunks > 0x7fffffffL || heads > 65535 || B > 65535) { set_error("vlfm_biattn_f16: grid too large"); return VLFM_E_INVALID; }
-  biattn_kernel<<<dim3((unsigned)(qblocks * a.chunks), heads, B), 256, smem, st>>>(a);
+  const dim3 grid((unsigned)(qblocks * a.chunks), heads, B);
+  if (head_dim == 256) biattn_kernel<256, 2><<<grid, 256, smem, st>>>(a);
+  else biattn_kernel<32, 1><<<grid, 256, smem, st>>>(a);
   VLFM_CHECK_LAUNCH("biattn_kernel");
   count_launch();
   if (a.chunks > 1) {
-    biattn_merge_kernel<<<dim3(Nq, heads, B), 256, 0, st>>>(d_part, (__half*)d_out16, heads, Nq, a.NqP, a.chunks, ldo);
+    biattn_merge_kernel<<<dim3(Nq, heads, B), head_dim, 0, st>>>(d_part, (__half*)d_out16, heads, Nq, a.NqP, a.chunks, ldo, head_dim);
     VLFM_CHECK_LAUNCH("biattn_merge_kernel");
     count_launch();
   }

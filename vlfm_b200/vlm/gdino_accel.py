@@ -110,7 +110,10 @@ class TcDeformAttn(torch.nn.Module):
                    "vlfm_cast_addpos_f16")
         if not same:
             s = enc.shape[1]
-            x16 = cast_f16(enc.contiguous()).view(b * s, d)
+            x16 = getattr(enc, "_vlfm_f16", None)      # the six decoder layers read the same encoder output
+            if x16 is None:
+                x16 = cast_f16(enc.contiguous()).view(b * s, d)
+                enc._vlfm_f16 = x16
         else:
             s = q
         value16 = gemm_f16(x16, self.wv, self.bv, _lib.EPI_BIAS_F16)
@@ -163,15 +166,18 @@ class TcDeformableLayer(torch.nn.Module):
         return y.view(b, s, d), None
 
 
-def biattn_f16(q, k, v, b: int, heads: int, nq: int, nk: int, scale: float, key_chunk: int = 128) -> torch.Tensor:
-    """softmax(scale q k^T) v per (batch, head), head_dim 256; q/k/v are fp16 2-D (strided column views allowed)."""
-    out = torch.empty((b * nq, heads * 256), dtype=torch.float16, device=q.device)
+def biattn_f16(q, k, v, b: int, heads: int, nq: int, nk: int, scale: float, key_chunk: int = 0, head_dim: int = 256) -> torch.Tensor:
+    """softmax(scale q k^T) v per (batch, head), head_dim 256 or 32; q/k/v are fp16 2-D (strided column views allowed)."""
+    if key_chunk == 0:
+        key_chunk = 128 if head_dim == 256 else 1024
+    out = torch.empty((b * nq, heads * head_dim), dtype=torch.float16, device=q.device)
     part = None
     if nk > key_chunk:
         chunks = (nk + key_chunk - 1) // key_chunk
-        part = torch.empty(b * heads * chunks * ((nq + 63) // 64 * 64) * 258, dtype=torch.float32, device=q.device)
+        rpb = 64 if head_dim == 256 else 128
+        part = torch.empty(b * heads * chunks * ((nq + rpb - 1) // rpb * rpb) * (head_dim + 2), dtype=torch.float32, device=q.device)
     rc = _lib.load().vlfm_biattn_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _lib.ptr(part), 0 if part is None else part.numel(),
-                                    b, heads, nq, nk, q.stride(0), k.stride(0), v.stride(0), out.stride(0), key_chunk, float(scale),
+                                    b, heads, head_dim, nq, nk, q.stride(0), k.stride(0), v.stride(0), out.stride(0), key_chunk, float(scale),
                                     _lib.stream_ptr())
     _lib.check(rc, "vlfm_biattn_f16")
     return out
@@ -228,6 +234,84 @@ class TcFusionLayer(torch.nn.Module):
         return (v32.view(b, nv, d), None), (t32.view(b, t, d), None)
 
 
+class TcDecoderLayer(torch.nn.Module):
+    """``GroundingDinoDecoderLayer.forward`` (self-attention over the 900 queries, text cross-attention, deformable image
+    cross-attention, FFN; post-LN) on the library's kernels.  Attention masks are not supported (``self_attn_mask`` is None
+    at inference and captions are never padded on this path); a non-None ``self_attn_mask`` falls back to the original."""
+
+    def __init__(self, m):
+        super().__init__()
+        sa, ta = m.self_attn, m.encoder_attn_text
+        assert sa.attention_head_size == 32 and ta.attention_head_size == 32
+        self.heads = sa.num_attention_heads
+        self.deform = m.encoder_attn if isinstance(m.encoder_attn, TcDeformAttn) else TcDeformAttn(m.encoder_attn)
+        wq, bq = _w16(sa.query); wk, bk = _w16(sa.key); wv, bv = _w16(sa.value); wo, bo = _w16(sa.out_proj)
+        tq, tbq = _w16(ta.query); tk, tbk = _w16(ta.key); tv, tbv = _w16(ta.value); to, tbo = _w16(ta.out_proj)
+        w1, b1 = _w16(m.fc1); w2, b2 = _w16(m.fc2)
+        bufs = {"wqk": torch.cat([wq, wk]).contiguous(), "bqk": torch.cat([bq, bk]).contiguous(), "wv": wv, "bv": bv, "wo": wo, "bo": bo,
+                "xq": tq, "xbq": tbq, "xkv": torch.cat([tk, tv]).contiguous(), "xbkv": torch.cat([tbk, tbv]).contiguous(), "xo": to, "xbo": tbo,
+                "w1": w1, "b1": b1, "w2": w2, "b2": b2}
+        self.eps = []
+        for i, ln in enumerate((m.self_attn_layer_norm, m.encoder_attn_text_layer_norm, m.encoder_attn_layer_norm, m.final_layer_norm)):
+            bufs[f"g{i}"] = ln.weight.detach().float().contiguous(); bufs[f"be{i}"] = ln.bias.detach().float().contiguous()
+            self.eps.append(ln.eps)
+        for n, t in bufs.items():
+            self.register_buffer(n, t, persistent=False)
+        self.orig = [m]
+
+    def forward(self, hidden_states, position_embeddings=None, reference_points=None, spatial_shapes=None, spatial_shapes_list=None,
+                level_start_index=None, vision_encoder_hidden_states=None, vision_encoder_attention_mask=None,
+                text_encoder_hidden_states=None, text_encoder_attention_mask=None, self_attn_mask=None, output_attentions=False):
+        from .dense import gemm_f16, layernorm
+
+        if self_attn_mask is not None or output_attentions:
+            return self.orig[0](hidden_states, position_embeddings, reference_points, spatial_shapes, spatial_shapes_list, level_start_index,
+                                vision_encoder_hidden_states, vision_encoder_attention_mask, text_encoder_hidden_states,
+                                text_encoder_attention_mask, self_attn_mask, output_attentions)
+        lib = _lib.load()
+        b, nq, d = hidden_states.shape
+        t = text_encoder_hidden_states.shape[1]
+        scale = 32 ** -0.5
+        x = hidden_states.reshape(b * nq, d).clone()                              # fp32 residual stream
+        pos = None if position_embeddings is None else position_embeddings.expand(b, nq, d).reshape(b * nq, d).contiguous()
+
+        def with_pos(x32, want_plain):
+            xp16 = torch.empty((b * nq, d), dtype=torch.float16, device=x32.device)
+            x16 = torch.empty((b * nq, d), dtype=torch.float16, device=x32.device) if want_plain else None
+            _lib.check(lib.vlfm_cast_addpos_f16(x32.data_ptr(), _lib.ptr(pos), _lib.ptr(x16), xp16.data_ptr(), x32.numel(), _lib.stream_ptr()),
+                       "vlfm_cast_addpos_f16")
+            return x16, xp16
+
+        # ---- self-attention: q = k = x + pos, v = x
+        x16, xp16 = with_pos(x, True)
+        qk = gemm_f16(xp16, self.wqk, self.bqk, _lib.EPI_BIAS_F16)
+        v = gemm_f16(x16, self.wv, self.bv, _lib.EPI_BIAS_F16)
+        a = biattn_f16(qk[:, :d], qk[:, d:], v, b, self.heads, nq, nq, scale, head_dim=32)
+        gemm_f16(a, self.wo, self.bo, _lib.EPI_BIAS_RESID_F32, out=x)
+        _, x = layernorm(x, self.g0, self.be0, self.eps[0], want16=False, want32=True)
+        # ---- text cross-attention: q = x + pos, k = v = text
+        _, xp16 = with_pos(x, False)
+        q = gemm_f16(xp16, self.xq, self.xbq, _lib.EPI_BIAS_F16)
+        txt = text_encoder_hidden_states
+        t16 = getattr(txt, "_vlfm_f16", None)
+        if t16 is None:
+            t16 = cast_f16(txt.reshape(b * t, d).float().contiguous())
+            txt._vlfm_f16 = t16
+        kv = gemm_f16(t16, self.xkv, self.xbkv, _lib.EPI_BIAS_F16)
+        a = biattn_f16(q, kv[:, :d], kv[:, d:], b, self.heads, nq, t, scale, head_dim=32)
+        gemm_f16(a, self.xo, self.xbo, _lib.EPI_BIAS_RESID_F32, out=x)
+        _, x = layernorm(x, self.g1, self.be1, self.eps[1], want16=False, want32=True)
+        # ---- deformable cross-attention over the image features
+        out16 = self.deform.sample(x.view(b, nq, d), position_embeddings, vision_encoder_hidden_states, reference_points, spatial_shapes_list)
+        gemm_f16(out16, self.deform.wo, self.deform.bo, _lib.EPI_BIAS_RESID_F32, out=x)
+        x16, x = layernorm(x, self.g2, self.be2, self.eps[2], want16=True, want32=True)
+        # ---- FFN
+        h16 = gemm_f16(x16, self.w1, self.b1, _lib.EPI_BIAS_RELU_F16)
+        gemm_f16(h16, self.w2, self.b2, _lib.EPI_BIAS_RESID_F32, out=x)
+        _, y = layernorm(x, self.g3, self.be3, self.eps[3], want16=False, want32=True)
+        return (y.view(b, nq, d),)
+
+
 class CachedTextBackbone(torch.nn.Module):
     """The BERT text tower depends only on the caption: its output is computed once per (caption ids, batch) and reused
     (the reference re-runs it for every frame: groundingdino ... predict -> model(image, captions=[caption]))."""
@@ -255,9 +339,9 @@ def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
                                                                            GroundingDinoMultiscaleDeformableAttention,
                                                                            MultiScaleDeformableAttention)
 
-    from transformers.models.grounding_dino.modeling_grounding_dino import GroundingDinoFusionLayer
+    from transformers.models.grounding_dino.modeling_grounding_dino import GroundingDinoDecoderLayer, GroundingDinoFusionLayer
 
-    n_lin = n_msda = n_skip = n_layer = n_attn = n_fuse = 0
+    n_lin = n_msda = n_skip = n_layer = n_attn = n_fuse = n_dec = 0
     assert getattr(model.config, "activation_function", "relu") == "relu"
     for parent in list(model.modules()):
         for name, child in list(parent.named_children()):
@@ -265,6 +349,8 @@ def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
                 setattr(parent, name, TcDeformableLayer(child)); n_layer += 1
             elif isinstance(child, GroundingDinoFusionLayer) and child.attn.head_dim == 256:
                 setattr(parent, name, TcFusionLayer(child)); n_fuse += 1
+            elif isinstance(child, GroundingDinoDecoderLayer) and child.self_attn.attention_head_size == 32:
+                setattr(parent, name, TcDecoderLayer(child)); n_dec += 1
     for parent in list(model.modules()):
         for name, child in list(parent.named_children()):
             if isinstance(child, GroundingDinoMultiscaleDeformableAttention):
@@ -280,4 +366,4 @@ def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
                 setattr(parent, name, TcMSDA()); n_msda += 1
     if hasattr(model, "model") and hasattr(model.model, "text_backbone"):
         model.model.text_backbone = CachedTextBackbone(model.model.text_backbone)
-    return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda, "deformable_layers": n_layer, "deformable_attn": n_attn, "fusion_layers": n_fuse}
+    return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda, "deformable_layers": n_layer, "deformable_attn": n_attn, "fusion_layers": n_fuse, "decoder_layers": n_dec}
