@@ -111,7 +111,7 @@ def main():
         "timing": "host wall clock around whole steps incl. H2D of RGB-D + D2H of frontier lists; per-component CUDA events",
         "component_ms_per_step": {k: v / a.steps for k, v in acc.items()},
         "frontiers_per_env_step": n_front / (B * a.steps), "streams": len(streams), "hole_area_thresh": a.hole_thresh,
-        "gdino": "Swin-T on own kernels, neck/encoder/decoder HF PyTorch modules on the GPU" if gd is not None else "skipped",
+        "gdino": "Swin-T, linears, deformable / fusion / decoder layers on own kernels; neck, query selection and glue HF PyTorch" if gd is not None else "skipped",
         "config": {"workload": f"configs[2]: full step, batch={B} envs, 640x480 RGB-D, 1000^2 grid, 1xB200", "data": "synthetic"},
     }
     print(json.dumps(out))
