@@ -170,9 +170,10 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 // shorter critical path).  KH = 1: 64 query rows per CTA, every warp sees all keys (large batches: the K/V
 // staging is amortised over twice the queries, no merge).
 template <int HDP, int KH>
-__global__ void __launch_bounds__(32 * ATT_WARPS)
+__global__ void __launch_bounds__(32 * (KH == 4 ? 8 : ATT_WARPS))
 attention_kernel(AttnArgs a) {
-  constexpr int RG = ATT_WARPS / KH;     // row groups of 16 queries
+  constexpr int NW = KH == 4 ? 8 : ATT_WARPS;   // KH = 4: eight warps = 2 row groups x 4 key quarters (batch 1: shortest critical path)
+  constexpr int RG = NW / KH;            // row groups of 16 queries
   constexpr int ATT_QBLK = 16 * RG;
   constexpr int KS = HDP + 8;            // row stride (halves) of sK / sV
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -189,7 +190,7 @@ attention_kernel(AttnArgs a) {
   // ---- stage K and V with cp.async (16-byte LDGSTS, all copies in flight at once; src-size 0 zero-fills the
   // padding rows >= Nk and columns >= hd)
   constexpr int CH = HDP / 8;
-  for (int i = tid; i < NKP * CH; i += 32 * ATT_WARPS) {
+  for (int i = tid; i < NKP * CH; i += 32 * NW) {
     const int key = i / CH, c = (i - key * CH) * 8;
     const bool ok = key < a.Nk && c < a.hd;
     const __half* ksrc = ok ? kbase + (size_t)key * a.ldk + c : kbase;
@@ -223,9 +224,9 @@ attention_kernel(AttnArgs a) {
   for (int i = 0; i < HDP / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
-  // key range of this warp: first half gets the extra 16-key tile
-  const int halfk = KH == 2 ? ((NKP >> 4) + 1) / 2 * 16 : NKP;
-  const int k_begin = (warp / RG) ? halfk : 0, k_end = (warp / RG) ? NKP : halfk;
+  // key range of this warp: the 16-key tiles are dealt to the KH parts, the first parts take the remainder
+  const int part = warp / RG, tiles = NKP >> 4, tbase = tiles / KH, trem = tiles % KH;
+  const int k_begin = 16 * (part * tbase + min(part, trem)), k_end = k_begin + 16 * (tbase + (part < trem ? 1 : 0));
   for (int kb = k_begin; kb < k_end; kb += 64) {
     const int ntiles = min(8, (k_end - kb) >> 3);   // warp-uniform, even
     float s[8][4];
@@ -309,12 +310,12 @@ attention_kernel(AttnArgs a) {
     }
     return;
   }
-  // ---- merge the two key halves (warps 2,3 -> warps 0,1) through shared memory
+  // ---- merge the key parts (warps >= RG -> warps < RG) through shared memory, flash-style
   __syncthreads();                                   // everyone is done with sK / sV
-  float* mrg = reinterpret_cast<float*>(att_smem);   // [2 warps][HDP/8*4 + 4][32 lanes]
+  float* mrg = reinterpret_cast<float*>(att_smem);   // [(KH-1)*RG warps][HDP/8*4 + 4][32 lanes]
   constexpr int MW = HDP / 8 * 4 + 4;
-  if (warp >= 2) {
-    float* dst = mrg + (size_t)(warp - 2) * MW * 32 + lane;
+  if (warp >= RG) {
+    float* dst = mrg + (size_t)(warp - RG) * MW * 32 + lane;
 #pragma unroll
     for (int i = 0; i < HDP / 8; ++i) {
 #pragma unroll
@@ -323,27 +324,35 @@ attention_kernel(AttnArgs a) {
     dst[(MW - 4) * 32] = m_lo; dst[(MW - 3) * 32] = m_hi; dst[(MW - 2) * 32] = l_lo; dst[(MW - 1) * 32] = l_hi;
   }
   __syncthreads();
-  if (warp >= 2) return;
-  {
-    const float* src = mrg + (size_t)warp * MW * 32 + lane;
+  if (warp >= RG) return;
+#pragma unroll
+  for (int p = 1; p < KH; ++p) {
+    const float* src = mrg + (size_t)((p - 1) * RG + warp) * MW * 32 + lane;
     const float m2_lo = src[(MW - 4) * 32], m2_hi = src[(MW - 3) * 32], l2_lo = src[(MW - 2) * 32], l2_hi = src[(MW - 1) * 32];
     const float mm_lo = fmaxf(m_lo, m2_lo), mm_hi = fmaxf(m_hi, m2_hi);
     const float r_lo_ = mm_lo == -INFINITY ? 0.f : mm_lo, r_hi_ = mm_hi == -INFINITY ? 0.f : mm_hi;
     const float a1_lo = exp2f(m_lo - r_lo_), a2_lo = exp2f(m2_lo - r_lo_);
     const float a1_hi = exp2f(m_hi - r_hi_), a2_hi = exp2f(m2_hi - r_hi_);
-    const float inv_lo = 1.f / (l_lo * a1_lo + l2_lo * a2_lo), inv_hi = 1.f / (l_hi * a1_hi + l2_hi * a2_hi);
+    l_lo = l_lo * a1_lo + l2_lo * a2_lo; l_hi = l_hi * a1_hi + l2_hi * a2_hi;
+    m_lo = mm_lo; m_hi = mm_hi;
+#pragma unroll
+    for (int i = 0; i < HDP / 8; ++i) {
+      o[i][0] = o[i][0] * a1_lo + src[(i * 4 + 0) * 32] * a2_lo;
+      o[i][1] = o[i][1] * a1_lo + src[(i * 4 + 1) * 32] * a2_lo;
+      o[i][2] = o[i][2] * a1_hi + src[(i * 4 + 2) * 32] * a2_hi;
+      o[i][3] = o[i][3] * a1_hi + src[(i * 4 + 3) * 32] * a2_hi;
+    }
+  }
+  {
+    const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
     __half* olo = a.o + ((size_t)b * a.Nq + r_lo) * a.ldo + (size_t)h * a.hd;
     __half* ohi = a.o + ((size_t)b * a.Nq + r_hi) * a.ldo + (size_t)h * a.hd;
 #pragma unroll
     for (int i = 0; i < HDP / 8; ++i) {
       const int c = i * 8 + 2 * t;
-      const float v0 = (o[i][0] * a1_lo + src[(i * 4 + 0) * 32] * a2_lo) * inv_lo;
-      const float v1 = (o[i][1] * a1_lo + src[(i * 4 + 1) * 32] * a2_lo) * inv_lo;
-      const float v2 = (o[i][2] * a1_hi + src[(i * 4 + 2) * 32] * a2_hi) * inv_hi;
-      const float v3 = (o[i][3] * a1_hi + src[(i * 4 + 3) * 32] * a2_hi) * inv_hi;
       if (c < a.hd) {
-        if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = pack_half2(v0, v1);
-        if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = pack_half2(v2, v3);
+        if (r_lo < a.Nq) *reinterpret_cast<uint32_t*>(olo + c) = pack_half2(o[i][0] * inv_lo, o[i][1] * inv_lo);
+        if (r_hi < a.Nq) *reinterpret_cast<uint32_t*>(ohi + c) = pack_half2(o[i][2] * inv_hi, o[i][3] * inv_hi);
       }
     }
   }
@@ -433,8 +442,13 @@ extern "C" int vlfm_attention_f16(const void* d_q, const void* d_k, const void* 
   AttnArgs a{(const __half*)d_q, (const __half*)d_k, (const __half*)d_v, (__half*)d_o, ldq, ldk, ldv, ldo, Nq, Nk, hd, heads,
              scale * 1.4426950408889634f};
   cudaStream_t st = (cudaStream_t)stream;
-  // few (batch, head, block) work items -> 32-row blocks with split keys; many -> 64-row blocks
-  const bool big = (long)B * heads * ((Nq + 31) / 32) > 2 * 296;
+  // few (batch, head, block) work items -> 32-row blocks with split keys (4-way when they fit one wave of 8-warp CTAs,
+  // else 2-way); many -> 64-row blocks
+  const long items = (long)B * heads * ((Nq + 31) / 32);
+  const bool big = items > 2 * 296;
+  static int kh4 = -1;
+  if (kh4 < 0) { const char* e = getenv("VLFM_ATT_KH4"); kh4 = e ? atoi(e) : 1; }
+  const bool quad = !big && kh4 && items <= 296 && Nk >= 64;
   const int qblk = big ? 64 : 32;
   dim3 grid((Nq + qblk - 1) / qblk, heads, B);
   const size_t nkp = ((size_t)Nk + 15) & ~(size_t)15;
@@ -444,14 +458,17 @@ extern "C" int vlfm_attention_f16(const void* d_q, const void* d_k, const void* 
     if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (64 + 8) * 2), "attr(attention)");
     if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (96 + 8) * 2), "attr(attention)");
     if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (96 + 8) * 2), "attr(attention)");
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (64 + 8) * 2), "attr(attention)");
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(attention_kernel<96, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ATT_NKMAX * (96 + 8) * 2), "attr(attention)");
     if (rc) return rc;
     cfg = true;
   }
   const int hdp = hd <= 64 ? 64 : 96;
   size_t sm = 2 * nkp * (hdp + 8) * 2;
-  if (sm < 2 * 52 * 32 * 4) sm = 2 * 52 * 32 * 4;   // merge buffer of the split-key variant
+  if (sm < 6 * 52 * 32 * 4) sm = 6 * 52 * 32 * 4;   // merge buffer of the split-key variants
   cudaError_t e;
-  if (hdp == 64) e = big ? launch_pdl(attention_kernel<64, 1>, grid, dim3(32 * ATT_WARPS), sm, st, a) : launch_pdl(attention_kernel<64, 2>, grid, dim3(32 * ATT_WARPS), sm, st, a);
+  if (quad) e = hdp == 64 ? launch_pdl(attention_kernel<64, 4>, grid, dim3(256), sm, st, a) : launch_pdl(attention_kernel<96, 4>, grid, dim3(256), sm, st, a);
+  else if (hdp == 64) e = big ? launch_pdl(attention_kernel<64, 1>, grid, dim3(32 * ATT_WARPS), sm, st, a) : launch_pdl(attention_kernel<64, 2>, grid, dim3(32 * ATT_WARPS), sm, st, a);
   else e = big ? launch_pdl(attention_kernel<96, 1>, grid, dim3(32 * ATT_WARPS), sm, st, a) : launch_pdl(attention_kernel<96, 2>, grid, dim3(32 * ATT_WARPS), sm, st, a);
   { int rc = check_cuda(e, "attention_kernel"); if (rc) return rc; }
   count_launch();
