@@ -483,6 +483,7 @@ __device__ void line2_fixed(uint8_t* img, int W, int H, long long x1, long long 
     while (ecount >= 0) { put_px(img, W, H, x >> XYS, y); x += x_step; ++y; --ecount; }
   }
 }
+__device__ __forceinline__ long long pick4(const long long (&a)[4], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3])); }
 __global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __restrict__ cut, int W, int H, const ExState* st) {
   const int ri = blockIdx.x * blockDim.x + threadIdx.x;
   if (ri >= st->n_rays) return;
@@ -495,11 +496,13 @@ __global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __rest
     const long long dpx = (long long)rint(dy * rr), dpy = (long long)rint(dx * rr);
     long long vx[4] = {x0 + dpx, x0 - dpx, x1 - dpx, x1 + dpx}, vy[4] = {y0 + dpy, y0 - dpy, y1 - dpy, y1 + dpy};
     // FillConvexPoly (shift = 16): Line2 outline ...
+#pragma unroll
     for (int i = 0; i < 4; ++i) { const int j = (i + 3) & 3; line2_fixed(cut, W, H, vx[j], vy[j], vx[i], vy[i]); }
     // ... + two-edge scan
     const long long delta = XYONE >> 1;
     int imin = 0;
     long long ymin_f = vy[0], ymax_f = vy[0], xmin_f = vx[0], xmax_f = vx[0];
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (vy[i] < ymin_f) { ymin_f = vy[i]; imin = i; }
       ymax_f = vy[i] > ymax_f ? vy[i] : ymax_f; xmax_f = vx[i] > xmax_f ? vx[i] : xmax_f; xmin_f = vx[i] < xmin_f ? vx[i] : xmin_f;
@@ -512,13 +515,14 @@ __global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __rest
     int edges = 4;
     long long y = ymin;
     do {
+#pragma unroll
       for (int i = 0; i < 2; ++i) {
         if (y >= e[i].ye) {
           int idx0 = e[i].idx, di = e[i].di, idx = (idx0 + di) & 3;
           for (; edges-- > 0;) {
-            const long long ty = (vy[idx] + delta) >> XYS;
+            const long long ty = (pick4(vy, idx) + delta) >> XYS;
             if (ty > y) {
-              const long long xs = vx[idx0], xe = vx[idx];
+              const long long xs = pick4(vx, idx0), xe = pick4(vx, idx);
               e[i].ye = ty; e[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y)); e[i].x = xs; e[i].idx = idx;
               break;
             }
@@ -528,8 +532,8 @@ __global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __rest
       }
       if (edges < 0) break;
       {
-        const int l = e[0].x > e[1].x ? 1 : 0, rgt = 1 - l;
-        const long long xx1 = (e[l].x + delta) >> XYS, xx2 = (e[rgt].x + delta) >> XYS;
+        const bool sw = e[0].x > e[1].x;
+        const long long xx1 = ((sw ? e[1].x : e[0].x) + delta) >> XYS, xx2 = ((sw ? e[0].x : e[1].x) + delta) >> XYS;
         if (y >= 0 && y < H) for (long long x = xx1 < 0 ? 0 : xx1; x <= xx2 && x < W; ++x) cut[y * W + x] = 1;
       }
       e[0].x += e[0].dx; e[1].x += e[1].dx;

@@ -46,7 +46,10 @@ msda_kernel(const T* __restrict__ value, const float* __restrict__ loc, const fl
         const float x = __shfl_sync(0xffffffffu, mine, 2 * jj), y = __shfl_sync(0xffffffffu, mine, 2 * jj + 1);
         const float w = __shfl_sync(0xffffffffu, wmine, jj);
         const int l = (j0 + jj) / a.points;
-        const int Wl = a.W[l], Hl = a.H[l];
+        int Wl = a.W[0], Hl = a.H[0], lstart = a.start[0];
+#pragma unroll
+        for (int k = 1; k < MSDA_MAX_LEVELS; ++k)
+          if (l >= k) { Wl = a.W[k]; Hl = a.H[k]; lstart = a.start[k]; }
         // HF: grid = 2*loc - 1 ; grid_sample: ((grid + 1) / 2) * size - 0.5   (no FMA contraction)
         const float gx = __fsub_rn(__fmul_rn(2.f, x), 1.f), gy = __fsub_rn(__fmul_rn(2.f, y), 1.f);
         const float ix = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)Wl), 0.5f);
@@ -57,7 +60,7 @@ msda_kernel(const T* __restrict__ value, const float* __restrict__ loc, const fl
         const float w00 = (1.f - tx) * (1.f - ty), w01 = tx * (1.f - ty), w10 = (1.f - tx) * ty, w11 = tx * ty;
         const bool xin0 = x0 >= 0 && x0 < Wl, xin1 = x0 + 1 >= 0 && x0 + 1 < Wl, yin0 = y0 >= 0 && y0 < Hl, yin1 = y0 + 1 >= 0 && y0 + 1 < Hl;
         if (!cv || !((xin0 || xin1) && (yin0 || yin1))) continue;
-        const T* base = vb + (size_t)a.start[l] * vstride + c;
+        const T* base = vb + (size_t)lstart * vstride + c;
         float s = 0.f;
         if (yin0 && xin0) s += w00 * ld_val<T>(base + (size_t)(y0 * Wl + x0) * vstride);
         if (yin0 && xin1) s += w01 * ld_val<T>(base + (size_t)(y0 * Wl + x0 + 1) * vstride);
@@ -94,7 +97,10 @@ msda_fused_kernel(const __half* __restrict__ value, const float* __restrict__ of
     const float2 off = __ldg(reinterpret_cast<const float2*>(row + (size_t)h * LP * 2) + lane);
     logit = __ldg(row + logit_col + h * LP + lane);
     const int l = lane / points;
-    Wl = a.W[l]; Hl = a.H[l]; lbase = a.start[l];
+    Wl = a.W[0]; Hl = a.H[0]; lbase = a.start[0];
+#pragma unroll
+    for (int k = 1; k < MSDA_MAX_LEVELS; ++k)          // constant indices only: a dynamic a.W[l] would copy the struct to local memory
+      if (l >= k) { Wl = a.W[k]; Hl = a.H[k]; lbase = a.start[k]; }
     const float* rp = ref + ((size_t)bq * (LEVELS ? LEVELS : a.levels) + l) * REF_DIM;
     float lx, ly;
     if (REF_DIM == 2) {

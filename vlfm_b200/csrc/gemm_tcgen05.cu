@@ -153,7 +153,8 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
           *reinterpret_cast<uint4*>(o + j) = pk;
         }
       } else {
-        for (int j = 0; j < 32 && n0 + j < g.N; ++j) o[j] = __float2half_rn(v[j]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n0 + j < g.N) o[j] = __float2half_rn(v[j]);   // static indices: keeps v[] in registers
       }
     } else {
       float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
@@ -170,9 +171,12 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
           *reinterpret_cast<float4*>(o + j) = t;
         }
       } else {
-        for (int j = 0; j < 32 && n0 + j < g.N; ++j) {
-          if (split) atomicAdd(o + j, v[j]);
-          else o[j] = add ? o[j] + v[j] : v[j];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (n0 + j < g.N) {
+            if (split) atomicAdd(o + j, v[j]);
+            else o[j] = add ? o[j] + v[j] : v[j];
+          }
         }
       }
     }
