@@ -239,14 +239,22 @@ class ValueMap(BaseMap):
         assert 0 <= row < self.size and 0 <= col < self.size, "Pixel location is outside the image."
         h, w = depth.shape
         pin_d, pin_s, ev = self._staging(h, w)
-        pin_d[0].numpy()[...] = depth  # converts to float32 if needed
+        direct = None
+        if isinstance(depth, np.ndarray) and depth.dtype == np.float32 and depth.flags.c_contiguous:
+            t = torch.from_numpy(depth)
+            if t.is_pinned():
+                direct = t          # page-locked caller buffer: DMA straight from it (waited for below, the caller may reuse it)
+        if direct is None:
+            pin_d[0].numpy()[...] = depth  # converts to float32 if needed
         s = pin_s.numpy()
         s[:16] = np.asarray(tf_camera_to_episodic, dtype=np.float64).reshape(16)
         s[16:] = np.asarray(values, dtype=np.float64)
         with torch.cuda.device(self.device):
-            self._dev_depth.copy_(pin_d, non_blocking=True)
+            self._dev_depth.copy_(pin_d if direct is None else direct[None], non_blocking=True)
             self._dev_small.copy_(pin_s, non_blocking=True)
             ev.record()
+            if direct is not None:
+                ev.synchronize()
             if self._obstacle_map is not None:  # value_map.py:365-375
                 exp = self._obstacle_map.explored_device()
                 self._eng.mask_unexplored(exp)

@@ -117,8 +117,12 @@ class BLIP2ITM:
         if self._pin is None or self._pin.shape[1:] != image.shape:
             self._pin = torch.empty((1,) + image.shape, dtype=torch.uint8).pin_memory()
             self._dev_img = torch.empty((1,) + image.shape, dtype=torch.uint8, device=self.device)
-        self._pin[0].numpy()[...] = image
-        self._dev_img.copy_(self._pin, non_blocking=True)
+        src = torch.from_numpy(image)
+        if src.is_pinned():          # caller's frame already lives in page-locked memory: DMA straight from it (the call syncs below)
+            self._dev_img.copy_(src[None], non_blocking=True)
+        else:
+            self._pin[0].numpy()[...] = image
+            self._dev_img.copy_(self._pin, non_blocking=True)
         return float(self.engine.forward(self._dev_img)[0].item())  # .item(): D2H sync, as in the reference
 
 
