@@ -109,7 +109,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // fused bias / GELU / residual, vectorised global stores.  `q` = TMEM lane quarter of this warp.
 template <int BN>
 __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row, int n_blk, const GemmArgs& g, bool split,
-                                              int c_first) {
+                                              int c_first, const float* sbias = nullptr) {
   // the two warps sharing a lane quarter interleave the 32-column chunks
 #pragma unroll 1
   for (int c = c_first; c < BN / 32; c += 2) {
@@ -119,7 +119,15 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
     if (row >= g.M || n0 >= g.N) continue;
     float v[32];
     const bool fullw = (n0 + 32 <= g.N);
-    if (g.bias && blockIdx.z == 0 && fullw) {
+    if (sbias) {   // bias tile staged in shared memory before the accumulator wait (zero-filled past N / without bias)
+      const bool addb = blockIdx.z == 0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = addb ? *reinterpret_cast<const float4*>(sbias + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+      }
+    } else if (g.bias && blockIdx.z == 0 && fullw) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + j));
@@ -198,6 +206,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accbar = smem_u32(bars + 2 * STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // [BN]
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,11 +285,15 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
     const int row = m_blk * BM + q * 32 + lane;
+    // bias is a weight (no dependency on the predecessor): stage this tile's slice while the main loop runs
+    const int et = threadIdx.x - 64;
+    if (et < BN) { const int n = n_blk * BN + et; sbias[et] = (g.bias && n < g.N) ? __ldg(g.bias + n) : 0.f; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
     pdl_wait();          // residual stream / output buffers of the predecessor are visible
     mbar_wait(accbar, 0);
     if (dbg && threadIdx.x == 64) g.dbg[5] = clock64();
     tc_fence_after();
-    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split, (warp - 2) >> 2);
+    epilogue_slab<BN>(tmem_base, q, row, n_blk, g, split, (warp - 2) >> 2, sbias);
   }
   tc_fence_before();
   __syncthreads();
@@ -590,7 +603,7 @@ static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const Gemm
   CUtensorMap tb;
   int rc = make_map(&tb, W, g.N, g.K, ldw, BN);
   if (rc) return rc;
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024 + BN * 4 + 32;
   static bool configured = false;
   if (!configured) {
     rc = check_cuda(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gemm)");
