@@ -248,3 +248,38 @@ def test_decoder_layer_vs_hf_module():
     err = (got - want).abs()
     print("decoder layer max", float(err.max()), "mean", float(err.mean()))
     assert float(err.max()) <= 5e-2 and float(err.mean()) <= 5e-3
+
+
+def test_batch1_cuda_graph_replay_matches_eager(pair):
+    """The per-step policy call (batch 1) replays a CUDA graph of the whole detector from the second call on; its outputs must
+    be those of the eager module graph.  With random weights the 900-of-6380 query selection is a top-k over near-tied scores,
+    so even two EAGER runs differ (fp32 atomics order in the split-K GEMMs flips selections): the graph-vs-eager difference is
+    held to the same level as eager-vs-eager, measured here on the spot (sorted confidences, boxes as sets)."""
+    import time
+
+    _, g = pair
+    ids = g.tokenizer.encode("chair . couch . tv .")
+    rng = np.random.default_rng(11)
+    img1, img2 = make_rgb(rng, 480, 640), make_rgb(rng, 480, 640)
+
+    def metrics(la, ba, lb, bb):
+        ca, cb = la.max(dim=1)[0].sort()[0], lb.max(dim=1)[0].sort()[0]
+        dist = (bb[:, None, :] - ba[None, :, :]).abs().sum(-1).min(dim=1)[0]
+        return float((ca - cb).abs().mean()), float(dist.mean())
+
+    g._graph_ok = False                                               # eager baseline: same image twice
+    e0 = [t.clone() for t in g.raw_outputs(img1, ids)]
+    e1 = [t.clone() for t in g.raw_outputs(img1, ids)]
+    g._graph_ok = True
+    g.raw_outputs(img2, ids)                                          # capture + first replay (this key already ran eagerly)
+    assert g.graph_error is None, g.graph_error
+    assert g._static[(1, 480, 640, tuple(ids))]["graph"] is not None
+    r = [t.clone() for t in g.raw_outputs(img1, ids)]                 # replay
+    ee, ge = metrics(e0[0], e0[1], e1[0], e1[1]), metrics(e0[0], e0[1], r[0], r[1])
+    print("eager vs eager (confidence, box-set):", ee, " graph vs eager:", ge)
+    assert ge[0] <= max(1e-4, 3 * ee[0]) and ge[1] <= max(1e-4, 3 * ee[1])
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10):
+        g.raw_outputs(img1, ids)
+    torch.cuda.synchronize()
+    print(f"batch-1 GroundingDINO forward (graph replay incl. H2D): {(time.perf_counter() - t0) * 100:.2f} ms")

@@ -333,6 +333,43 @@ class CachedTextBackbone(torch.nn.Module):
         return self.cache[self.key]
 
 
+class _TorchProxy:
+    """Stands in for the ``torch`` module inside transformers' GroundingDINO modelling file so that the handful of
+    host-list -> device tensor constructions in its forward (spatial shapes, special-token ids) are served from a cache
+    instead of issuing a synchronous H2D copy every call -- which is also what makes the forward CUDA-graph capturable."""
+
+    def __init__(self, real):
+        object.__setattr__(self, "_real", real)
+        object.__setattr__(self, "_cache", {})
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def _cached(self, fn, data, args, kwargs):
+        dev = kwargs.get("device", None)
+        if isinstance(data, (list, tuple, int, float)) and dev is not None and self._real.device(dev).type == "cuda":
+            key = (fn.__name__, repr(data), str(kwargs.get("dtype", None)), str(dev))
+            hit = self._cache.get(key)
+            if hit is None:
+                hit = fn(data, *args, **kwargs)
+                self._cache[key] = hit
+            return hit
+        return fn(data, *args, **kwargs)
+
+    def as_tensor(self, data, *args, **kwargs):
+        return self._cached(self._real.as_tensor, data, args, kwargs)
+
+    def tensor(self, data, *args, **kwargs):
+        return self._cached(self._real.tensor, data, args, kwargs)
+
+
+def install_torch_proxy() -> None:
+    import transformers.models.grounding_dino.modeling_grounding_dino as mgd
+
+    if not isinstance(mgd.torch, _TorchProxy):
+        mgd.torch = _TorchProxy(mgd.torch)
+
+
 def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
     """Swap the primitives in place (model already on the GPU).  Returns counts for the log / tests."""
     from transformers.models.grounding_dino.modeling_grounding_dino import (GroundingDinoDeformableLayer,
@@ -366,4 +403,5 @@ def accelerate(model: torch.nn.Module, min_out: int = 16) -> dict:
                 setattr(parent, name, TcMSDA()); n_msda += 1
     if hasattr(model, "model") and hasattr(model.model, "text_backbone"):
         model.model.text_backbone = CachedTextBackbone(model.model.text_backbone)
+        install_torch_proxy()
     return {"linear": n_lin, "linear_kept": n_skip, "msda": n_msda, "deformable_layers": n_layer, "deformable_attn": n_attn, "fusion_layers": n_fuse, "decoder_layers": n_dec}

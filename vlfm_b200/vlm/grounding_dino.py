@@ -96,20 +96,57 @@ class GroundingDINO:
         self.tokenizer = tokenizer or SimpleCaptionTokenizer(cfg.text_config.vocab_size)
         self._pin: Optional[torch.Tensor] = None
         self._dev: Optional[torch.Tensor] = None
+        self._static: Dict[Any, Dict[str, Any]] = {}
+        self._graph_ok = os.environ.get("VLFM_GDINO_GRAPH", "1") != "0"
+        self._graph_max_batch = int(os.environ.get("VLFM_GDINO_GRAPH_MAX_BATCH", "4"))
+        self.graph_error: Optional[str] = None
+
+    def _forward_static(self, st):
+        """One forward on the static buffers of ``st`` (eager or under CUDA-graph capture)."""
+        self._features.maps = self.backbone.forward(st["img"])
+        out = self.model(pixel_values=st["dummy"], input_ids=st["ids"], token_type_ids=st["tt"], attention_mask=st["am"], pixel_mask=st["pm"])
+        st["logits"], st["boxes"] = out.logits.sigmoid(), out.pred_boxes
 
     @torch.inference_mode()
     def raw_outputs_device(self, images: torch.Tensor, input_ids: List[int]):
-        """images [B,H,W,3] uint8 on the device -> (sigmoid logits [B,900,256], boxes [B,900,4] cxcywh)."""
-        self._features.maps = self.backbone.forward(images)
+        """images [B,H,W,3] uint8 on the device -> (sigmoid logits [B,900,256], boxes [B,900,4] cxcywh).
+
+        Small batches (the per-step policy call is batch 1) replay a CUDA graph of the whole detector per
+        (batch, image size, caption): the module graph is ~700 launches and launch-bound otherwise."""
         b, h, w = images.shape[:3]
+        key = (int(b), int(h), int(w), tuple(int(i) for i in input_ids))
         tb = self.model.model.text_backbone
         if hasattr(tb, "key"):
-            tb.key = (tuple(int(i) for i in input_ids), int(b))
-        ids = torch.tensor([input_ids], dtype=torch.long, device=self.device).expand(b, -1).contiguous()
-        dummy = torch.zeros(b, 3, h, w, device=self.device)  # only its shape is used (pixel mask); features come from our engine
-        out = self.model(pixel_values=dummy, input_ids=ids, token_type_ids=torch.zeros_like(ids), attention_mask=torch.ones_like(ids),
-                         pixel_mask=torch.ones(b, h, w, dtype=torch.long, device=self.device))
-        return out.logits.sigmoid(), out.pred_boxes
+            tb.key = (key[3], key[0])
+        st = self._static.get(key)
+        if st is None:
+            ids = torch.tensor([list(key[3])], dtype=torch.long, device=self.device).expand(b, -1).contiguous()
+            st = {"img": torch.empty_like(images), "ids": ids, "tt": torch.zeros_like(ids), "am": torch.ones_like(ids),
+                  "dummy": torch.zeros(b, 3, h, w, device=self.device),   # only its shape is used (pixel mask); features come from our engine
+                  "pm": torch.ones(b, h, w, dtype=torch.long, device=self.device), "calls": 0, "graph": None}
+            if len(self._static) >= 4:
+                self._static.pop(next(iter(self._static)))
+            self._static[key] = st
+        st["img"].copy_(images, non_blocking=True)
+        st["calls"] += 1
+        use_graph = self._graph_ok and b <= self._graph_max_batch
+        if use_graph and st["graph"] is None and st["calls"] >= 2:       # call 1 warmed every cache up eagerly
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._forward_static(st)
+                st["graph"] = g
+            except Exception as e:  # a sync point inside the module graph: stay eager (loudly, once)
+                self._graph_ok = False
+                self.graph_error = repr(e)
+                print(f"[vlfm_b200] GroundingDINO CUDA-graph capture disabled: {e}", flush=True)
+                torch.cuda.synchronize()
+        if st["graph"] is not None:
+            st["graph"].replay()
+        else:
+            self._forward_static(st)
+        return st["logits"], st["boxes"]
 
     def raw_outputs(self, image: np.ndarray, input_ids: List[int]):
         """-> (sigmoid logits [900,256], boxes [900,4] cxcywh) on the device."""
