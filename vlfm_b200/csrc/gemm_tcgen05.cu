@@ -97,7 +97,12 @@ struct GemmArgs {
   // optional fused LayerNorm of the updated residual rows (grid-wide barrier, then warp-per-row LN)
   const float* ln_gamma; const float* ln_beta; __half* ln_out16; float* ln_out32; unsigned* ln_sync;
   int ln_ld16, ln_ld32; float ln_eps;
+  // "tail rows": when M = 128*q + r with 1 <= r <= GEMM_TAIL_MAX (ViT: 257 tokens), only q row tiles are launched and the CTAs
+  // of the last one also compute the r extra rows on CUDA cores from the W tiles already staged for the tensor core
+  const __half* a_tail; int lda, tail_rows, tail_row0;
 };
+constexpr int GEMM_TAIL_MAX = 2;
+constexpr int GEMM_TAIL_KMAX = 6144;   // K elements of one CTA's slice that fit the tail-row staging buffer
 
 __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -219,10 +224,12 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int num_k = min((g.K + BK - 1) / BK - kb_begin, g.kb_per_split);   // K-blocks of this split
   const bool split = gridDim.z > 1;
 
+  const bool tail_cta = g.tail_rows > 0 && m_blk == (int)gridDim.y - 1;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    // a stage is released by the MMA commit and, in tail CTAs, by the eight epilogue warps that also read its W tile
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, tail_cta ? 9 : 1); }
     mbar_init(accbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -290,6 +297,79 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     if (et < BN) { const int n = n_blk * BN + et; sbias[et] = (g.bias && n < g.N) ? __ldg(g.bias + n) : 0.f; }
     asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
     pdl_wait();          // residual stream / output buffers of the predecessor are visible
+    if (tail_cta) {
+      // ---- tail rows on CUDA cores: thread = (feature f of this tile, K half hk); W from the 128B-swizzled stage
+      const int f = et >> 1, hk = et & 1;
+      float tacc[GEMM_TAIL_MAX];
+#pragma unroll
+      for (int r = 0; r < GEMM_TAIL_MAX; ++r) tacc[r] = 0.f;
+      // stage this CTA's K slice of the tail rows once (global latency must not sit between "stage full" and "stage released")
+      __half* sx = reinterpret_cast<__half*>(sbias + BN);
+      const int kslice = num_k * BK, kbase = kb_begin * BK;
+      for (int i = et; i < g.tail_rows * (kslice >> 3); i += 256) {
+        const int r = i / (kslice >> 3), c8 = (i - r * (kslice >> 3)) << 3;
+        uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+        if (kbase + c8 < g.K) xv = __ldg(reinterpret_cast<const uint4*>(g.a_tail + (size_t)r * g.lda + kbase + c8));
+        *reinterpret_cast<uint4*>(sx + (size_t)r * kslice + c8) = xv;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
+        if (f < BN) {
+          const uint8_t* wrow = sB + (size_t)s * B_BYTES + (size_t)f * 128;
+          const int k0 = kb * BK + hk * 32;                    // offset inside the staged slice
+          uint4 wv[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const uint4*>(wrow + (((hk * 4 + c) ^ (f & 7)) << 4));
+#pragma unroll
+          for (int r = 0; r < GEMM_TAIL_MAX; ++r) {
+            if (r < g.tail_rows) {
+              const __half* xr = sx + (size_t)r * kslice + k0;
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                {                                              // chunks past K were staged as zeros (and W is zero-filled by TMA)
+                  const uint4 xv = *reinterpret_cast<const uint4*>(xr + c * 8);
+                  const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+                  const __half2* wh = reinterpret_cast<const __half2*>(&wv[c]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 xf = __half22float2(xh[e]), wf = __half22float2(wh[e]);
+                    acc = fmaf(xf.x, wf.x, acc); acc = fmaf(xf.y, wf.y, acc);
+                  }
+                }
+              }
+              tacc[r] += acc;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory");
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+#pragma unroll
+      for (int r = 0; r < GEMM_TAIL_MAX; ++r) tacc[r] += __shfl_xor_sync(0xffffffffu, tacc[r], 1);
+      const int n = n_blk * BN + f;
+      if (hk == 0 && f < BN && n < g.N) {
+#pragma unroll
+        for (int r = 0; r < GEMM_TAIL_MAX; ++r) {
+          if (r < g.tail_rows) {
+            float v = tacc[r] + (blockIdx.z == 0 ? sbias[f] : 0.f);
+            const size_t o = (size_t)(g.tail_row0 + r) * g.ldo + n;
+            if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16 || g.epi == VLFM_EPI_BIAS_RELU_F16) {
+              if (g.epi == VLFM_EPI_BIAS_GELU_F16) v = gelu_erf(v);
+              else if (g.epi == VLFM_EPI_BIAS_RELU_F16) v = fmaxf(v, 0.f);
+              reinterpret_cast<__half*>(g.out)[o] = __float2half_rn(v);
+            } else {
+              float* po = reinterpret_cast<float*>(g.out) + o;
+              if (split) atomicAdd(po, v);
+              else *po = (g.epi == VLFM_EPI_BIAS_RESID_F32) ? *po + v : v;
+            }
+          }
+        }
+      }
+    }
     mbar_wait(accbar, 0);
     if (dbg && threadIdx.x == 64) g.dbg[5] = clock64();
     tc_fence_after();
@@ -603,7 +683,8 @@ static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const Gemm
   CUtensorMap tb;
   int rc = make_map(&tb, W, g.N, g.K, ldw, BN);
   if (rc) return rc;
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024 + BN * 4 + 32;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024 + BN * 4 + 32 +
+                          (size_t)GEMM_TAIL_MAX * GEMM_TAIL_KMAX * 2;
   static bool configured = false;
   if (!configured) {
     rc = check_cuda(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gemm)");
@@ -611,7 +692,7 @@ static int launch_gemm(const CUtensorMap& ta, const void* W, int ldw, const Gemm
     configured = true;
   }
   const int num_k = (g.K + BK - 1) / BK;
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (num_k + g.kb_per_split - 1) / g.kb_per_split);
+  dim3 grid((g.N + BN - 1) / BN, g.tail_rows > 0 ? g.M / BM : (g.M + BM - 1) / BM, (num_k + g.kb_per_split - 1) / g.kb_per_split);
   rc = check_cuda(launch_pdl(gemm_f16_tcgen05_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), smem, st, ta, tb, g), "gemm_f16_tcgen05_kernel");
   if (rc) return rc;
   count_launch();
@@ -680,7 +761,7 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
     set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
   if (epilogue < 0 || epilogue > 4) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f};
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr, 0, 0, 0};
   return gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, nullptr);
 }
 
@@ -710,24 +791,41 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
       return launch_gemm_2cta<256, 6>(ta, d_W, ldw, g, st);
     }
   }
+  // M = 128*q + r with a tiny remainder (ViT: 257 tokens = 2*128 + 1): launch q row tiles only; the last tile's CTAs compute
+  // the r tail rows on CUDA cores from the W tiles they stage anyway.  A third of the CTAs (and of the W traffic) disappears,
+  // which buys narrower tiles / deeper split-K inside one wave.
+  static int tail_on = -1;
+  if (tail_on < 0) { const char* e = getenv("VLFM_GEMM_TAIL"); tail_on = (e && e[0] == '0') ? 0 : 1; }
+  const int rem = M % BM;
+  const bool tail = tail_on && M > BM && rem >= 1 && rem <= GEMM_TAIL_MAX && !g.ln_sync && num_k * BK <= GEMM_TAIL_KMAX;
   int best_bn = 128, best_s = 1, force_shallow = 0;
   double best_t = 1e30;
+  bool best_tail = false;
+  // Cost model fitted to in-graph measurements on B200 (scripts/gemm_m256_probe.py, profiles/r01_gemm_tail_probe.txt):
+  //   t = waves * (c0 + K-blocks per CTA * per_kb),  per_kb = max(0.33 us pipeline floor, CTAs * KB per K-block / 12.6 TB/s chip L2->SM),
+  //   c0 = prologue + epilogue: 2.6 / 3.0 / 3.8 us for 32 / 64 / 128-wide tiles, + split-K atomics, + the tail-row work.
   const int bns[3] = {128, 64, 32};
-  for (int bi = 0; bi < 3; ++bi) {
-    const int bn = bns[bi], nt = (N + bn - 1) / bn;
-    int smax = (epilogue == VLFM_EPI_BIAS_RESID_F32) ? num_k / 4 : 1;
-    if (smax < 1) smax = 1;
-    if (smax > 8) smax = 8;
-    for (int sp = 1; sp <= smax; ++sp) {
-      const double ctas = (double)mt * nt * sp;
-      const int kb = (num_k + sp - 1) / sp;
-      const double waves = (double)(long)((ctas + 147) / 148);
-      const double active = ctas < 148 ? ctas : 148;
-      double bw = 8000.0 / active;             // KB/us per CTA when the chip-wide rate is shared
-      if (bw > 90.0) bw = 90.0;                // one SM's ingest limit
-      const double kbytes = (double)kb * (128 + bn) * 128 / 1024.0;
-      const double t = waves * (3.5 + kbytes / bw) + (sp > 1 ? 0.7 : 0.0);
-      if (t < best_t) { best_t = t; best_bn = bn; best_s = sp; }
+  for (int tm = 0; tm < (tail ? 2 : 1); ++tm) {
+    const bool use_tail = tail && tm == 0;
+    const int mte = use_tail ? M / BM : mt;
+    for (int bi = 0; bi < 3; ++bi) {
+      const int bn = bns[bi], nt = (N + bn - 1) / bn;
+      int smax = (epilogue == VLFM_EPI_BIAS_RESID_F32) ? num_k / 4 : 1;
+      if (smax < 1) smax = 1;
+      if (smax > 8) smax = 8;
+      for (int sp = 1; sp <= smax; ++sp) {
+        const double ctas = (double)mte * nt * sp;
+        const int kb = (num_k + sp - 1) / sp;
+        const double waves = (double)(long)((ctas + 147) / 148);
+        const double active = ctas < 148 ? ctas : 148;
+        const double kb_kbytes = (double)(128 + bn) * 128 / 1024.0;
+        double per_kb = active * kb_kbytes / 12600.0;
+        if (per_kb < 0.33) per_kb = 0.33;
+        double c0 = bn == 128 ? 3.8 + 0.22 * sp : (bn == 64 ? 3.0 : 2.6) + (sp > 1 ? 0.1 * sp : 0.0);
+        if (use_tail) c0 += bn == 128 ? 0.9 : 0.3;
+        const double t = waves * (c0 + kb * per_kb);
+        if (t < best_t) { best_t = t; best_bn = bn; best_s = sp; best_tail = use_tail; }
+      }
     }
   }
   if (const char* f = getenv("VLFM_GEMM_FORCE")) {   // development sweep: "bn:splits"
@@ -743,7 +841,8 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
   // programmatic dependent launch, the next GEMM's CTAs are already resident when this one drains.
   static int shallow = -1;
   if (shallow < 0) { const char* e = getenv("VLFM_GEMM_SHALLOW"); shallow = (e && e[0] == '1') ? 1 : 0; }  // measured slower on B200 (3 stages cannot cover the latency): off
-  const bool one_wave = (long)mt * ((N + best_bn - 1) / best_bn) * best_s <= 148;
+  const bool one_wave = (long)(best_tail ? M / BM : mt) * ((N + best_bn - 1) / best_bn) * best_s <= 148;
+  if (best_tail) { g.a_tail = (const __half*)d_A + (size_t)(M / BM) * BM * lda; g.lda = lda; g.tail_rows = rem; g.tail_row0 = (M / BM) * BM; }
   if (g.ln_sync) {                               // grid-barrier fusion needs every CTA resident at once
     if (one_wave) { if (fused) *fused = true; }
     else { g.ln_sync = nullptr; if (fused) *fused = false; }
