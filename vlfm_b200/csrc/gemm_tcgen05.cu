@@ -200,7 +200,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, STAGES <= 4 ? 2 : 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // allocation granularity: powers of two
   // instruction descriptor: D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -804,12 +804,17 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
   // Cost model fitted to in-graph measurements on B200 (scripts/gemm_m256_probe.py, profiles/r01_gemm_tail_probe.txt):
   //   t = waves * (c0 + K-blocks per CTA * per_kb),  per_kb = max(0.33 us pipeline floor, CTAs * KB per K-block / 12.6 TB/s chip L2->SM),
   //   c0 = prologue + epilogue: 2.6 / 3.0 / 3.8 us for 32 / 64 / 128-wide tiles, + split-K atomics, + the tail-row work.
-  const int bns[3] = {128, 64, 32};
+  const int bns[4] = {128, 96, 64, 32};
   for (int tm = 0; tm < (tail ? 2 : 1); ++tm) {
     const bool use_tail = tail && tm == 0;
     const int mte = use_tail ? M / BM : mt;
-    for (int bi = 0; bi < 3; ++bi) {
+    for (int bi = 0; bi < 4; ++bi) {
       const int bn = bns[bi], nt = (N + bn - 1) / bn;
+      static int bn96 = -1;
+      if (bn96 < 0) { const char* e = getenv("VLFM_GEMM_BN96"); bn96 = (e && e[0] == '1') ? 1 : 0; }
+      // 96-wide tiles for the two-row-tile (tail) plans: FC1 at 257 tokens is 0.6 us faster in isolation (L2-resident weights) but
+      // 1 % slower inside the forward (weights from HBM): opt-in only
+      if (bn == 96 && (!use_tail || !bn96)) continue;
       int smax = (epilogue == VLFM_EPI_BIAS_RESID_F32) ? num_k / 4 : 1;
       if (smax < 1) smax = 1;
       if (smax > 8) smax = 8;
@@ -821,8 +826,8 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
         const double kb_kbytes = (double)(128 + bn) * 128 / 1024.0;
         double per_kb = active * kb_kbytes / 12600.0;
         if (per_kb < 0.33) per_kb = 0.33;
-        double c0 = bn == 128 ? 3.8 + 0.22 * sp : (bn == 64 ? 3.0 : 2.6) + (sp > 1 ? 0.1 * sp : 0.0);
-        if (use_tail) c0 += bn == 128 ? 0.9 : 0.3;
+        double c0 = bn == 128 ? 3.8 + 0.22 * sp : (bn == 96 ? 3.4 + 0.16 * sp : (bn == 64 ? 3.0 : 2.6) + (sp > 1 ? 0.1 * sp : 0.0));
+        if (use_tail) c0 += bn == 128 ? 0.9 : (bn == 96 ? 0.6 : 0.3);
         const double t = waves * (c0 + kb * per_kb);
         if (t < best_t) { best_t = t; best_bn = bn; best_s = sp; best_tail = use_tail; }
       }
@@ -830,7 +835,8 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
   }
   if (const char* f = getenv("VLFM_GEMM_FORCE")) {   // development sweep: "bn:splits"
     int fb = 0, fs = 0, fsh = 0;
-    if (sscanf(f, "%d:%d:%d", &fb, &fs, &fsh) >= 2 && (fb == 128 || fb == 64 || fb == 32) && fs >= 1) {
+    if (sscanf(f, "%d:%d:%d", &fb, &fs, &fsh) >= 2 && (fb == 128 || fb == 64 || fb == 32 || (fb == 96 && tail)) && fs >= 1) {
+      if (fb == 96) best_tail = true;
       best_bn = fb;
       best_s = (epilogue == VLFM_EPI_BIAS_RESID_F32) ? (fs > num_k ? num_k : fs) : 1;
       force_shallow = fsh;
@@ -847,12 +853,13 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
     if (one_wave) { if (fused) *fused = true; }
     else { g.ln_sync = nullptr; if (fused) *fused = false; }
   }
-  if ((shallow && one_wave) || force_shallow) {
+  if (((shallow && one_wave) || force_shallow) && best_bn != 96) {
     if (best_bn == 128) return launch_gemm<128, 3>(ta, d_W, ldw, g, st);
     if (best_bn == 64) return launch_gemm<64, 4>(ta, d_W, ldw, g, st);
     return launch_gemm<32, 4>(ta, d_W, ldw, g, st);
   }
   if (best_bn == 128) return launch_gemm<128, 6>(ta, d_W, ldw, g, st);
+  if (best_bn == 96) return launch_gemm<96, 7>(ta, d_W, ldw, g, st);
   if (best_bn == 64) return launch_gemm<64, 8>(ta, d_W, ldw, g, st);
   return launch_gemm<32, 8>(ta, d_W, ldw, g, st);
 }
