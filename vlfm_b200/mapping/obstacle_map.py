@@ -104,8 +104,21 @@ class ObstacleMap(BaseMap):
             if self._pin is None or self._pin.shape != (1, h, w):
                 self._pin = torch.empty((1, h, w), dtype=torch.float32).pin_memory()
                 self._dev_depth = torch.empty((1, h, w), dtype=torch.float32, device=self.device)
-            self._pin[0].numpy()[...] = depth
-            self._dev_depth.copy_(self._pin, non_blocking=True)
+            direct = None
+            if isinstance(depth, np.ndarray) and depth.dtype == np.float32 and depth.flags.c_contiguous:
+                t = torch.from_numpy(depth)
+                # page-locked caller frame and an idle stream: DMA straight from it and wait (the caller may reuse the frame);
+                # with work queued ahead the wait would stall the host, so the frame is staged instead
+                if t.is_pinned() and torch.cuda.current_stream(self.device).query():
+                    direct = t
+            if direct is None:
+                self._pin[0].numpy()[...] = depth
+            self._dev_depth.copy_(self._pin if direct is None else direct[None], non_blocking=True)
+            self._dev_tf.copy_(self._pin_tf, non_blocking=True)
+            self._ev.record()
+            if direct is not None:
+                self._ev.synchronize()
+            return
         self._dev_tf.copy_(self._pin_tf, non_blocking=True)
         self._ev.record()
 

@@ -242,8 +242,10 @@ class ValueMap(BaseMap):
         direct = None
         if isinstance(depth, np.ndarray) and depth.dtype == np.float32 and depth.flags.c_contiguous:
             t = torch.from_numpy(depth)
-            if t.is_pinned():
-                direct = t          # page-locked caller buffer: DMA straight from it (waited for below, the caller may reuse it)
+            # page-locked caller buffer and an idle stream: DMA straight from it and wait (the caller may reuse the buffer);
+            # with work queued ahead the wait would stall the host, so the frame is staged instead
+            if t.is_pinned() and torch.cuda.current_stream(self.device).query():
+                direct = t
         if direct is None:
             pin_d[0].numpy()[...] = depth  # converts to float32 if needed
         s = pin_s.numpy()
