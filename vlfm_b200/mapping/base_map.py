@@ -1,4 +1,12 @@
-"""Grid conventions shared by the maps (reference: vlfm/mapping/base_map.py:10-60)."""
+"""Grid conventions shared by the maps (reference: vlfm/mapping/base_map.py:10-60).
+
+The episodic frame is metres with +x forward / +y left; a map is a G x G grid whose cell (row, col) = (G//2, G//2) is the
+episode origin, rows growing with +x and columns growing with -y.  The reference exposes the conversion in cv2 (col, row)
+order; the formulae below are its arithmetic written out per axis:
+
+    col = G - (rint(y * ppm) + G//2)        row = rint(x * ppm) + G//2
+    x   = (row - G//2) / ppm                y   = ((G - col) - G//2) / ppm
+"""
 from __future__ import annotations
 
 from typing import Any, List
@@ -7,33 +15,40 @@ import numpy as np
 
 
 class BaseMap:
-    """Host-side mirror of the reference ``BaseMap``: size, pixels_per_meter, origin and
-    the metre <-> cell conversions.  The grids themselves live on the GPU in subclasses."""
+    """Host-side bookkeeping of a map: geometry (size, pixels_per_meter, origin), the metre <-> cell conversions and the
+    camera trajectory used by ``visualize``.  The grids themselves live on the GPU in the subclasses."""
 
     _camera_positions: List[np.ndarray] = []
     _last_camera_yaw: float = 0.0
 
     def __init__(self, size: int = 1000, pixels_per_meter: int = 20, *args: Any, **kwargs: Any):
+        self.size = int(size)
         self.pixels_per_meter = pixels_per_meter
-        self.size = size
-        self._episode_pixel_origin = np.array([size // 2, size // 2])
+        half = self.size // 2
+        self._episode_pixel_origin = np.array([half, half])
         self._camera_positions = []
 
-    def reset(self) -> None:  # base_map.py:26-29
+    # ---- episode bookkeeping (base_map.py:26-33)
+    def reset(self) -> None:
         self._camera_positions = []
 
-    def update_agent_traj(self, robot_xy: np.ndarray, robot_heading: float) -> None:  # :31-33
-        self._camera_positions.append(robot_xy)
+    def update_agent_traj(self, robot_xy: np.ndarray, robot_heading: float) -> None:
         self._last_camera_yaw = robot_heading
+        self._camera_positions.append(robot_xy)
 
+    # ---- conversions (base_map.py:35-60); same floating-point operations per element as the reference
     def _xy_to_px(self, points: np.ndarray) -> np.ndarray:
-        """(x, y) metres -> (col, row) cells; np.rint, y flipped (base_map.py:35-46)."""
-        px = np.rint(points[:, ::-1] * self.pixels_per_meter) + self._episode_pixel_origin
-        px[:, 0] = self.size - px[:, 0]
-        return px.astype(int)
+        """[(x, y)] metres -> [(col, row)] integer cells (np.rint: half to even)."""
+        pts = np.asarray(points)
+        o_col, o_row = self._episode_pixel_origin
+        col = self.size - (np.rint(pts[:, 1] * self.pixels_per_meter) + o_col)
+        row = np.rint(pts[:, 0] * self.pixels_per_meter) + o_row
+        return np.stack((col, row), axis=1).astype(int)
 
     def _px_to_xy(self, px: np.ndarray) -> np.ndarray:
-        """(col, row) cells -> (x, y) metres (base_map.py:48-60)."""
-        q = px.copy()
-        q[:, 0] = self.size - q[:, 0]
-        return ((q - self._episode_pixel_origin) / self.pixels_per_meter)[:, ::-1]
+        """[(col, row)] cells (integer or fractional, e.g. frontier midpoints) -> [(x, y)] metres."""
+        cells = np.asarray(px)
+        o_col, o_row = self._episode_pixel_origin
+        x = (cells[:, 1] - o_row) / self.pixels_per_meter
+        y = ((self.size - cells[:, 0]) - o_col) / self.pixels_per_meter
+        return np.stack((x, y), axis=1)
