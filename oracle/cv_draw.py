@@ -17,7 +17,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from .cv_prims import line8
+from .cv_prims import clip_line, line8_clipped
 
 XY_SHIFT = 16
 XY_ONE = 1 << XY_SHIFT
@@ -35,24 +35,42 @@ def _plot(mask: np.ndarray, xs, ys) -> None:
     mask[ys[ok], xs[ok]] = True
 
 
+def poly_edge(w: int, h: int, p0: Tuple[int, int], p1: Tuple[int, int]):
+    """One PolyEdge of CollectPolyEdges (cv2 4.13): p0, p1 = (x in 16.16, integer row).  Returns (y0, y1, x_at_y0, dx)
+    or None for a horizontal edge.  When a (pixel-rounded) end point lies outside the image, cv2 clips the segment
+    (clipLine, integer pixels) and builds the edge from the CLIPPED columns -- always -- and from the clipped rows when
+    they differ, extrapolating back to the original first row (pinned by tests/test_oracle_cv_draw.py)."""
+    t0 = ((p0[0] + (XY_ONE >> 1)) >> XY_SHIFT, p0[1])
+    t1 = ((p1[0] + (XY_ONE >> 1)) >> XY_SHIFT, p1[1])
+    c0, c1 = p0, p1
+    if not (0 <= t0[0] < w and 0 <= t1[0] < w and 0 <= t0[1] < h and 0 <= t1[1] < h):
+        _, a, b = clip_line(w, h, t0, t1)
+        if a[1] != b[1]:
+            c0, c1 = (a[0] << XY_SHIFT, a[1]), (b[0] << XY_SHIFT, b[1])
+        else:
+            c0, c1 = (a[0] << XY_SHIFT, p0[1]), (b[0] << XY_SHIFT, p1[1])
+    if p0[1] == p1[1]:
+        return None
+    num, den = c1[0] - c0[0], c1[1] - c0[1]
+    dx = abs(num) // abs(den) * (1 if (num >= 0) == (den > 0) else -1)           # C truncating division
+    if p0[1] < p1[1]:
+        return (p0[1], p1[1], c0[0] + (p0[1] - c0[1]) * dx, dx)
+    return (p1[1], p0[1], c1[0] + (p1[1] - c1[1]) * dx, dx)
+
+
 def fill_poly_fixed(mask: np.ndarray, v: List[Tuple[int, int]]) -> None:
     """v: closed polygon, (x, y) in 16.16 fixed point.  Sets the cells cv2 would write."""
     h, w = mask.shape
-    n = len(v)
     pts = [(int(x), (int(y) + (XY_ONE >> 1)) >> XY_SHIFT) for x, y in v]       # x: 16.16, y: rounded row
     edges = []
     p0 = pts[-1]
     for p1 in pts:
         t0 = ((p0[0] + (XY_ONE >> 1)) >> XY_SHIFT, p0[1])
         t1 = ((p1[0] + (XY_ONE >> 1)) >> XY_SHIFT, p1[1])
-        _plot(mask, *line8(t0, t1))
-        if p0[1] != p1[1]:
-            num, den = p1[0] - p0[0], p1[1] - p0[1]
-            dx = abs(num) // abs(den) * (1 if (num >= 0) == (den > 0) else -1)       # C truncating division
-            if p0[1] < p1[1]:
-                edges.append((p0[1], p1[1], p0[0], dx))
-            else:
-                edges.append((p1[1], p0[1], p1[0], dx))
+        _plot(mask, *line8_clipped(w, h, t0, t1))
+        e = poly_edge(w, h, p0, p1)
+        if e is not None:
+            edges.append(e)
         p0 = p1
     if not edges:
         return
@@ -116,12 +134,13 @@ def ellipse_sector(h: int, w: int, center: Tuple[int, int], radius: int, start_d
 
 
 def _line2(mask: np.ndarray, p1: Tuple[int, int], p2: Tuple[int, int]) -> None:
-    """drawing.cpp Line2: DDA between 16.16 fixed-point endpoints (no clipping needed inside the image)."""
-    x1, y1 = p1
-    x2, y2 = p2
+    """drawing.cpp Line2: clipLine against the image scaled to 16.16, then a DDA between the clipped endpoints."""
+    h, w = mask.shape
+    ok, (x1, y1), (x2, y2) = clip_line(w << XY_SHIFT, h << XY_SHIFT, p1, p2)
+    if not ok:
+        return
     dx, dy = x2 - x1, y2 - y1
     ax, ay = abs(dx), abs(dy)
-    h, w = mask.shape
 
     def put(x, y):
         if 0 <= x < w and 0 <= y < h:
@@ -216,7 +235,17 @@ def fill_convex_fixed(mask: np.ndarray, v: List[Tuple[int, int]]) -> None:
 
 
 def thick_line2(mask: np.ndarray, p0: Tuple[int, int], p1: Tuple[int, int]) -> None:
-    """cv2.line(img, p0, p1, c, thickness=2, lineType=8) (drawing.cpp ThickLine)."""
+    """cv2.line / cv2.polylines(img, p0, p1, c, thickness=2, lineType=8) (drawing.cpp ThickLine).
+
+    cv2 4.13 first clips the integer centre line to the image rectangle grown by the thickness (2 px) on every side
+    (pinned empirically by tests/test_oracle_cv_draw.py: no other margin reproduces cv2 for segments that leave the image);
+    the 2-px rectangle and the end discs are then built from the CLIPPED end points."""
+    h, w = mask.shape
+    t = 2
+    ok, a, b = clip_line(w + 2 * t, h + 2 * t, (p0[0] + t, p0[1] + t), (p1[0] + t, p1[1] + t))
+    if not ok:
+        return
+    p0, p1 = (a[0] - t, a[1] - t), (b[0] - t, b[1] - t)
     x0, y0, x1, y1 = p0[0] << XY_SHIFT, p0[1] << XY_SHIFT, p1[0] << XY_SHIFT, p1[1] << XY_SHIFT
     dx, dy = (x0 - x1) / XY_ONE, (y1 - y0) / XY_ONE
     r = dx * dx + dy * dy

@@ -7,6 +7,7 @@ These are the rules the CUDA kernels re-implement, written so the kernels can be
 against them:
 
 * ``line8``            cv2.line(thickness=1, lineType=8) pixel set
+* ``clip_line``        cv::clipLine, applied by cv2 before any line is walked (``line8_clipped``)
                        (used by cv2.drawContours outline; reference call site
                        vlfm/mapping/value_map.py:260).
 * ``fill_polygon``     cv2.drawContours(img, [poly], -1, c, -1): outline + even-odd
@@ -60,6 +61,54 @@ def line8(p0, p1):
     return xs, ys
 
 
+def clip_line(w: int, h: int, p1, p2):
+    """cv::clipLine(Size2l(w, h), pt1, pt2) (drawing.cpp): Cohen-Sutherland with the intersection computed in double and
+    truncated toward zero.  Returns (visible, (x1, y1), (x2, y2)).  cv2 clips every line to the image BEFORE walking it
+    (LineIterator for thickness-1 lines, Line2 for the fixed-point outlines of FillConvexPoly), so the pixels of a line
+    that leaves the image are those of the CLIPPED segment, not the visible part of the unclipped one."""
+    x1, y1, x2, y2 = int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1])
+    right, bottom = w - 1, h - 1
+    if w <= 0 or h <= 0:
+        return False, (x1, y1), (x2, y2)
+
+    def tr(a: float) -> int:            # (int64)double
+        return int(a)
+
+    c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8
+    c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8
+    if (c1 & c2) == 0 and (c1 | c2) != 0:
+        if c1 & 12:
+            a = 0 if c1 < 8 else bottom
+            x1 += tr(float(a - y1) * float(x2 - x1) / float(y2 - y1))
+            y1 = a
+            c1 = (x1 < 0) + (x1 > right) * 2
+        if c2 & 12:
+            a = 0 if c2 < 8 else bottom
+            x2 += tr(float(a - y2) * float(x2 - x1) / float(y2 - y1))
+            y2 = a
+            c2 = (x2 < 0) + (x2 > right) * 2
+        if (c1 & c2) == 0 and (c1 | c2) != 0:
+            if c1:
+                a = 0 if c1 == 1 else right
+                y1 += tr(float(a - x1) * float(y2 - y1) / float(x2 - x1))
+                x1 = a
+                c1 = 0
+            if c2:
+                a = 0 if c2 == 1 else right
+                y2 += tr(float(a - x2) * float(y2 - y1) / float(x2 - x1))
+                x2 = a
+                c2 = 0
+    return (c1 | c2) == 0, (x1, y1), (x2, y2)
+
+
+def line8_clipped(w: int, h: int, p0, p1):
+    """Pixels of cv2.line(img[h, w], p0, p1, c, 1, 8): LineIterator clips to the image first, then walks the clipped segment."""
+    ok, a, b = clip_line(w, h, p0, p1)
+    if not ok:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    return line8(a, b)
+
+
 def fill_polygon(h: int, w: int, pts: np.ndarray) -> np.ndarray:
     """Boolean (h, w) mask of the cells cv2.drawContours(img,[pts],-1,c,-1) writes.
 
@@ -71,30 +120,34 @@ def fill_polygon(h: int, w: int, pts: np.ndarray) -> np.ndarray:
     nxt = np.roll(np.arange(n), -1)
     # --- outline: every edge, including the closing one, as an 8-connected line
     for i in range(n):
-        xs, ys = line8(pts[i], pts[nxt[i]])
+        xs, ys = line8_clipped(w, h, pts[i], pts[nxt[i]])
         ok = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
         out[ys[ok], xs[ok]] = True
-    # --- interior: even-odd scanline with 16.16 intercepts
-    x0 = pts[:, 0].copy()
-    y0 = pts[:, 1].copy()
-    x1 = pts[nxt, 0].copy()
-    y1 = pts[nxt, 1].copy()
-    keep = y0 != y1
-    x0, y0, x1, y1 = x0[keep], y0[keep], x1[keep], y1[keep]
-    sw = y0 > y1
-    x0, x1 = np.where(sw, x1, x0), np.where(sw, x0, x1)
-    y0, y1 = np.where(sw, y1, y0), np.where(sw, y0, y1)
-    num = (x1 - x0) << 16
-    den = y1 - y0
-    dxe = np.sign(num) * (np.abs(num) // den)  # C truncating division
-    xs16 = x0 << 16
+    # --- interior: even-odd scanline with 16.16 intercepts.  An edge with an end point outside the image is built from the
+    # CLIPPED end points (cv2 4.13 CollectPolyEdges, see oracle/cv_draw.py::poly_edge)
     toggle = np.zeros((h, w + 1), dtype=np.int64)
     exact = np.zeros((h, w), dtype=bool)
-    for e in range(len(x0)):
-        r = np.arange(max(int(y0[e]), 0), min(int(y1[e]), h), dtype=np.int64)
+    for i in range(n):
+        ax, ay, bx, by = int(pts[i, 0]), int(pts[i, 1]), int(pts[nxt[i], 0]), int(pts[nxt[i], 1])
+        if ay == by:
+            continue
+        c0, c1 = (ax << 16, ay), (bx << 16, by)
+        if not (0 <= ax < w and 0 <= bx < w and 0 <= ay < h and 0 <= by < h):
+            _, a, b = clip_line(w, h, (ax, ay), (bx, by))
+            if a[1] != b[1]:
+                c0, c1 = (a[0] << 16, a[1]), (b[0] << 16, b[1])
+            else:
+                c0, c1 = (a[0] << 16, ay), (b[0] << 16, by)
+        num, den = c1[0] - c0[0], c1[1] - c0[1]
+        dxe = abs(num) // abs(den) * (1 if (num >= 0) == (den > 0) else -1)  # C truncating division
+        if ay < by:
+            ya, yb, xs16 = ay, by, c0[0] + (ay - c0[1]) * dxe
+        else:
+            ya, yb, xs16 = by, ay, c1[0] + (by - c1[1]) * dxe
+        r = np.arange(max(ya, 0), min(yb, h), dtype=np.int64)
         if r.size == 0:
             continue
-        X = xs16[e] + dxe[e] * (r - y0[e])
+        X = xs16 + dxe * (r - ya)
         t = np.clip((X >> 16) + 1, 0, w)  # first column c with (c<<16) > X
         np.add.at(toggle, (r, t), 1)
         hit = ((X & 0xFFFF) == 0) & ((X >> 16) >= 0) & ((X >> 16) < w)

@@ -38,8 +38,7 @@ def test_area_convexity_and_point_distance():
 
 
 def test_ellipse_sector_inside_image():
-    """valid when the circle lies inside the image (the cone of the fog-of-war always does: the policy stops
-    before the map edge); clipped sectors follow OpenCV's clipLine path and are not restated."""
+    """circle inside the image; sectors clipped by the image border: tests/test_oracle_cv_draw.py"""
     rng = np.random.default_rng(2)
     for t in range(80):
         G, r = int(rng.integers(260, 400)), int(rng.integers(15, 120))
