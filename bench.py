@@ -33,6 +33,24 @@ MIN_D, MAX_D = 0.5, 5.0
 H, W, G = 480, 640, 1000
 PROMPT = "Seems like there is a chair ahead."
 NFRAMES = 16
+# the SAME string in both arms' config.workload
+WORKLOAD = ("configs[1]: BLIP-2 ITC (ViT-g/14 + Q-Former, synthetic weights) + ValueMap cone-fuse, batch=1 env/GPU, "
+            "640x480 RGB-D, 1000^2 grid, weighted fusion")
+
+
+def pin_cpu_threads() -> int:
+    """The CPU arm uses the host's cores the same way whatever launched it (torchrun exports OMP_NUM_THREADS=1)."""
+    import torch
+
+    n = max(1, min(64, (os.cpu_count() or 2) // 2))
+    torch.set_num_threads(n)
+    try:
+        import cv2
+
+        cv2.setNumThreads(n)
+    except Exception:
+        pass
+    return n
 
 
 def peaks():
@@ -96,6 +114,7 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, frames, state_dict, 
     from oracle.blip2_oracle import Blip2Oracle
     from oracle.value_map_oracle import ValueMapOracle
 
+    pin_cpu_threads()
     orc = Blip2Oracle(dims, state_dict)
     vm = ValueMapOracle(1, size=G, use_max_confidence=False, prims="cv2")
     ids = [101, 3849, 2066, 2045, 2003, 1037, 3242, 3805, 1012, 102]
@@ -134,10 +153,11 @@ def run_reference(args):
         "impl": "reference", "metric": "value-map steps/sec (ITM+cone-fuse)", "value": sps, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / sps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: BLIP-2 ITC (ViT-g/14 + Q-Former, synthetic weights) + ValueMap cone-fuse, batch=1 env, 640x480, 1000^2 grid"},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": 1,
+                   "note": "CPU arm: ONE process on rank 0 with the thread count below, whatever --gpus says (not multiplied by N)"},
         "cpu_baseline": {"value": sps, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{n} env-steps timed after {args.warmup} warm-up (fp32 HF BLIP-2 ITC forward + numpy/cv2 value-map oracle)",
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": sps, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -231,6 +251,24 @@ def run_b200(args):
     t_e2e = time.perf_counter() - t0
     t_e2e = max_over_ranks(t_e2e, dev)
     e2e = world * K / t_e2e
+    # the same loop with ORDINARY (pageable) numpy frames, as the reference's callers hand them over: staged through the
+    # classes' own page-locked buffers
+    fr_pg = [(np.array(f.rgb, copy=True), np.array(f.depth, copy=True), f.tf) for f in fr0]
+
+    def step_pageable(i):
+        rgb_, depth_, tf_ = fr_pg[i % NFRAMES]
+        c = itm1.cosine(rgb_, PROMPT)
+        vm.update_map(np.array([c]), depth_, tf_, MIN_D, MAX_D, FOV)
+
+    for i in range(Wm):
+        step_pageable(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_pageable(Wm + i)
+    torch.cuda.synchronize()
+    t_pg = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_pageable = world * K / t_pg
     # optional NCCL all-gather of a small per-rank metrics vector (never on the step path)
     per_rank = gather_metrics([rank, ms_local, float(eng.conf.sum().item())], dev)
     clocks = sampler.stop() if rank == 0 else None
@@ -242,24 +280,131 @@ def run_b200(args):
         sps, n, threads = cpu_reference(4, 1, 30.0, fr0, sd, dims)
         cpu = {"value": sps, "unit": "env-steps/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{n} env-steps (fp32 HF BLIP-2 ITC forward + numpy/cv2 value-map oracle), 1 warm-up"}
+    extra = None
+    if not args.no_extra:
+        extra = run_extras(args, dev, world, rank, sd, dims, itm if B >= 32 else None)
     if rank == 0:
         line = {
             "metric": "value-map steps/sec (ITM+cone-fuse)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "configs[1]: BLIP-2 ITC (ViT-g/14 + Q-Former, synthetic weights) + ValueMap cone-fuse, "
-                                   f"batch={B} env/GPU, 640x480 RGB-D, 1000^2 grid, weighted fusion",
+            "config": {"workload": WORKLOAD if B == 1 else WORKLOAD.replace("batch=1 env/GPU", f"batch={B} env/GPU"),
                        "envs_per_gpu": B, "l2": "per-step working set 2.0 GB of weights > 126 MB L2 (no flush needed)",
                        "timing": "CUDA events, max over ranks"},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": H * W * 3 + H * W * 4 + 17 * 8,
-                    "d2h_bytes_per_step": 4, "api": "BLIP2ITM.cosine + ValueMap.update_map (page-locked host numpy frames in, DMA to HBM, float out)"},
+                    "d2h_bytes_per_step": 4, "api": "BLIP2ITM.cosine + ValueMap.update_map (page-locked host numpy frames in, DMA to HBM, float out)",
+                    "pageable_value": e2e_pageable,
+                    "pageable_note": "same loop with ordinary (pageable) numpy frames: staged through the classes' page-locked buffers"},
             "gpu_launches": launches_per_step * K,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "per_rank": [{"rank": int(r[0]), "ms": r[1], "conf_checksum": r[2]} for r in per_rank],
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(args, dev, world, rank, sd, dims, itm32):
+    """The other BASELINE.json configs, a few steps each, on every rank (env shards, no collective): configs[1] at 32 env/GPU,
+    configs[2] (full step, 32 envs), a configs[3] slice (32 env/GPU, 2000^2 grid) and a configs[4] slice (1024^2 RGB-D,
+    4000^2 x 0.025 m grid, 8 env/GPU).  `value` of each = whole-job env-steps/s (max over ranks of the elapsed time)."""
+    import torch
+
+    from vlfm_b200.mapping.value_map import ValueMapBatch
+    from vlfm_b200.utils.dist import max_over_ranks
+    from vlfm_b200.utils.full_step import FullStep, grid_bytes
+    from vlfm_b200.vlm.blip2itm import BLIP2ITM
+    from vlfm_b200.vlm.grounding_dino import GroundingDINO
+
+    pk, src = peaks()
+    hbm = float(pk["hbm_gbs"])
+    out = {"peak_hbm_gbs": hbm, "peak_source": src}
+    EB = args.extra_batch
+    itm = itm32 if itm32 is not None else BLIP2ITM(state_dict=sd, dims=dims, max_batch=EB, device=dev)
+
+    # every rank records its own elapsed seconds; ONE max-over-ranks at the end turns them into whole-job values (an extra
+    # that fails on one rank must not desynchronise the collective)
+    pending = []
+
+    def agg(envs, steps, seconds):
+        pending.append((envs, steps, seconds))
+        return len(pending) - 1
+
+    # ---- configs[1] at EB env/GPU: ITC + cone-fuse, inputs resident in HBM
+    try:
+        eng = ValueMapBatch(EB, 1, size=G, use_max_confidence=False, device=dev)
+        fr = [make_frames(1000 + rank * EB + e) for e in range(EB)]
+        nfr = 4
+        rgb = torch.from_numpy(np.stack([np.stack([f[i].rgb for f in fr]) for i in range(nfr)])).to(dev)
+        depth = torch.from_numpy(np.stack([np.stack([f[i].depth for f in fr]) for i in range(nfr)])).to(dev)
+        tfs = torch.from_numpy(np.stack([np.stack([f[i].tf for f in fr]) for i in range(nfr)])).to(dev)
+
+        def st(i):
+            j = i % nfr
+            cos = itm.cosine_device(rgb[j], PROMPT)
+            eng.update(cos.double().view(EB, 1), depth[j], tfs[j], MIN_D, MAX_D, FOV)
+
+        for i in range(3):
+            st(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 6
+        e0.record()
+        for i in range(n):
+            st(3 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        roof = gemm_roofline(itm.engine, EB, dims)
+        out["configs1_b%d" % EB] = {"workload": WORKLOAD.replace("batch=1 env/GPU", f"batch={EB} env/GPU"), "value": agg(EB, n, ms * 1e-3),
+                                    "unit": "env-steps/s", "ms_per_step": ms / n, "steps": n, "gemm_roofline": {k: roof[k] for k in ("achieved", "peak", "frac", "unit", "launches_per_step", "gemm_ms_per_step")}}
+        del eng, rgb, depth, tfs, fr
+    except Exception as e:   # an extra never takes the headline down with it
+        out["configs1_b%d" % EB] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+
+    gd = None
+    try:
+        gd = GroundingDINO(device=dev, synthetic=True)
+    except Exception as e:
+        out["gdino_error"] = repr(e)
+
+    def full(name, workload, B, h, w, g, ppm, steps, warm, bound):
+        try:
+            fs = FullStep(dev, B, h, w, g, ppm, itm, gd, frames_per_env=steps + warm, seed0=2000 + rank * B, bound_m=bound)
+            r = fs.run(steps, warm)
+            roofs = fs.grid_rooflines(hbm)
+            out[name] = {"workload": workload, "value": agg(B, steps, r["wall_s"]), "unit": "env-steps/s", "ms_per_step": r["ms_per_step"],
+                         "steps": steps, "warmup": warm, "envs_per_gpu": B, "component_ms_per_step": r["component_ms_per_step"],
+                         "frontiers_per_env_step": r["frontiers_per_env_step"], "grid_bytes_per_env_step": r["grid_bytes_per_env_step"],
+                         "grid_rooflines": roofs,
+                         "timing": "host wall clock around whole steps (H2D of the page-locked RGB-D batch and D2H of the frontier lists inside), max over ranks; components by CUDA events"}
+            del fs
+        except Exception as e:
+            out[name] = {"workload": workload, "error": repr(e)}
+        torch.cuda.empty_cache()
+
+    full("configs2_full_step", f"configs[2]: full step (GroundingDINO + BLIP-2 ITC + Obstacle/Value/Frontier update), batch={EB} envs/GPU, 640x480 RGB-D, 1000^2 grid",
+         EB, H, W, 1000, 20, 4, 3, 15.0)
+    full("configs3_slice", f"configs[3] slice: full step, {EB} envs/GPU (256 envs = 32/GPU x 8), 640x480 RGB-D, 2000^2 x 0.05 m grid",
+         EB, H, W, 2000, 20, 3, 2, 30.0)
+    b4 = max(1, EB // 4)
+    full("configs4_slice", f"configs[4] slice: full step, {b4} envs/GPU (64 envs on 8 GPUs), 1024x1024 RGB-D, ViT-g at 224 (reference semantics), 4000^2 x 0.025 m grid",
+         b4, 1024, 1024, 4000, 40, 3, 2, 30.0)
+    names = ["configs1_b%d" % EB, "configs2_full_step", "configs3_slice", "configs4_slice"]
+    for nme in names:
+        ent = out.get(nme, {})
+        idx = ent.get("value")
+        local = pending[idx][2] if isinstance(idx, int) and "error" not in ent else 1e30
+        worst = max_over_ranks(local, dev)
+        if "error" not in ent:
+            if worst >= 1e29:
+                ent["error"] = "failed on another rank"; ent["value"] = None
+            else:
+                envs, steps, _ = pending[idx]
+                ent["value"] = world * envs * steps / worst
+    return out
 
 
 def gemm_roofline(engine, B, dims):
@@ -323,6 +468,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[1]@32 / [2] / [3] / [4] slices")
+    ap.add_argument("--extra-batch", type=int, default=32, help="envs per GPU of the extra slices")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

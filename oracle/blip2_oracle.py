@@ -51,6 +51,30 @@ class Blip2Oracle:
         out = self.model(pixel_values=px, input_ids=ids, attention_mask=torch.ones_like(ids), use_image_text_matching_head=False)
         return float(out.logits_per_image.reshape(-1)[0])
 
+    # The same forward split at the image / text boundary (modeling_blip_2.py, ITC branch of Blip2ForImageTextRetrieval.forward):
+    # many frames x many prompts cost one ViT pass per frame.  tests/test_oracle_blip2_split.py pins the split to cosine().
+    @torch.inference_mode()
+    def image_features(self, image: np.ndarray) -> torch.Tensor:
+        """normalised vision_projection of the 32 query outputs, [queries, proj]"""
+        m = self.model
+        px = preprocess(image, self.dims.image).unsqueeze(0)
+        img = m.vision_model(pixel_values=px)[0]
+        att = torch.ones(img.shape[:-1], dtype=torch.long)
+        q = m.qformer(query_embeds=m.query_tokens.expand(1, -1, -1), encoder_hidden_states=img, encoder_attention_mask=att, return_dict=True)[0]
+        return torch.nn.functional.normalize(m.vision_projection(q), dim=-1)[0]
+
+    @torch.inference_mode()
+    def text_feature(self, token_ids: Sequence[int]) -> torch.Tensor:
+        m = self.model
+        ids = torch.tensor([list(token_ids)], dtype=torch.long)
+        emb = m.embeddings(input_ids=ids)
+        t = m.qformer(query_embeds=emb, query_length=0, attention_mask=torch.ones_like(ids), return_dict=True)[0]
+        return torch.nn.functional.normalize(m.text_projection(t[:, 0, :]), dim=-1)[0]
+
+    @staticmethod
+    def cosine_from(img_feat: torch.Tensor, txt_feat: torch.Tensor) -> float:
+        return float((img_feat @ txt_feat).max())
+
     @torch.inference_mode()
     def image_tokens(self, image: np.ndarray) -> torch.Tensor:
         px = preprocess(image, self.dims.image).unsqueeze(0)

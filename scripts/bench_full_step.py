@@ -42,7 +42,7 @@ def main():
     if not a.no_gdino:
         from vlfm_b200.vlm.grounding_dino import GroundingDINO
 
-        gd = GroundingDINO(device=dev)
+        gd = GroundingDINO(device=dev, synthetic=True)
         ids = gd.tokenizer.encode("chair . couch . potted plant . bed . toilet . tv .")
     vmb = ValueMapBatch(B, 1, size=G, use_max_confidence=False, device=dev)
     oms = [ObstacleMap(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=a.hole_thresh, size=G, device=dev) for _ in range(B)]

@@ -6,7 +6,7 @@ from vlfm_b200.vlm.grounding_dino import GroundingDINO
 
 B = int(os.environ.get("B", "32"))
 dev = torch.device("cuda", 0)
-gd = GroundingDINO(device=dev)
+gd = GroundingDINO(device=dev, synthetic=True)
 ids = gd.tokenizer.encode("chair . couch . potted plant . bed . toilet . tv .")
 rng = np.random.default_rng(0)
 img = torch.from_numpy(rng.integers(0, 256, (B, 480, 640, 3), dtype=np.uint8)).to(dev)

@@ -58,22 +58,37 @@ def test_small_models_vs_oracle(dims, tol):
     assert np.abs(tok - tok_ref).max() <= 3e-2 and np.abs(tok - tok_ref).mean() <= 3e-3
 
 
-def test_full_size_vitg_vs_oracle():
-    """ViT-g/14 (39 layers, 1408) + 12-layer Q-Former, seeded synthetic weights: cosine within 2e-4
-    of the fp32 oracle (fp16 tensor-core operands, fp32 accumulation; measured 5e-5 / 4e-6 on B200, printed)."""
-    from vlfm_b200.vlm.blip2itm import BLIP2ITM
+PROMPTS = ["Seems like there is a chair ahead.", "Seems like there is a potted plant ahead.", "Seems like there is a toilet ahead."]
 
+
+@pytest.mark.parametrize("outliers,frames", [(False, 32), (True, 8)])
+def test_full_size_vitg_vs_oracle(outliers, frames):
+    """ViT-g/14 (39 layers, 1408) + 12-layer Q-Former at full size, seeded synthetic weights (plain Gaussian, and with
+    trained-checkpoint-like LayerNorm outlier channels / massive activations): BLIP2ITM.cosine within the north-star 1e-4 of
+    the fp32 oracle on every one of frames x 3 prompts (fp16 tensor-core operands, fp32 accumulation / residual stream /
+    statistics; lavis runs the ViT under fp16 autocast and the Q-Former in fp32).  Also bounds the run-to-run spread of the
+    cosine (split-K red.add order inside the CUDA graph)."""
+    from vlfm_b200.vlm.blip2itm import BLIP2ITM, HashTokenizer, pre_caption
+
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
     dims = Blip2Dims()
-    sd = random_state_dict(dims, 0)
+    sd = random_state_dict(dims, 0, outliers=outliers)
     orc = blip2_oracle.Blip2Oracle(dims, sd)
     m = BLIP2ITM(state_dict=sd, dims=dims, max_batch=1)
-    ids = [101, 2000, 3000, 4000, 102]
-    m.tokenizer = lambda s: ids
+    tok = HashTokenizer(dims.vocab)
+    txt = [orc.text_feature(tok(pre_caption(p))) for p in PROMPTS]
     rng = np.random.default_rng(2)
-    errs = []
-    for _ in range(2):
+    errs, spread = [], 0.0
+    for k in range(frames):
         img = make_rgb(rng, 480, 640)
-        ref, got = orc.cosine(img, ids), m.cosine(img, "x")
-        errs.append(abs(ref - got))
-        print("cosine ref", ref, "gpu", got, "abs err", abs(ref - got))
-    assert max(errs) <= 2e-4
+        feat = orc.image_features(img)
+        for p, t in zip(PROMPTS, txt):
+            ref, got = orc.cosine_from(feat, t), m.cosine(img, p)
+            errs.append(abs(ref - got))
+        if k < 3:
+            rep = [m.cosine(img, PROMPTS[0]) for _ in range(6)]
+            spread = max(spread, max(rep) - min(rep))
+    errs = np.array(errs)
+    print(f"outliers={outliers}: {len(errs)} cosines, max |err| {errs.max():.3e}, mean {errs.mean():.3e}, run-to-run spread {spread:.3e}")
+    assert errs.max() <= 1e-4
+    assert spread <= 2e-5

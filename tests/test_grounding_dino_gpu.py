@@ -15,7 +15,7 @@ def pair():
     from vlfm_b200.vlm.grounding_dino import GroundingDINO
 
     orc = GdinoOracle(0)
-    g = GroundingDINO(state_dict={k: v.clone() for k, v in orc.state_dict().items()}, seed=0)
+    g = GroundingDINO(state_dict={k: v.clone() for k, v in orc.state_dict().items()}, seed=0, synthetic=True)
     return orc, g
 
 
@@ -284,3 +284,76 @@ def test_batch1_cuda_graph_replay_matches_eager(pair):
         g.raw_outputs(img1, ids)
     torch.cuda.synchronize()
     print(f"batch-1 GroundingDINO forward (graph replay incl. H2D): {(time.perf_counter() - t0) * 100:.2f} ms")
+
+
+def _decisions(logits, boxes, ids, box_thr, text_thr, decode):
+    """groundingdino.util.inference.predict restated (vlfm/vlm/grounding_dino.py:61-72): kept rows, their max score, phrase."""
+    mx = logits.max(dim=1)[0]
+    keep = mx > box_thr
+    out = []
+    for row, b, s in zip(logits[keep], boxes[keep], mx[keep]):
+        pos = row > text_thr
+        pos[0] = False
+        pos[len(ids) - 1:] = False
+        out.append((decode([ids[i] for i in pos.nonzero(as_tuple=True)[0].tolist()]).replace(".", "").strip(), b, float(s)))
+    return out
+
+
+@pytest.fixture(scope="module")
+def pair_calibrated():
+    """Same seeded weights with the decoder's output LayerNorm scaled by 0.1: with plain random weights the contrastive
+    logits (dot products of two un-normalised 256-d vectors) saturate the sigmoid at 0 / 1 and every decision is trivial."""
+    from vlfm_b200.vlm.grounding_dino import GroundingDINO
+
+    orc = GdinoOracle(0)
+    sd = orc.model.state_dict()
+    for k in ("model.decoder.layer_norm.weight", "model.decoder.layer_norm.bias"):
+        sd[k].mul_(0.1)
+    g = GroundingDINO(state_dict={k: v.clone() for k, v in orc.state_dict().items()}, seed=0, synthetic=True)
+    return orc, g
+
+
+def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
+    """Decision level: which queries pass box_threshold, which tokens pass text_threshold (the phrase) and where the box is.
+    Synthetic-weight scores have no natural gap at 0.35 / 0.25, so the thresholds are put at quantiles of the oracle's own
+    score distribution and detections whose score lies within DELTA of a threshold (either model could tip them) are
+    exempt; every other detection of one model must exist in the other with the same phrase, box and score.  The 900 rows
+    may permute between the two models (top-k over near-tied proposals), hence the set matching."""
+    orc, g = pair_calibrated
+    DELTA = 0.01
+    n_checked = n_exempt = 0
+    for seed, caption in ((21, "chair . person . dog ."), (22, "couch . potted plant . tv ."), (23, "bed . toilet .")):
+        img = make_rgb(np.random.default_rng(seed), 480, 640)
+        ids = g.tokenizer.encode(caption)
+        ref_l, ref_b = orc.raw_outputs(img, ids)
+        got_l, got_b = (t.cpu() for t in g.raw_outputs(img, ids))
+        mx = ref_l.max(dim=1)[0]
+        box_thr = float(mx.quantile(0.75))                     # ~225 of 900 queries kept
+        text_thr = box_thr * 0.25 / 0.35
+        a = _decisions(ref_l, ref_b, ids, box_thr, text_thr, g.tokenizer.decode)
+        b = _decisions(got_l, got_b, ids, box_thr, text_thr, g.tokenizer.decode)
+        assert len(a) > 20
+        # tokens of a kept row close to text_thr could flip the phrase: such rows are exempt too
+        def near_text(l_row):
+            v = l_row[1:len(ids) - 1]
+            return bool(((v - text_thr).abs() < DELTA).any())
+        for src, dst, src_l in ((a, b, ref_l), (b, a, got_l)):
+            rows = {id(d): None for d in src}
+            for phrase, box, score in src:
+                if score < box_thr + DELTA:
+                    n_exempt += 1
+                    continue
+                # the logits row this detection came from (for the text-threshold exemption)
+                r = src_l[(src_l.max(dim=1)[0] - score).abs().argmin()]
+                if near_text(r):
+                    n_exempt += 1
+                    continue
+                cand = [(float((box - bb).abs().sum()), p2, s2) for p2, bb, s2 in dst]
+                assert cand, "the other model kept nothing"
+                dist, p2, s2 = min(cand)
+                assert dist <= 2e-2, f"no matching box for {phrase!r} score {score:.3f} (nearest {dist:.3f})"
+                assert p2 == phrase, f"phrase differs: {phrase!r} vs {p2!r} (score {score:.3f})"
+                assert abs(s2 - score) <= DELTA
+                n_checked += 1
+    print(f"decision test: {n_checked} detections matched exactly, {n_exempt} within {DELTA} of a threshold (exempt)")
+    assert n_checked >= 60 and n_exempt <= n_checked

@@ -328,14 +328,39 @@ __global__ void planes_to_image_kernel(const uint32_t* __restrict__ tog, const u
   }
 }
 
+// cv::clipLine(Size2l(W, H), pt1, pt2) (oracle/cv_prims.py::clip_line): Cohen-Sutherland, intersections in double, truncated
+// toward zero.  cv2 clips every line to the image before walking it, so a line that leaves the grid is the walk of the CLIPPED
+// segment.  The end points are modified even when the function returns false (as in OpenCV).
+__device__ __forceinline__ long long clip_isect(long long a, long long b, long long c) {   // (int64)((double)a * b / c)
+  return (long long)__ddiv_rn(__dmul_rn((double)a, (double)b), (double)c);
+}
+__device__ bool clip_line(long long W, long long H, long long& x1, long long& y1, long long& x2, long long& y2) {
+  const long long right = W - 1, bottom = H - 1;
+  if (W <= 0 || H <= 0) return false;
+  int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+  int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+  if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+    long long a;
+    if (c1 & 12) { a = c1 < 8 ? 0 : bottom; x1 += clip_isect(a - y1, x2 - x1, y2 - y1); y1 = a; c1 = (x1 < 0) + (x1 > right) * 2; }
+    if (c2 & 12) { a = c2 < 8 ? 0 : bottom; x2 += clip_isect(a - y2, x2 - x1, y2 - y1); y2 = a; c2 = (x2 < 0) + (x2 > right) * 2; }
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      if (c1) { a = c1 == 1 ? 0 : right; y1 += clip_isect(a - x1, y2 - y1, x2 - x1); x1 = a; c1 = 0; }
+      if (c2) { a = c2 == 1 ? 0 : right; y2 += clip_isect(a - x2, y2 - y1, x2 - x1); x2 = a; c2 = 0; }
+    }
+  }
+  return (c1 | c2) == 0;
+}
+
 // cv2.ellipse filled sector: polygon (x, y in 16.16, last vertex = centre) from the host; CollectPolyEdges +
-// FillEdgeCollection (oracle/cv_draw.py::fill_poly_fixed).  One block; window image W x W.
-__device__ __forceinline__ void plot_line8(uint32_t* orb, int pw, int W, int H, int ax, int ay, int bx, int by) {
+// FillEdgeCollection (oracle/cv_draw.py::fill_poly_fixed / poly_edge).  One block; the image is the GW x GH grid, of which the
+// W x H window at (ox, oy) is rasterised (the window may hang over the grid edge: those cells are masked by the caller).
+// 8-connected line between two pixels of the grid (already clipped), plotted into the window's outline plane
+__device__ __forceinline__ void plot_line8(uint32_t* orb, int pw, int W, int H, int ox, int oy, int ax, int ay, int bx, int by) {
   if (bx < ax) { int t = ax; ax = bx; bx = t; t = ay; ay = by; by = t; }
   const int dx = bx - ax, dy = by - ay, sy = dy >= 0 ? 1 : -1, ady = dy >= 0 ? dy : -dy;
   const bool ymaj = ady > dx;
   const int major = ymaj ? ady : dx, minor = ymaj ? dx : ady;
-  int x = ax, y = ay, err = major - 2 * minor;
+  int x = ax - ox, y = ay - oy, err = major - 2 * minor;
   for (int k = 0; k <= major; ++k) {
     if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) atomicOr(&orb[y * pw + (x >> 5)], 1u << (x & 31));
     const bool m = err < 0;
@@ -343,24 +368,38 @@ __device__ __forceinline__ void plot_line8(uint32_t* orb, int pw, int W, int H, 
     if (ymaj) { y += sy; x += m ? 1 : 0; } else { x += 1; y += m ? sy : 0; }
   }
 }
-__global__ void sector_edges_kernel(const long long* __restrict__ v, int nv, int ox, int oy, uint32_t* tog, uint32_t* orb, int W, int H, int pw) {
-  // vertices are in grid coordinates (16.16); the window origin (ox, oy) is subtracted here
+__global__ void sector_edges_kernel(const long long* __restrict__ v, int nv, int ox, int oy, int GW, int GH, uint32_t* tog, uint32_t* orb,
+                                    int W, int H, int pw) {
   for (int e = threadIdx.x; e < nv; e += blockDim.x) {
     const int e0 = e == 0 ? nv - 1 : e - 1;
-    const long long x0 = v[2 * e0] - ((long long)ox << XYS), x1 = v[2 * e] - ((long long)ox << XYS);
-    const int y0 = (int)((v[2 * e0 + 1] + (XYONE >> 1)) >> XYS) - oy, y1 = (int)((v[2 * e + 1] + (XYONE >> 1)) >> XYS) - oy;
-    plot_line8(orb, pw, W, H, (int)((x0 + (XYONE >> 1)) >> XYS), y0, (int)((x1 + (XYONE >> 1)) >> XYS), y1);
+    const long long x0 = v[2 * e0], x1 = v[2 * e];                                                 // 16.16 columns
+    const long long y0 = (v[2 * e0 + 1] + (XYONE >> 1)) >> XYS, y1 = (v[2 * e + 1] + (XYONE >> 1)) >> XYS;   // rounded rows
+    long long ax = (x0 + (XYONE >> 1)) >> XYS, ay = y0, bx = (x1 + (XYONE >> 1)) >> XYS, by = y1;        // pixel end points
+    const bool outside = (unsigned long long)ax >= (unsigned long long)GW || (unsigned long long)bx >= (unsigned long long)GW ||
+                         (unsigned long long)ay >= (unsigned long long)GH || (unsigned long long)by >= (unsigned long long)GH;
+    long long cx0 = x0, cy0 = y0, cx1 = x1, cy1 = y1;
+    bool vis = true;
+    if (outside) {
+      vis = clip_line(GW, GH, ax, ay, bx, by);
+      // PolyEdge from the clipped columns (always) and the clipped rows (when they differ)
+      cx0 = ax << XYS; cx1 = bx << XYS;
+      if (ay != by) { cy0 = ay; cy1 = by; }
+    }
+    if (vis) plot_line8(orb, pw, W, H, ox, oy, (int)ax, (int)ay, (int)bx, (int)by);
     if (y0 == y1) continue;
-    const long long num = x1 - x0, den = y1 - y0;
-    const long long dxe = num / den;                       // C truncating division
-    const int ya = y0 < y1 ? y0 : y1, yb = y0 < y1 ? y1 : y0;
-    const long long xs = y0 < y1 ? x0 : x1;
-    for (int r = max(ya, 0); r < min(yb, H); ++r) {
+    const long long dxe = (cx1 - cx0) / (cy1 - cy0);          // C truncating division
+    long long ya, yb, xs;
+    if (y0 < y1) { ya = y0; yb = y1; xs = cx0 + (y0 - cy0) * dxe; } else { ya = y1; yb = y0; xs = cx1 + (y1 - cy1) * dxe; }
+    long long r0 = ya > 0 ? ya : 0, r1 = yb < GH ? yb : GH;
+    if (r0 < oy) r0 = oy;
+    if (r1 > oy + H) r1 = oy + H;
+    for (long long r = r0; r < r1; ++r) {
       const long long X = xs + dxe * (r - ya);
-      long long t = (X >> XYS) + 1;
+      const int wr = (int)(r - oy);
+      long long t = (X >> XYS) + 1 - ox;
       if (t < 0) t = 0;
-      if (t < W) atomicXor(&tog[r * pw + (int)(t >> 5)], 1u << ((int)t & 31));
-      if ((X & (XYONE - 1)) == 0) { const long long c = X >> XYS; if (c >= 0 && c < W) atomicOr(&orb[r * pw + (int)(c >> 5)], 1u << ((int)c & 31)); }
+      if (t < W) atomicXor(&tog[wr * pw + (int)(t >> 5)], 1u << ((int)t & 31));
+      if ((X & (XYONE - 1)) == 0) { const long long c = (X >> XYS) - ox; if (c >= 0 && c < W) atomicOr(&orb[wr * pw + (int)(c >> 5)], 1u << ((int)c & 31)); }
     }
   }
 }
@@ -384,7 +423,9 @@ __global__ void fog_masks_kernel(const uint8_t* __restrict__ cone, const uint8_t
                                  uint8_t* __restrict__ blocked, uint8_t* __restrict__ visible) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W0 * W0; i += gridDim.x * blockDim.x) {
     const int y = i / W0, x = i - y * W0;
-    const uint8_t c = cone[i], nv = nav[(size_t)(oy + y) * G + ox + x];
+    const int gx = ox + x, gy = oy + y;
+    if ((unsigned)gx >= (unsigned)G || (unsigned)gy >= (unsigned)G) { blocked[i] = 0; visible[i] = 0; continue; }   // cv2 clips at the grid edge
+    const uint8_t c = cone[i], nv = nav[(size_t)gy * G + gx];
     blocked[i] = c && !nv; visible[i] = c && nv;
   }
 }
@@ -455,14 +496,19 @@ __global__ void rays_kernel(const Contour* __restrict__ cont, const int2* __rest
   }
 }
 
-// cv2 thickness-2 line into the byte image `cut` (oracle/cv_draw.py::thick_line2); coordinates may leave the window
-__device__ __forceinline__ void put_px(uint8_t* img, int W, int H, long long x, long long y) {
-  if (x >= 0 && x < W && y >= 0 && y < H) img[y * W + x] = 1;
+// cv2 thickness-2 line into the byte image `cut` (oracle/cv_draw.py::thick_line2).  All geometry is in GRID coordinates (the
+// clipping rules refer to the grid); `cut` is the window at (ox, oy), pixels outside it are skipped.
+struct CutWin { uint8_t* img; int W, H, ox, oy; };
+__device__ __forceinline__ void put_px(const CutWin& c, long long x, long long y) {
+  x -= c.ox; y -= c.oy;
+  if (x >= 0 && x < c.W && y >= 0 && y < c.H) c.img[y * c.W + x] = 1;
 }
 __device__ __forceinline__ long long cdiv(long long a, long long b) {   // C truncating division (b > 0)
   return a / b;
 }
-__device__ void line2_fixed(uint8_t* img, int W, int H, long long x1, long long y1, long long x2, long long y2) {
+// drawing.cpp Line2: clipLine against the image scaled to 16.16, then a DDA between the clipped end points
+__device__ void line2_fixed(const CutWin& c, int G, long long x1, long long y1, long long x2, long long y2) {
+  if (!clip_line((long long)G << XYS, (long long)G << XYS, x1, y1, x2, y2)) return;
   long long dx = x2 - x1, dy = y2 - y1;
   const long long ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
   long long x_step, y_step, ecount;
@@ -474,21 +520,26 @@ __device__ void line2_fixed(uint8_t* img, int W, int H, long long x1, long long 
     x_step = cdiv(dx << XYS, ay | 1); y_step = XYONE; ecount = (y2 - y1) >> XYS;
   }
   x1 += XYONE >> 1; y1 += XYONE >> 1;
-  put_px(img, W, H, (x2 + (XYONE >> 1)) >> XYS, (y2 + (XYONE >> 1)) >> XYS);
+  put_px(c, (x2 + (XYONE >> 1)) >> XYS, (y2 + (XYONE >> 1)) >> XYS);
   if (ax > ay) {
     long long x = x1 >> XYS, y = y1;
-    while (ecount >= 0) { put_px(img, W, H, x, y >> XYS); ++x; y += y_step; --ecount; }
+    while (ecount >= 0) { put_px(c, x, y >> XYS); ++x; y += y_step; --ecount; }
   } else {
     long long y = y1 >> XYS, x = x1;
-    while (ecount >= 0) { put_px(img, W, H, x >> XYS, y); x += x_step; ++y; --ecount; }
+    while (ecount >= 0) { put_px(c, x >> XYS, y); x += x_step; ++y; --ecount; }
   }
 }
 __device__ __forceinline__ long long pick4(const long long (&a)[4], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3])); }
-__global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __restrict__ cut, int W, int H, const ExState* st) {
+__global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __restrict__ cut, int W, int H, int ox, int oy, int G, const ExState* st) {
   const int ri = blockIdx.x * blockDim.x + threadIdx.x;
   if (ri >= st->n_rays) return;
   const int4 r = rays[ri];
-  const long long x0 = (long long)r.x << XYS, y0 = (long long)r.y << XYS, x1 = (long long)r.z << XYS, y1 = (long long)r.w << XYS;
+  const CutWin cw{cut, W, H, ox, oy};
+  // ThickLine (cv2 4.13): the integer centre line is first clipped to the image grown by the thickness on every side
+  long long px0 = r.x + ox + 2, py0 = r.y + oy + 2, px1 = r.z + ox + 2, py1 = r.w + oy + 2;
+  if (!clip_line((long long)G + 4, (long long)G + 4, px0, py0, px1, py1)) return;
+  px0 -= 2; py0 -= 2; px1 -= 2; py1 -= 2;
+  const long long x0 = px0 << XYS, y0 = py0 << XYS, x1 = px1 << XYS, y1 = py1 << XYS;
   const double dx = (double)(x0 - x1) / 65536.0, dy = (double)(y1 - y0) / 65536.0;
   double rr = dx * dx + dy * dy;
   if (fabs(rr) > 2.220446049250313e-16) {
@@ -497,7 +548,7 @@ __global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __rest
     long long vx[4] = {x0 + dpx, x0 - dpx, x1 - dpx, x1 + dpx}, vy[4] = {y0 + dpy, y0 - dpy, y1 - dpy, y1 + dpy};
     // FillConvexPoly (shift = 16): Line2 outline ...
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const int j = (i + 3) & 3; line2_fixed(cut, W, H, vx[j], vy[j], vx[i], vy[i]); }
+    for (int i = 0; i < 4; ++i) { const int j = (i + 3) & 3; line2_fixed(cw, G, vx[j], vy[j], vx[i], vy[i]); }
     // ... + two-edge scan
     const long long delta = XYONE >> 1;
     int imin = 0;
@@ -508,42 +559,49 @@ __global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __rest
       ymax_f = vy[i] > ymax_f ? vy[i] : ymax_f; xmax_f = vx[i] > xmax_f ? vx[i] : xmax_f; xmin_f = vx[i] < xmin_f ? vx[i] : xmin_f;
     }
     long long ymin = (ymin_f + delta) >> XYS, ymax = (ymax_f + delta) >> XYS;
-    // (the image-bounds early-out of OpenCV refers to the full grid; rows/cols outside the window are skipped per pixel)
-    struct { int idx, di; long long x, dx; long long ye; } e[2];
-    e[0].idx = e[1].idx = imin; e[0].ye = e[1].ye = ymin; e[0].di = 1; e[1].di = 3;
-    e[0].x = e[1].x = -XYONE; e[0].dx = e[1].dx = 0;
-    int edges = 4;
-    long long y = ymin;
-    do {
+    const long long xmin = (xmin_f + delta) >> XYS, xmax = (xmax_f + delta) >> XYS;
+    if (!(xmax < 0 || ymax < 0 || xmin >= G || ymin >= G)) {       // OpenCV's early-out refers to the grid
+      if (ymax > G - 1) ymax = G - 1;
+      struct { int idx, di; long long x, dx; long long ye; } e[2];
+      e[0].idx = e[1].idx = imin; e[0].ye = e[1].ye = ymin; e[0].di = 1; e[1].di = 3;
+      e[0].x = e[1].x = -XYONE; e[0].dx = e[1].dx = 0;
+      int edges = 4;
+      long long y = ymin;
+      do {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        if (y >= e[i].ye) {
-          int idx0 = e[i].idx, di = e[i].di, idx = (idx0 + di) & 3;
-          for (; edges-- > 0;) {
-            const long long ty = (pick4(vy, idx) + delta) >> XYS;
-            if (ty > y) {
-              const long long xs = pick4(vx, idx0), xe = pick4(vx, idx);
-              e[i].ye = ty; e[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y)); e[i].x = xs; e[i].idx = idx;
-              break;
+        for (int i = 0; i < 2; ++i) {
+          if (y >= e[i].ye) {
+            int idx0 = e[i].idx, di = e[i].di, idx = (idx0 + di) & 3;
+            for (; edges-- > 0;) {
+              const long long ty = (pick4(vy, idx) + delta) >> XYS;
+              if (ty > y) {
+                const long long xs = pick4(vx, idx0), xe = pick4(vx, idx);
+                e[i].ye = ty; e[i].dx = ((xe - xs) * 2 + (ty - y)) / (2 * (ty - y)); e[i].x = xs; e[i].idx = idx;
+                break;
+              }
+              idx0 = idx; idx = (idx + di) & 3;
             }
-            idx0 = idx; idx = (idx + di) & 3;
           }
         }
-      }
-      if (edges < 0) break;
-      {
-        const bool sw = e[0].x > e[1].x;
-        const long long xx1 = ((sw ? e[1].x : e[0].x) + delta) >> XYS, xx2 = ((sw ? e[0].x : e[1].x) + delta) >> XYS;
-        if (y >= 0 && y < H) for (long long x = xx1 < 0 ? 0 : xx1; x <= xx2 && x < W; ++x) cut[y * W + x] = 1;
-      }
-      e[0].x += e[0].dx; e[1].x += e[1].dx;
-    } while (++y <= ymax);
+        if (edges < 0) break;
+        {
+          const bool sw = e[0].x > e[1].x;
+          long long xx1 = ((sw ? e[1].x : e[0].x) + delta) >> XYS, xx2 = ((sw ? e[0].x : e[1].x) + delta) >> XYS;
+          const long long wy = y - oy;
+          if (y >= 0 && wy >= 0 && wy < H) {
+            xx1 -= ox; xx2 -= ox;
+            for (long long x = xx1 < 0 ? 0 : xx1; x <= xx2 && x < W; ++x) cut[wy * W + x] = 1;
+          }
+        }
+        e[0].x += e[0].dx; e[1].x += e[1].dx;
+      } while (++y <= ymax);
+    }
   }
-  // Circle(center, 1, filled) at both ends
-  const int cxs[2] = {r.x, r.z}, cys[2] = {r.y, r.w};
+  // Circle(center, 1, filled) at both (clipped) ends
+  const long long cxs[2] = {px0, px1}, cys[2] = {py0, py1};
   for (int k = 0; k < 2; ++k) {
-    put_px(cut, W, H, cxs[k], cys[k]); put_px(cut, W, H, cxs[k] - 1, cys[k]); put_px(cut, W, H, cxs[k] + 1, cys[k]);
-    put_px(cut, W, H, cxs[k], cys[k] - 1); put_px(cut, W, H, cxs[k], cys[k] + 1);
+    put_px(cw, cxs[k], cys[k]); put_px(cw, cxs[k] - 1, cys[k]); put_px(cw, cxs[k] + 1, cys[k]);
+    put_px(cw, cxs[k], cys[k] - 1); put_px(cw, cxs[k], cys[k] + 1);
   }
 }
 __global__ void apply_cut_kernel(uint8_t* __restrict__ visible, const uint8_t* __restrict__ cut, int n, const ExState* st) {
@@ -983,9 +1041,9 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   if (!d_explored || !d_nav || !d_frontiers || !d_count || !d_workspace || !d_status || G < 8) { set_error("vlfm_explore_update: bad argument"); return VLFM_E_INVALID; }
   const int L = (int)max_line_len, W0 = 2 * L + 9;
   if (W0 > WIN_MAX) { set_error("vlfm_explore_update: max_line_len %d too large (window %d > %d)", L, W0, WIN_MAX); return VLFM_E_UNSUPPORTED; }
+  // the window is centred on the agent and may hang over the grid edge: cv2 clips the cone and the rays there
+  // (clip_line rules above), cells outside the grid are masked out of the window images
   const int ox = agent_col - L - 4, oy = agent_row - L - 4;
-  if (ox < 0 || oy < 0 || ox + W0 > G || oy + W0 > G) {
-    set_error("vlfm_explore_update: the fog-of-war window leaves the grid (agent too close to the map edge)"); return VLFM_E_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   Ws w;
   carve(&w, (uint8_t*)d_workspace, G);
@@ -998,7 +1056,7 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   int rc = check_cuda(cudaMemcpyAsync(w.verts, hv, sizeof(long long) * 2 * nv, cudaMemcpyHostToDevice, st), "explore: vertex upload");
   if (rc) return rc;
   zero_planes_kernel<<<nblk(pw0 * W0), 256, 0, st>>>(w.tog, w.orb, pw0 * W0);
-  sector_edges_kernel<<<1, 64, 0, st>>>(w.verts, nv, ox, oy, w.tog, w.orb, W0, W0, pw0);
+  sector_edges_kernel<<<1, 64, 0, st>>>(w.verts, nv, ox, oy, G, G, w.tog, w.orb, W0, W0, pw0);
   planes_to_image_kernel<<<nblk(W0, 64), 64, 0, st>>>(w.tog, w.orb, w.cone, W0, W0, pw0, 1, 1, nullptr);
   fog_masks_kernel<<<nblk(wn), 256, 0, st>>>(w.cone, d_nav, G, ox, oy, W0, w.blocked, w.visible);
   // ---- R2/R3/R4: obstacle contours -> rays -> cut
@@ -1007,7 +1065,7 @@ extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_
   simple_vertices_kernel<<<EX_MAXC / 8, 256, 0, st>>>(w.cont, w.chain, w.sv, w.nsv, w.st);
   rays_kernel<<<EX_MAXC / 8, 256, 0, st>>>(w.cont, w.sv, w.nsv, w.rays, w.rays_cap, sx, sy, ox, oy, heading_deg, max_line_len * 1.05, w.st);
   clear_bytes_kernel<<<nblk(wn), 256, 0, st>>>(w.cut, wn);
-  thick_rays_kernel<<<RAYS_CAP / 64, 64, 0, st>>>(w.rays, w.cut, W0, W0, w.st);
+  thick_rays_kernel<<<RAYS_CAP / 64, 64, 0, st>>>(w.rays, w.cut, W0, W0, ox, oy, G, w.st);
   apply_cut_kernel<<<nblk(wn), 256, 0, st>>>(w.visible, w.cut, wn, w.st);
   // ---- R5: contours of the visible area, nearest to the agent, filled
   contours(w, w.visible, W0, W0, st, 1);
@@ -1105,7 +1163,7 @@ extern "C" int vlfm_value_cone_template(double fov, double max_depth, int ppm, d
   int rc = check_cuda(cudaMemcpyAsync(verts, hv, sizeof(long long) * 2 * nv, cudaMemcpyHostToDevice, st), "cone template: vertex upload");
   if (rc) return rc;
   zero_planes_kernel<<<nblk((long)pw * R), 256, 0, st>>>(tog, orb, pw * R);
-  sector_edges_kernel<<<1, 64, 0, st>>>(verts, nv, 0, 0, tog, orb, R, R, pw);
+  sector_edges_kernel<<<1, 64, 0, st>>>(verts, nv, 0, 0, R, R, tog, orb, R, R, pw);
   planes_to_image_kernel<<<nblk(R, 64), 64, 0, st>>>(tog, orb, sector, R, R, pw, 1, 1, nullptr);
   cone_template_kernel<<<nblk((long)R * R), 256, 0, st>>>(sector, d_out, R, fov, min_conf);
   rc = check_cuda(cudaStreamSynchronize(st), "cone template");   // hv is a stack buffer: the upload must finish before returning

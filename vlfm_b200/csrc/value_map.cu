@@ -470,16 +470,17 @@ __global__ void value_mask_unexplored_kernel(int G, int C, const int* __restrict
 }
 
 // pixel_value_within_radius (img_utils.py:213-266), reduction="median".
-// one block per (point, channel); bitonic sort of the <= 1024 candidate values.
+// one block per (point, channel); bitonic sort of the <= CAP candidate values (CAP = 1024: radius <= 15 cells, 4096: <= 31).
+template <int CAP>
 __global__ void __launch_bounds__(256)
 value_disc_median_kernel(int G, int C, const float* __restrict__ valueS, const int* __restrict__ pts,
                          int radius, const uint8_t* __restrict__ disc, double* __restrict__ out) {
-  __shared__ float vals[1024];
+  __shared__ float vals[CAP];
   __shared__ int s_n;
   const int pi = blockIdx.x, ch = blockIdx.y, tid = threadIdx.x;
   const int row = pts[2 * pi], col = pts[2 * pi + 1];
   if (tid == 0) s_n = 0;
-  for (int i = tid; i < 1024; i += 256) vals[i] = INFINITY;
+  for (int i = tid; i < CAP; i += 256) vals[i] = INFINITY;
   __syncthreads();
   const int D = 2 * radius + 1;
   const int r0 = max(0, row - radius), c0 = max(0, col - radius);
@@ -490,15 +491,17 @@ value_disc_median_kernel(int G, int C, const float* __restrict__ valueS, const i
       int rr = i / w, cc = i % w;
       if (disc[rr * D + cc]) {  // disc centred at (radius, radius) of the clipped crop
         float v = valueS[((size_t)(r0 + rr) * G + (c0 + cc)) * C + ch];
-        if (v > 0.f) { int k = atomicAdd(&s_n, 1); if (k < 1024) vals[k] = v; }
+        if (v > 0.f) { int k = atomicAdd(&s_n, 1); if (k < CAP) vals[k] = v; }
       }
     }
   }
   __syncthreads();
-  const int n = min(s_n, 1024);
-  for (int k = 2; k <= 1024; k <<= 1)
+  const int n = min(s_n, CAP);
+  int P = 2;
+  while (P < n) P <<= 1;                      // the unused tail is +inf: sorting the next power of two suffices
+  for (int k = 2; k <= P; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < 1024; i += 256) {
+      for (int i = tid; i < P; i += 256) {
         int ixj = i ^ j;
         if (ixj > i) {
           float a = vals[i], bq = vals[ixj];
@@ -593,12 +596,16 @@ extern "C" int vlfm_value_mask_unexplored(int G, int C, int batch, const int32_t
 extern "C" int vlfm_value_disc_median(int G, int C, int slot, const float* d_value, const int32_t* d_points,
                                       int npoints, int radius, const uint8_t* d_disc, double* d_out,
                                       void* stream) {
-  if (!d_value || !d_points || !d_disc || !d_out || radius < 0 || radius > 15 || C < 1) {
-    set_error("vlfm_value_disc_median: bad argument (radius must be <= 15 cells)"); return VLFM_E_INVALID; }
+  if (!d_value || !d_points || !d_disc || !d_out || radius < 0 || radius > 31 || C < 1) {
+    set_error("vlfm_value_disc_median: bad argument (radius must be <= 31 cells)"); return VLFM_E_INVALID; }
   if (npoints <= 0) return VLFM_OK;
   dim3 g(npoints, C);
-  value_disc_median_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(G, C, d_value + (size_t)slot * G * G * C,
-                                                               d_points, radius, d_disc, d_out);
+  if (radius <= 15)
+    value_disc_median_kernel<1024><<<g, 256, 0, (cudaStream_t)stream>>>(G, C, d_value + (size_t)slot * G * G * C,
+                                                                       d_points, radius, d_disc, d_out);
+  else
+    value_disc_median_kernel<4096><<<g, 256, 0, (cudaStream_t)stream>>>(G, C, d_value + (size_t)slot * G * G * C,
+                                                                       d_points, radius, d_disc, d_out);
   VLFM_CHECK_LAUNCH("value_disc_median_kernel");
   count_launch();
   return VLFM_OK;

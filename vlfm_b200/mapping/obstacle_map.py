@@ -39,6 +39,11 @@ class ObstacleMap(BaseMap):
         kernel_size = self.pixels_per_meter * agent_radius * 2  # :43-46
         self._kernel = int(kernel_size) + (int(kernel_size) % 2 == 0)
         self._nav_valid = False  # before the first obstacle update the reference's navigable map is all 0
+        # cells whose navigable value may have changed since the last explore step, as a grid rectangle (col0, row0, col1, row1):
+        # the union of the obstacle updates' dilation windows.  The reference clears explored cells on non-navigable cells over
+        # the WHOLE grid (:127); outside this rectangle nothing changed, so masking it is identical (several update_map(explore=
+        # False) calls with different cameras followed by one explore call: reality_policies.py:114-138)
+        self._dirty: Optional[tuple] = None
         self._front_cache: Optional[np.ndarray] = np.array([])
         self._pin: Optional[torch.Tensor] = None
         self._pin_tf: Optional[torch.Tensor] = None
@@ -90,7 +95,20 @@ class ObstacleMap(BaseMap):
         super().reset()
         self._obst.zero_(); self._nav.zero_(); self._explored.zero_(); self._status.zero_()
         self._nav_valid = False
+        self._dirty = None
         self._front_cache = np.array([])
+
+    def _mark_dirty(self, tf: np.ndarray, half: int) -> None:
+        g = self.size
+        if not self._nav_valid:                       # first update: the navigable map changes everywhere (0 -> 1)
+            self._dirty = (0, 0, g, g)
+            return
+        col, row = (int(v) for v in self._xy_to_px(np.asarray(tf[:2, 3], dtype=np.float64).reshape(1, 2))[0])
+        r = (col - half, row - half, col + half + 1, row + half + 1)
+        if r[0] < 0 or r[1] < 0 or r[2] > g or r[3] > g:   # near the edge the scatter may wrap (numpy negative indices): whole grid
+            r = (0, 0, g, g)
+        d = self._dirty
+        self._dirty = r if d is None else (min(d[0], r[0]), min(d[1], r[1]), max(d[2], r[2]), max(d[3], r[3]))
 
     def _upload(self, depth: Optional[np.ndarray], tf: np.ndarray) -> None:
         if self._pin_tf is None:
@@ -133,7 +151,7 @@ class ObstacleMap(BaseMap):
                 self._upload(depth, tf_camera_to_episodic)
                 h, w = depth.shape
                 half = int(math.ceil(max_depth * self.pixels_per_meter * math.sqrt(1.0 + (w / 2.0 / fx) ** 2))) + self._kernel // 2 + 2
-                self._last_half = half if self._nav_valid else self.size    # first update: the navigable map changed everywhere
+                self._mark_dirty(tf_camera_to_episodic, half)
                 p = _lib.ObstacleParams(h, w, self.size, self.pixels_per_meter,
                                         float(np.float32(max_depth - min_depth)), float(np.float32(min_depth)),
                                         float(np.float32(max_depth)), float(fx), float(fy),
@@ -173,7 +191,13 @@ class ObstacleMap(BaseMap):
                 from .explore import ExploreEngine
 
                 self._explore_impl = ExploreEngine(self)
-            self._explore_impl.update(tf_camera_to_episodic, max_depth, topdown_fov, getattr(self, "_last_half", 0))
+            nav_half = 0
+            if self._dirty is not None:                # square around the explore pose that covers the dirty rectangle
+                col, row = (int(v) for v in self._xy_to_px(np.asarray(tf_camera_to_episodic[:2, 3], dtype=np.float64).reshape(1, 2))[0])
+                d = self._dirty
+                nav_half = max(col - d[0], d[2] - 1 - col, row - d[1], d[3] - 1 - row, 0)
+                self._dirty = None
+            self._explore_impl.update(tf_camera_to_episodic, max_depth, topdown_fov, nav_half)
             self._front_cache = None
 
     def visualize(self) -> np.ndarray:

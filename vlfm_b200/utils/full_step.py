@@ -1,0 +1,160 @@
+"""The FULL policy step for a batch of environments on one GPU -- GroundingDINO detect + BLIP-2 ITC + ObstacleMap (hole fill,
+scatter, dilate, fog-of-war, frontiers) + ValueMap fuse + frontier scoring -- with per-component CUDA-event times and the
+grid kernels' achieved HBM bandwidth.  Shared by bench.py (BASELINE.json configs[2], [3], [4] slices) and
+scripts/bench_full_step.py.  Reference call sites: base_objectnav_policy.py:153-241 (_cache_observations /
+_get_object_detections), itm_policy.py:191-211, 263-294 (_update_value_map / _sort_frontiers_by_value)."""
+from __future__ import annotations
+
+import time
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+MIN_D, MAX_D, FOV = 0.5, 5.0, float(np.deg2rad(79))
+PROMPT = "Seems like there is a chair ahead."
+CAPTION = "chair . couch . potted plant . bed . toilet . tv ."
+
+
+def grid_bytes(h: int, w: int, g: int, ppm: int, channels: int = 1, max_depth: float = MAX_D) -> Dict[str, float]:
+    """Algorithmic bytes per env-step of the grid path."""
+    r = 2 * int(max_depth * ppm) + 1
+    return {"value": 4.0 * h * w + (12 + 8 * channels) * r * r, "obstacle": 4.0 * h * w + 7.0 * g * g, "R": r}
+
+
+class FullStep:
+    def __init__(self, dev: torch.device, batch: int, h: int, w: int, grid: int, ppm: int, itm, gdino, frames_per_env: int,
+                 seed0: int = 0, streams: int = 8, hole_thresh: int = 100000, bound_m: float = 15.0) -> None:
+        from ..mapping.obstacle_map import ObstacleMap
+        from ..mapping.value_map import ValueMapBatch
+        from .synthetic import focal_from_hfov, trajectory
+
+        self.dev, self.B, self.H, self.W, self.G, self.ppm = dev, batch, h, w, grid, ppm
+        self.itm, self.gd = itm, gdino
+        self.ids = gdino.tokenizer.encode(CAPTION) if gdino is not None else None
+        self.vmb = ValueMapBatch(batch, 1, size=grid, pixels_per_meter=ppm, use_max_confidence=False, device=dev)
+        self.oms = [ObstacleMap(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=hole_thresh, size=grid, pixels_per_meter=ppm, device=dev)
+                    for _ in range(batch)]
+        self.streams = [torch.cuda.Stream(dev) for _ in range(max(1, streams))]
+        self.fx = focal_from_hfov(w)
+        nf = frames_per_env
+        self.frames = [trajectory(seed0 + e, nf, h=h, w=w, bound_m=bound_m, with_rgb=True) for e in range(batch)]
+        # every step's frames wait in page-locked host memory, batched per step (as a vectorised simulator bridge leaves them)
+        self.rgb_pin = torch.empty((nf, batch, h, w, 3), dtype=torch.uint8).pin_memory()
+        self.depth_pin = torch.empty((nf, batch, h, w), dtype=torch.float32).pin_memory()
+        self.tf_pin = torch.empty((nf, batch, 16), dtype=torch.float64).pin_memory()
+        for i in range(nf):
+            for e in range(batch):
+                f = self.frames[e][i]
+                self.rgb_pin[i, e].numpy()[...] = f.rgb
+                self.depth_pin[i, e].numpy()[...] = f.depth
+                self.tf_pin[i, e].numpy()[...] = f.tf.reshape(16)
+                f.depth = self.depth_pin[i, e].numpy()                    # ObstacleMap reads the same page-locked frame
+                f.rgb = None
+        self.rgb_dev, self.depth_dev, self.tf_dev = (torch.empty_like(t[0], device=dev) for t in (self.rgb_pin, self.depth_pin, self.tf_pin))
+        self.names = ["h2d", "gdino", "itc", "obstacle+explore", "value_fuse", "frontier_scoring"]
+        self.acc = {k: 0.0 for k in self.names}
+        self.n_front = 0
+        self.nf = nf
+
+    def step(self, i: int, timed: bool) -> None:
+        i %= self.nf
+        B = self.B
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.names) + 1)]
+        main = torch.cuda.current_stream()
+        ev[0].record()
+        self.rgb_dev.copy_(self.rgb_pin[i], non_blocking=True)
+        self.depth_dev.copy_(self.depth_pin[i], non_blocking=True)
+        self.tf_dev.copy_(self.tf_pin[i], non_blocking=True)
+        ev[1].record()
+        if self.gd is not None:
+            logits, boxes = self.gd.raw_outputs_device(self.rgb_dev, self.ids)
+            keep = logits.max(dim=2)[0] > self.gd.box_threshold    # compaction mask stays on the device
+            _ = keep.sum()
+        ev[2].record()
+        cos = self.itm.cosine_device(self.rgb_dev, PROMPT)
+        ev[3].record()
+        for s in self.streams:
+            s.wait_stream(main)
+        for e in range(B):                                    # independent envs: round-robin over streams
+            with torch.cuda.stream(self.streams[e % len(self.streams)]):
+                self.oms[e].update_map(self.frames[e][i].depth, self.frames[e][i].tf, MIN_D, MAX_D, self.fx, self.fx, FOV)
+        for s in self.streams:
+            main.wait_stream(s)
+        ev[4].record()
+        self.vmb.update(cos.double().view(B, 1), self.depth_dev, self.tf_dev.view(B, 4, 4), MIN_D, MAX_D, FOV)
+        ev[5].record()
+        for e in range(B):                                    # ITMPolicy._sort_frontiers_by_value: D2H of the frontier list + disc medians
+            fr = self.oms[e].frontiers
+            self.n_front += len(fr)
+            if len(fr):
+                px = self.oms[e]._xy_to_px(fr[:, :2])
+                self.vmb.disc_median(e, np.stack([px[:, 1], px[:, 0]], axis=1), int(0.5 * self.ppm))
+        ev[6].record()
+        torch.cuda.synchronize()
+        if timed:
+            for k, nme in enumerate(self.names):
+                self.acc[nme] += ev[k].elapsed_time(ev[k + 1])
+
+    def run(self, steps: int, warmup: int) -> Dict[str, Any]:
+        for i in range(warmup):
+            self.step(i, False)
+        torch.cuda.synchronize()
+        self.n_front = 0
+        self.acc = {k: 0.0 for k in self.names}
+        t0 = time.perf_counter()
+        for i in range(steps):
+            self.step(warmup + i, True)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        comp = {k: v / steps for k, v in self.acc.items()}
+        gb = grid_bytes(self.H, self.W, self.G, self.ppm)
+        return {"env_steps_per_s": self.B * steps / wall, "ms_per_step": 1e3 * wall / steps, "wall_s": wall, "steps": steps, "warmup": warmup,
+                "batch": self.B, "component_ms_per_step": comp, "frontiers_per_env_step": self.n_front / (self.B * steps),
+                "grid_bytes_per_env_step": gb}
+
+    def grid_rooflines(self, hbm_gbs: float, reps: int = 6) -> Dict[str, Any]:
+        """Achieved algorithmic-bytes/s of the grid kernels alone (CUDA events on the launching stream, inputs resident in HBM)."""
+        B = self.B
+        gb = grid_bytes(self.H, self.W, self.G, self.ppm)
+        out: Dict[str, Any] = {}
+        cos = torch.full((B, 1), 0.5, dtype=torch.float64, device=self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            self.vmb.update(cos, self.depth_dev, self.tf_dev.view(B, 4, 4), MIN_D, MAX_D, FOV)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            self.vmb.update(cos, self.depth_dev, self.tf_dev.view(B, 4, 4), MIN_D, MAX_D, FOV)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        ach = gb["value"] * B / (ms * 1e-3) / 1e9
+        out["value_update"] = {"kernels": "value_depth_geom_kernel + value_cone_fuse_kernel", "ms": ms, "envs": B, "bytes_per_env": gb["value"],
+                               "achieved_gbs": ach, "peak_gbs": hbm_gbs, "frac": ach / hbm_gbs, "bound": "hbm"}
+        # obstacle + explore: per-env objects over the stream pool, as in step()
+        i = 0
+        main = torch.cuda.current_stream()
+
+        def obst():
+            for s in self.streams:
+                s.wait_stream(main)
+            for e in range(B):
+                with torch.cuda.stream(self.streams[e % len(self.streams)]):
+                    self.oms[e].update_map(self.frames[e][i].depth, self.frames[e][i].tf, MIN_D, MAX_D, self.fx, self.fx, FOV)
+            for s in self.streams:
+                main.wait_stream(s)
+
+        obst()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            obst()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        ach = gb["obstacle"] * B / (ms * 1e-3) / 1e9
+        out["obstacle_explore"] = {"kernels": "fill_small_holes + obstacle_scatter/dilate + explore (fog-of-war, component, frontiers), incl. H2D of depth",
+                                   "ms": ms, "envs": B, "bytes_per_env": gb["obstacle"], "achieved_gbs": ach, "peak_gbs": hbm_gbs,
+                                   "frac": ach / hbm_gbs, "bound": "hbm (latency-bound border following in practice)"}
+        return out

@@ -79,12 +79,17 @@ def hf_config(d: Blip2Dims):
                        image_text_hidden_size=d.proj)
 
 
-def random_state_dict(d: Blip2Dims, seed: int = 0) -> Dict[str, torch.Tensor]:
+def random_state_dict(d: Blip2Dims, seed: int = 0, outliers: bool = False) -> Dict[str, torch.Tensor]:
     """Seeded fp32 CPU weights under HF names.  Linear weights ~ N(0, 1/sqrt(fan_in)) * 0.8
     (keeps activations O(1) through 39 pre-LN blocks), biases ~ N(0, 0.05),
-    LayerNorm gamma ~ 1 + N(0, 0.05), beta ~ N(0, 0.05)."""
+    LayerNorm gamma ~ 1 + N(0, 0.05), beta ~ N(0, 0.05).
+
+    ``outliers=True`` adds what trained ViT / BERT checkpoints show and plain Gaussians do not: a few LayerNorm channels with
+    gains several times the rest and offsets of order one, and a handful of residual-stream channels carrying "massive
+    activations" (large biases on the block outputs) -- the cases where half-precision operands lose the most."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
+    hot = {}
 
     def lin(name: str, out_f: int, in_f: int, bias: bool = True) -> None:
         sd[name + ".weight"] = torch.randn(out_f, in_f, generator=g) * (0.8 / in_f**0.5)
@@ -94,6 +99,10 @@ def random_state_dict(d: Blip2Dims, seed: int = 0) -> Dict[str, torch.Tensor]:
     def ln(name: str, n: int) -> None:
         sd[name + ".weight"] = 1.0 + torch.randn(n, generator=g) * 0.05
         sd[name + ".bias"] = torch.randn(n, generator=g) * 0.05
+        if outliers:
+            idx = hot.setdefault(n, torch.randperm(n, generator=g)[:6])
+            sd[name + ".weight"][idx] *= torch.tensor([6.0, 5.0, 4.0, 3.0, 0.2, 0.1])
+            sd[name + ".bias"][idx[:3]] += torch.tensor([1.0, -1.5, 0.7])
 
     D, F = d.v_hidden, d.v_inter
     sd["query_tokens"] = torch.randn(1, d.queries, d.q_hidden, generator=g) * 0.5
@@ -129,6 +138,12 @@ def random_state_dict(d: Blip2Dims, seed: int = 0) -> Dict[str, torch.Tensor]:
         lin(p + "intermediate_query.dense", I, H)
         lin(p + "output_query.dense", H, I)
         ln(p + "output_query.LayerNorm", H)
+    if outliers:     # massive activations: two residual channels of the ViT and of the Q-Former get a large constant push mid-network
+        for i in (d.v_layers // 3, 2 * d.v_layers // 3):
+            b = sd[f"vision_model.encoder.layers.{i}.mlp.fc2.bias"]
+            b[hot[D][:2]] += torch.tensor([25.0, -18.0])
+        b = sd[f"qformer.encoder.layer.{d.q_layers // 2}.output_query.dense.bias"]
+        b[hot[H][:2]] += torch.tensor([6.0, -4.0])
     lin("vision_projection", d.proj, H)
     lin("text_projection", d.proj, H)
     lin("itm_head", 2, H)

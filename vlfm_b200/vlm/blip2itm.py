@@ -58,6 +58,26 @@ class WordPieceTokenizer:
         return ids + [self.vocab["[SEP]"]]
 
 
+class WordPieceCaptionTokenizer(WordPieceTokenizer):
+    """encode / decode pair GroundingDINO.predict needs (bert-base-uncased ids <-> words)."""
+
+    def __init__(self, vocab_path: str, max_len: int = 256):
+        super().__init__(vocab_path, max_len)
+        self.inv = {i: t for t, i in self.vocab.items()}
+
+    def encode(self, caption: str) -> List[int]:
+        return self(caption)
+
+    def decode(self, ids: Sequence[int]) -> str:
+        out = ""
+        for i in ids:
+            t = self.inv.get(int(i), "[UNK]")
+            if t in ("[CLS]", "[SEP]", "[PAD]"):
+                continue
+            out = out + t[2:] if t.startswith("##") else (out + " " + t if out else t)
+        return out
+
+
 class HashTokenizer:
     """SYNTHETIC stand-in used when no bert-base-uncased vocab is on disk (there is none
     offline): [CLS]=101, one crc32-hashed id per word, [SEP]=102.  Scores are then only
@@ -77,20 +97,40 @@ class BLIP2ITM:
 
     def __init__(self, name: str = "blip2_image_text_matching", model_type: str = "pretrain", device: Optional[Any] = None,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, dims: Optional[Blip2Dims] = None,
-                 tokenizer: Optional[Any] = None, max_batch: int = 1, seed: int = 0) -> None:
+                 tokenizer: Optional[Any] = None, max_batch: int = 1, seed: int = 0, synthetic: bool = False) -> None:
+        """``name`` / ``model_type`` are lavis registry keys (blip2itm.py:29-34); the only pair this engine implements is the
+        reference's default ("blip2_image_text_matching", "pretrain") = ViT-g/14 + 12-layer Q-Former, anything else raises.
+        Weights: ``state_dict`` (HF ``Blip2ForImageTextRetrieval`` names or lavis names -- converted by
+        ``blip2_weights.convert_lavis_state_dict``) or the file ``VLFM_BLIP2_WEIGHTS``.  Without either the constructor
+        RAISES unless ``synthetic=True`` (seeded random weights: tests / benchmarks only)."""
+        if (name, model_type) != ("blip2_image_text_matching", "pretrain"):
+            raise ValueError(f"BLIP2ITM: only ('blip2_image_text_matching', 'pretrain') is implemented, got ({name!r}, {model_type!r})")
         if device is None:
             device = torch.device("cuda")
         self.device = device
         self.dims = dims or Blip2Dims()
+        from .blip2_weights import load_checkpoint
+
+        real = False
         if state_dict is None:
             path = os.environ.get("VLFM_BLIP2_WEIGHTS", "")
             if path:
-                state_dict = torch.load(path, map_location="cpu")
-            else:  # no checkpoint offline: seeded synthetic weights of the right architecture
+                state_dict = load_checkpoint(path, self.dims)
+                real = True
+            elif synthetic:   # no checkpoint offline: seeded synthetic weights of the right architecture
                 state_dict = random_state_dict(self.dims, seed)
+            else:
+                raise FileNotFoundError("BLIP2ITM: no checkpoint configured (VLFM_BLIP2_WEIGHTS unset, no state_dict). "
+                                        "Pass synthetic=True to run on seeded random weights (tests / benchmarks only).")
         if tokenizer is None:
             vocab = os.environ.get("VLFM_BERT_VOCAB", "")
-            tokenizer = WordPieceTokenizer(vocab) if vocab else HashTokenizer(self.dims.vocab)
+            if vocab:
+                tokenizer = WordPieceTokenizer(vocab)
+            elif real:
+                raise FileNotFoundError("BLIP2ITM: real weights need the bert-base-uncased vocabulary: set VLFM_BERT_VOCAB=<vocab.txt> "
+                                        "or pass tokenizer=")
+            else:
+                tokenizer = HashTokenizer(self.dims.vocab)
         self.tokenizer = tokenizer
         self.engine = Blip2ITCEngine(self.dims, state_dict, device=device, max_batch=max_batch)
         self._text_cache: Dict[str, torch.Tensor] = {}
@@ -136,7 +176,7 @@ class BLIP2ITMClient:
     def __init__(self, port: int = 12182, model: Optional[BLIP2ITM] = None):
         if model is None:
             if "default" not in _SHARED:
-                _SHARED["default"] = BLIP2ITM()
+                _SHARED["default"] = BLIP2ITM(synthetic=os.environ.get("VLFM_SYNTHETIC_WEIGHTS", "") == "1")
             model = _SHARED["default"]
         self.model = model
 

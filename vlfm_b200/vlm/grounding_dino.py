@@ -1,11 +1,10 @@
 """GroundingDINO behind the reference's class surface (vlfm/vlm/grounding_dino.py:23-85).
 
-The Swin-T backbone -- the dense contraction north_star names -- runs on the hand-written
-sm_100a kernels (``SwinBackboneEngine``).  The rest of the detector (BERT text encoder,
-feature enhancer, deformable encoder/decoder, heads) is not on the hand-written path yet
-(SURVEY.md section 8f rank 1): it runs as the architecture-equivalent HF
-``GroundingDinoForObjectDetection`` PyTorch modules on the same GPU, fed with our backbone
-feature maps.  Post-processing restates groundingdino.util.inference.predict.
+The Swin-T backbone -- the dense contraction north_star names -- runs on the hand-written sm_100a kernels
+(``SwinBackboneEngine``); every nn.Linear, the deformable encoder layers, the image<->text fusion layers and the decoder layers
+run on the library too (``gdino_accel``: tcgen05 GEMM, fused multi-scale deformable sampling, bi-attention).  The module graph
+that sequences them is HF's ``GroundingDinoForObjectDetection`` (architecture-equivalent to groundingdino@eeba084); what is
+still PyTorch glue is listed in DESIGN.md section 7.  Post-processing restates groundingdino.util.inference.predict.
 """
 from __future__ import annotations
 
@@ -67,18 +66,36 @@ class GroundingDINO:
     def __init__(self, config_path: str = GROUNDING_DINO_CONFIG, weights_path: str = GROUNDING_DINO_WEIGHTS,
                  caption: str = CLASSES, box_threshold: float = 0.35, text_threshold: float = 0.25,
                  device: torch.device = torch.device("cuda"), state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 tokenizer: Optional[Any] = None, seed: int = 0):
+                 tokenizer: Optional[Any] = None, seed: int = 0, synthetic: bool = False):
+        """``weights_path`` (grounding_dino.py:33 ``load_model(config_path, weights_path)``) is honoured: a groundingdino
+        ``.pth`` (original key names, converted by ``gdino_weights.convert_groundingdino_state_dict``) or an HF-layout
+        state dict; ``VLFM_GDINO_WEIGHTS`` overrides it.  ``config_path`` selects nothing here: the only architecture built
+        is GroundingDINO_SwinT_OGC (the reference's default and the one its weights file is for).  Without a checkpoint
+        the constructor RAISES unless ``synthetic=True`` (seeded random weights: tests / benchmarks only) -- a detector
+        that silently runs on random weights returns meaningless boxes."""
         from transformers import GroundingDinoConfig, GroundingDinoForObjectDetection
 
+        from .gdino_weights import load_checkpoint
+
         cfg = GroundingDinoConfig()
+        real = False          # weights read from a checkpoint file (then the real vocabulary is mandatory)
         if state_dict is None:
-            path = os.environ.get("VLFM_GDINO_WEIGHTS", "")
+            path = os.environ.get("VLFM_GDINO_WEIGHTS", "") or (weights_path if weights_path and os.path.exists(weights_path) else "")
             if path:
-                state_dict = torch.load(path, map_location="cpu")
+                state_dict = load_checkpoint(path)
+                real = True
+            elif not synthetic:
+                raise FileNotFoundError(
+                    f"GroundingDINO: no checkpoint at weights_path={weights_path!r} and VLFM_GDINO_WEIGHTS is unset. "
+                    "Pass synthetic=True to run on seeded random weights (tests / benchmarks only).")
         torch.manual_seed(seed)
-        model = GroundingDinoForObjectDetection(cfg)  # random init when no checkpoint (there is none offline)
+        model = GroundingDinoForObjectDetection(cfg)
         if state_dict is not None:
-            model.load_state_dict(state_dict, strict=False)
+            missing, unexpected = model.load_state_dict(state_dict, strict=False)
+            missing = [k for k in missing if "position_ids" not in k]
+            if missing or unexpected:      # a checkpoint that does not cover the model is an error, never a silent partial load
+                raise KeyError(f"GroundingDINO checkpoint does not match the model: {len(missing)} missing keys (e.g. {missing[:4]}), "
+                               f"{len(unexpected)} unexpected keys (e.g. {list(unexpected)[:4]})")
         sd = model.state_dict()
         self.device = device
         self.backbone = SwinBackboneEngine(sd, prefix=BACKBONE_PREFIX, embed_dim=cfg.backbone_config.embed_dim,
@@ -93,7 +110,23 @@ class GroundingDINO:
         self.caption = caption
         self.box_threshold = box_threshold
         self.text_threshold = text_threshold
-        self.tokenizer = tokenizer or SimpleCaptionTokenizer(cfg.text_config.vocab_size)
+        if tokenizer is None:
+            vocab = os.environ.get("VLFM_BERT_VOCAB", "")
+            if vocab:
+                from .blip2itm import WordPieceCaptionTokenizer
+
+                tokenizer = WordPieceCaptionTokenizer(vocab)
+            elif real and not synthetic:
+                raise FileNotFoundError("GroundingDINO: real weights need the bert-base-uncased vocabulary: set VLFM_BERT_VOCAB=<vocab.txt> "
+                                        "or pass tokenizer= (the crc32 stand-in only makes sense with synthetic weights)")
+            else:
+                if not synthetic:
+                    import warnings
+
+                    warnings.warn("GroundingDINO: in-memory state_dict without tokenizer= / VLFM_BERT_VOCAB: using the crc32 stand-in "
+                                  "tokenizer, which is only meaningful with synthetic weights")
+                tokenizer = SimpleCaptionTokenizer(cfg.text_config.vocab_size)
+        self.tokenizer = tokenizer
         self._pin: Optional[torch.Tensor] = None
         self._dev: Optional[torch.Tensor] = None
         self._static: Dict[Any, Dict[str, Any]] = {}
@@ -191,7 +224,7 @@ class GroundingDINOClient:
     def __init__(self, port: int = 12181, model: Optional[GroundingDINO] = None):
         if model is None:
             if "default" not in _SHARED:
-                _SHARED["default"] = GroundingDINO()
+                _SHARED["default"] = GroundingDINO(synthetic=os.environ.get("VLFM_SYNTHETIC_WEIGHTS", "") == "1")
             model = _SHARED["default"]
         self.model = model
 
