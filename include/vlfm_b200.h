@@ -246,11 +246,28 @@ int vlfm_cast_addpos_f16(const float* d_x, const float* d_pos, void* d_out_x16, 
  * rad2deg(wrap(yaw + pi/2)); fov_deg = rad2deg(topdown_fov); max_line_len = max_depth*ppm;
  * area_thresh_px = area_thresh*ppm^2; nav_half = half-size of the window in which the navigable map changed.
  * d_frontiers [4096,2] float64 (x=col, y=row), d_count int32, d_status int32 (non-zero: a scratch buffer overflowed).
- * Fails (VLFM_E_UNSUPPORTED) when the fog-of-war window would leave the grid.                                  */
+ * The agent may be anywhere: near the map edge the cone and the occlusion rays are clipped with cv2's own rules
+ * (clipLine before every line walk, PolyEdges from clipped end points, thick segments clipped to the grid + 2 px). */
 int vlfm_explore_workspace_bytes(int G, size_t* bytes);
 int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_nav, int agent_col, int agent_row, double heading_deg,
                         double fov_deg, double max_line_len, double area_thresh_px, int nav_half, double* d_frontiers,
                         int32_t* d_count, void* d_workspace, int32_t* d_status, void* stream);
+
+/* -------------------------------------------------------- object point clouds ---- */
+/* Replaces ObjectPointCloudMap._extract_object_cloud (vlfm/mapping/object_point_cloud_map.py:143-163) up to the random
+ * subsample: cv2.erode(mask*255, None, iterations=k) (:153-154), depth 0 -> 1 -> metres in float32 (:156-158),
+ * get_point_cloud (vlfm/utils/geometry_utils.py:216-236): d_points [cap,3] float64 (z, -x, -y) in np.where (row-major)
+ * order, *d_count = number of mask pixels after the erosion (may exceed cap).  d_scratch >= H*W + 8*H + 512 bytes.  */
+int vlfm_object_cloud_extract(const float* d_depth, const uint8_t* d_mask, int H, int W, int erosion_iterations,
+                              float depth_scale, float depth_offset, double fx, double fy, double* d_points, int cap,
+                              int32_t* d_count, void* d_scratch, size_t scratch_bytes, void* stream);
+/* Replaces open3d_dbscan_filtering (:192-219; Open3D cluster_dbscan(eps, min_points), largest non-noise cluster, input
+ * order; spec: oracle/object_map_oracle.py::dbscan_labels).  d_gather (int32[n]) or NULL: optional index list applied to
+ * d_points first (the host's np.random.choice subsample, :246-266), staged in d_gathered [n,3].  n <= 65535.        */
+int vlfm_dbscan_workspace_bytes(int n, size_t* bytes);
+int vlfm_dbscan_largest_cluster(const double* d_points, const int32_t* d_gather, int n, double eps, int min_points,
+                                double* d_gathered, double* d_out, int32_t* d_out_count, void* d_workspace,
+                                size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

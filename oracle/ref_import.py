@@ -69,3 +69,38 @@ def img_utils():
     import vlfm.utils.img_utils as g  # type: ignore
 
     return g
+
+
+def object_map_module():
+    """vlfm.mapping.object_point_cloud_map imports ``open3d`` (absent offline).  A stub module is injected whose
+    ``PointCloud.cluster_dbscan`` is scikit-learn's DBSCAN (an independent implementation of the same published algorithm with
+    the same sequential cluster numbering), so the reference's own code runs unmodified around it."""
+    _ensure_path()
+    if "open3d" not in sys.modules:
+        import numpy as np
+
+        o3d = types.ModuleType("open3d")
+        geometry = types.ModuleType("open3d.geometry")
+        utility = types.ModuleType("open3d.utility")
+
+        class PointCloud:
+            def __init__(self):
+                self.points = None
+
+            def cluster_dbscan(self, eps, min_points, print_progress=False):
+                from sklearn.cluster import DBSCAN
+
+                pts = np.asarray(self.points, dtype=np.float64)
+                if len(pts) == 0:
+                    return []
+                return DBSCAN(eps=eps, min_samples=min_points, algorithm="brute").fit(pts).labels_.tolist()
+
+        geometry.PointCloud = PointCloud
+        utility.Vector3dVector = lambda a: np.asarray(a, dtype=np.float64)
+        o3d.geometry, o3d.utility = geometry, utility
+        sys.modules["open3d"] = o3d
+        sys.modules["open3d.geometry"] = geometry
+        sys.modules["open3d.utility"] = utility
+    import vlfm.mapping.object_point_cloud_map as m  # type: ignore
+
+    return m

@@ -68,6 +68,10 @@ _SIGNATURES = {
     "vlfm_explore_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_explore_update": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P]),
     "vlfm_itc_head": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "vlfm_object_cloud_extract": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_double, C.c_double, _P, C.c_int, _P, _P,
+                                            C.c_size_t, _P]),
+    "vlfm_dbscan_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    "vlfm_dbscan_largest_cluster": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
 }
 
 _lib = None

@@ -91,3 +91,25 @@ def trajectory(seed: int, steps: int, h: int = 480, w: int = 640, holes: bool = 
         rgb = make_rgb(rng, h, w) if with_rgb else np.zeros((0, 0, 3), np.uint8)
         frames.append(Frame(depth, rgb, tf_from_pose(x, y, CAMERA_HEIGHT, yaw), (x, y), yaw))
     return frames
+
+
+def make_object_mask(rng: np.random.Generator, h: int, w: int, side: str = "any") -> np.ndarray:
+    """uint8 0/1 mask of a blob-shaped detection (what MobileSAM hands to ObjectPointCloudMap.update_map,
+    base_objectnav_policy.py:311-346): an ellipse with a ragged rim plus a few stray specks (removed by the erosion).
+    ``side``: "left" / "right" put the whole blob in an outer third of the image (the too_offset case)."""
+    cy = int(rng.integers(int(0.3 * h), int(0.8 * h)))
+    ry, rx = int(rng.integers(max(6, h // 12), max(8, h // 4))), int(rng.integers(max(6, w // 16), max(8, w // 6)))
+    if side == "left":
+        rx = min(rx, w // 8); cx = int(rng.integers(rx // 2, max(rx // 2 + 1, w // 3 - rx - 1)))
+    elif side == "right":
+        rx = min(rx, w // 8); cx = int(rng.integers(2 * (w // 3) + rx + 1, w - 1))
+    else:
+        cx = int(rng.integers(int(0.3 * w), int(0.7 * w)))
+    yy, xx = np.mgrid[0:h, 0:w]
+    ang = np.arctan2(yy - cy, xx - cx)
+    rim = 1.0 + 0.12 * np.sin(5 * ang + rng.uniform(0, 6)) + 0.06 * np.sin(11 * ang + rng.uniform(0, 6))
+    m = (((xx - cx) / (rx * rim)) ** 2 + ((yy - cy) / (ry * rim)) ** 2 <= 1.0)
+    for _ in range(int(rng.integers(2, 8))):
+        y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+        m[y:y + 2, x:x + 2] = True
+    return m.astype(np.uint8)

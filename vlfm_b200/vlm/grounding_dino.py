@@ -139,6 +139,11 @@ class GroundingDINO:
         self._features.maps = self.backbone.forward(st["img"])
         out = self.model(pixel_values=st["dummy"], input_ids=st["ids"], token_type_ids=st["tt"], attention_mask=st["am"], pixel_mask=st["pm"])
         st["logits"], st["boxes"] = out.logits.sigmoid(), out.pred_boxes
+        # a captured graph reads the cached text-tower output by ADDRESS: this entry owns a reference, so evicting the caption
+        # from the text cache (FIFO, 8 entries) can never free memory a live graph replays from
+        tb = self.model.model.text_backbone
+        if hasattr(tb, "cache"):
+            st["text_ref"] = tb.cache.get(tb.key)
 
     @torch.inference_mode()
     def raw_outputs_device(self, images: torch.Tensor, input_ids: List[int]):

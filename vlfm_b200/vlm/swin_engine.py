@@ -110,6 +110,11 @@ class SwinBackboneEngine:
             feats: List[torch.Tensor] = []
             cur, other = "x", "x2"
             for s, stage in enumerate(self.stages):
+                if min(h, w) <= 7:
+                    # HF's Swin (set_shift_and_window_size) drops the shift and shrinks the window when a stage's map is not larger
+                    # than the 7x7 window; that variant is not built: refuse instead of silently computing something else
+                    raise _lib.VlfmError(f"Swin backbone: stage {s + 1} feature map {h}x{w} is not larger than the 7x7 window "
+                                         f"(image {H}x{W} too small; the minimum side is 225 px)")
                 n = B * h * w
                 x = flat(bufs[cur], n, C)
                 xn, qkv, ao, hh = flat(bufs["xn"], n, C), flat(bufs["qkv"], n, 3 * C), flat(bufs["ao"], n, C), flat(bufs["h"], n, 4 * C)
