@@ -104,6 +104,10 @@ int vlfm_value_mask_unexplored(int G, int C, int batch, const int32_t* d_slot, f
 int vlfm_value_disc_median(int G, int C, int slot, const float* d_value, const int32_t* d_points,
                            int npoints, int radius, const uint8_t* d_disc, double* d_out,
                            void* stream);
+/* The same for the frontiers of MANY environments in one launch: d_points_srl [npoints,3] int32 = (slot, row, col),
+ * d_value [nslots,G,G,C]; d_out [npoints,C].  (ITMPolicy._sort_frontiers_by_value, itm_policy.py:263-294, per env.) */
+int vlfm_value_disc_median_batch(int G, int C, const float* d_value, const int32_t* d_points_srl, int npoints, int radius,
+                                 const uint8_t* d_disc, double* d_out, void* stream);
 
 /* --------------------------------------------------------------- obstacle map ---- */
 /* Replaces ObstacleMap.update_map obstacle half (vlfm/mapping/obstacle_map.py:86-109):
@@ -252,6 +256,34 @@ int vlfm_explore_workspace_bytes(int G, size_t* bytes);
 int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_nav, int agent_col, int agent_row, double heading_deg,
                         double fov_deg, double max_line_len, double area_thresh_px, int nav_half, double* d_frontiers,
                         int32_t* d_count, void* d_workspace, int32_t* d_status, void* stream);
+
+/* The same step for a BATCH of environments in one launch sequence (every kernel runs with gridDim.y = batch).
+ * frame = {col0, row0, col1, row1}: the grid rectangle ("S frame") in which the whole-grid operations of the reference
+ * (explored &= navigable, component selection, frontier search) are carried out.  It must contain every cell any obstacle /
+ * explore update of the episode has touched plus a margin of >= 8 cells, and each side must either be a grid edge or lie
+ * >= ceil(area_thresh_px / (G - 1)) + 2 cells inside it: outside the frame explored == 0 and navigable == 1 then, which
+ * makes the restriction exact.  {0, 0, G, G} is always valid.                                  */
+typedef struct {
+  int32_t slot;                 /* index of this environment's grids in d_explored / d_nav [nslots, G, G] */
+  int32_t agent_col, agent_row;
+  int32_t frame[4];
+  int32_t pad;
+  double heading_deg, fov_deg, max_line_len, area_thresh_px;
+} VlfmExploreEnv;
+size_t vlfm_explore_env_record_bytes(void);   /* bytes of page-locked staging per environment (h_pinned below) */
+int vlfm_explore_batch_workspace_bytes(int G, int batch, size_t* bytes);
+/* h_envs: host array [batch].  d_frontiers [batch,4096,2] float64, d_count / d_status [batch] int32 (call order).
+ * h_pinned (optional, page-locked, >= batch * vlfm_explore_env_record_bytes()): staging for the per-environment device
+ * records; it must not be reused before the copy issued by this call has executed.  Without it the records are copied
+ * from pageable memory, which makes cudaMemcpyAsync wait for the stream.                                                 */
+int vlfm_explore_update_batch(int G, int batch, const VlfmExploreEnv* h_envs, uint8_t* d_explored, const uint8_t* d_nav,
+                              double* d_frontiers, int32_t* d_count, int32_t* d_status, void* d_workspace,
+                              size_t workspace_bytes, void* h_pinned, size_t h_pinned_bytes, void* stream);
+/* fill_small_holes for a batch of depth images [batch,H,W] -> d_filled [batch,H,W]; d_status [batch] sticky overflow flags. */
+int vlfm_holes_batch_workspace_bytes(int H, int W, int batch, size_t* bytes);
+int vlfm_fill_small_holes_batch(const float* d_depth, int H, int W, int batch, double area_thresh, uint8_t* d_filled,
+                                void* d_workspace, size_t workspace_bytes, int32_t* d_status, void* h_pinned,
+                                size_t h_pinned_bytes, void* stream);
 
 /* -------------------------------------------------------- object point clouds ---- */
 /* Replaces ObjectPointCloudMap._extract_object_cloud (vlfm/mapping/object_point_cloud_map.py:143-163) up to the random

@@ -35,6 +35,14 @@ class ObstacleParams(C.Structure):
     ]
 
 
+class ExploreEnv(C.Structure):
+    """VlfmExploreEnv (include/vlfm_b200.h)"""
+    _fields_ = [
+        ("slot", C.c_int32), ("agent_col", C.c_int32), ("agent_row", C.c_int32), ("frame", C.c_int32 * 4), ("pad", C.c_int32),
+        ("heading_deg", C.c_double), ("fov_deg", C.c_double), ("max_line_len", C.c_double), ("area_thresh_px", C.c_double),
+    ]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "vlfm_last_error": (C.c_char_p, []),
@@ -45,6 +53,7 @@ _SIGNATURES = {
     "vlfm_value_update": (C.c_int, [C.POINTER(ValueParams), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vlfm_value_mask_unexplored": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "vlfm_value_disc_median": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "vlfm_value_disc_median_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "vlfm_obstacle_update": (C.c_int, [C.POINTER(ObstacleParams), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vlfm_value_cone_template": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_double, _P, _P, C.c_size_t, _P]),
     "vlfm_msda_forward": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
@@ -67,6 +76,11 @@ _SIGNATURES = {
     "vlfm_swin_patch_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vlfm_explore_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_explore_update": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _P, _P, _P, _P, _P]),
+    "vlfm_explore_env_record_bytes": (C.c_size_t, []),
+    "vlfm_explore_batch_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "vlfm_explore_update_batch": (C.c_int, [C.c_int, C.c_int, C.POINTER(ExploreEnv), _P, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "vlfm_holes_batch_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "vlfm_fill_small_holes_batch": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, C.c_size_t, _P, _P, C.c_size_t, _P]),
     "vlfm_itc_head": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vlfm_object_cloud_extract": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_double, C.c_double, _P, C.c_int, _P, _P,
                                             C.c_size_t, _P]),

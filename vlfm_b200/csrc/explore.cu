@@ -1,34 +1,47 @@
 // Explore half of the obstacle map on the GPU (sm_100a): fog-of-war, explored-area component selection,
-// frontier waypoints.
+// frontier waypoints -- for a BATCH of environments per call.
 //
 // Reference: vlfm/mapping/obstacle_map.py:114-169 and the two `frontier_exploration` functions it calls
 // (reveal_fog_of_war, detect_frontier_waypoints; third-party, absent from the reference tree).  The SPEC these
 // kernels follow step by step is oracle/explore_oracle.py (numpy backend) with oracle/contours.py,
 // oracle/cv_draw.py and oracle/cv_prims.py -- restatements of the OpenCV primitives pinned against cv2.
 //
+// Batching: every kernel runs with gridDim.y = environments of the call and reads its environment's record (ExEnv: image
+// pointers, frame geometry, pose scalars) from device memory; one call = one launch SEQUENCE for all environments.
+//
+// Frames.  The fog-of-war runs in a (2L+9)^2 WINDOW around the agent (L = max_depth*ppm), which may hang over the grid edge
+// (cv2's clipping rules are reproduced; cells outside the grid are masked).  Component selection and the frontier search --
+// full-grid operations in the reference -- run in the S-FRAME: a grid rectangle that contains every cell the explore / obstacle
+// updates of this episode have touched plus a margin; outside it explored == 0 and navigable == 1, which makes the restriction
+// exact: label arrays and masks cover the S-frame, not G^2 cells.
+//
 // Building blocks
 //   ccl_*            label-equivalence connected components (union-find, atomicMin): 8-connected foreground
 //                    and 4-connected background; root = raster-first pixel of the component.
 //   collect_roots    cv2.findContours(RETR_EXTERNAL): outer borders of the components whose west background
 //                    region is the outer background, in REVERSE raster order of their first pixels.
-//   trace_kernel     Suzuki-Abe border following (one thread per contour; borders are short), CHAIN_APPROX_NONE
+//   trace_kernel     Suzuki-Abe border following (one thread per contour), CHAIN_APPROX_NONE
 //                    chain + bounding box; CHAIN_APPROX_SIMPLE vertices = direction changes of the chain.
-//   fill_chain_*     cv2.drawContours(..., -1) of a traced chain: outline + even-odd scan conversion as XOR toggles
+//   chain_edges      cv2.drawContours(..., -1) of a traced chain: outline + even-odd scan conversion as XOR toggles
 //                    + per-row prefix XOR (every chain edge is a unit step, so intercepts are exact).
-//   sector_fill      cv2.ellipse filled sector: 16.16 polygon from the host (integer-degree ellipse2Poly), same
-//                    scan conversion with fractional columns.
+//   sector_edges     cv2.ellipse filled sector: 16.16 polygon from the host (integer-degree ellipse2Poly), same
+//                    scan conversion with fractional columns, PolyEdges from clipped end points at the grid edge.
 //   rays / thick     occlusion rays: cv2.polylines thickness 2 = FillConvexPoly rectangle (Line2 outline + two-edge
-//                    scan) + radius-1 discs.
+//                    scan) + radius-1 discs, clipped like cv2 (grid + 2 px for the centre line, grid for Line2).
 //   frontier_kernel  contour split at cells whose 3x3 blurred unexplored mask is 0, arc-length midpoints.
 #include <math.h>
+#include <string.h>
+
+#include <vector>
 
 #include "common.cuh"
 
 namespace vlfm {
 
-constexpr int EX_MAXC = 8192;      // contours per image
+constexpr int EX_MAXC = 8192;      // contours per image (explore); fill_small_holes uses HOLES_MAXC
 constexpr int XYS = 16;
 constexpr long long XYONE = 1ll << XYS;
+constexpr int MAXV = 64;           // sector polygon vertices
 
 struct Contour { int start, off, len, x0, y0, x1, y1, ed; };   // start pixel, chain offset/length, bbox, entry direction (0 = west: outer border, 4 = east: hole border)
 
@@ -43,6 +56,42 @@ struct ExState {
   int overflow;
   int pad;
 };
+
+enum { IMG_BLOCKED = 0, IMG_VISIBLE = 1, IMG_EXS = 2, IMG_UNEXP = 3, IMG_EX2 = 4 };
+enum { FRAME_WIN = 0, FRAME_S = 1 };
+
+// one environment of a call (device memory)
+struct ExEnv {
+  uint8_t *cone, *blocked, *visible, *cut, *newexp;     // window frame [W0 * W0]
+  uint8_t *exS, *navS, *grown, *unexp, *ex2;            // S frame [Sw * Sh]
+  uint8_t *outer, *hashole, *nbm, *flags;               // per-label flags / 8-neighbour masks of the image being processed; bad flags per chain point
+  int *Lfg, *Lbg, *which, *nsv;
+  Contour* cont; int2 *chain, *sv; int4* rays; double* dist; uint32_t *tog, *orb; ExState* st;
+  uint8_t* explored; const uint8_t* nav;                // this environment's [G, G] grids
+  double* frontiers; int* out_count; int* out_status;
+  const float* depth; uint8_t* filled;                  // fill_small_holes: depth image in, byte mask out
+  int G, maxc, chain_cap, rays_cap, maxf;
+  int ox, oy, W0, sx, sy;                               // window origin (grid coordinates), side, agent in window coordinates
+  int fx0, fy0, Sw, Sh;                                 // S frame origin (grid coordinates) and size
+  int ax, ay;                                           // agent cell (col, row), grid coordinates
+  int ext_l, ext_t, ext_r, ext_b;                       // that edge of the S frame is NOT a grid edge: the exterior continues beyond it
+  int nv, pad0;
+  double heading_deg, ray_len, area_thresh;
+  long long verts[2 * MAXV];
+};
+
+struct View { uint8_t* p; int W, H; };
+__device__ __forceinline__ View view(const ExEnv& E, int id) {
+  View v;
+  switch (id) {
+    case IMG_BLOCKED: v.p = E.blocked; v.W = E.W0; v.H = E.W0; break;
+    case IMG_VISIBLE: v.p = E.visible; v.W = E.W0; v.H = E.W0; break;
+    case IMG_EXS: v.p = E.exS; v.W = E.Sw; v.H = E.Sh; break;
+    case IMG_UNEXP: v.p = E.unexp; v.W = E.Sw; v.H = E.Sh; break;
+    default: v.p = E.ex2; v.W = E.Sw; v.H = E.Sh; break;
+  }
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------- CCL ----
 __device__ __forceinline__ int uf_find(int* L, int i) {
@@ -63,19 +112,24 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
+
 // init: every pixel points at the first pixel of its horizontal run, for the foreground (8-connected) and the background
 // (4-connected) label arrays at once, so that the union phase only has to stitch runs of adjacent rows.  One warp per
-// row, 32 cells per ballot.  Block 0 also resets
-// the per-image bookkeeping.
+// row, 32 cells per ballot.  Block 0 also resets the per-image bookkeeping.
 __global__ void __launch_bounds__(256)
-ccl_init2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __restrict__ Lbg, int W, int H, ExState* st, int keep_fog) {
+ccl_init2_kernel(const ExEnv* __restrict__ envs, int img, int keep_fog) {
+  const ExEnv& E = envs[blockIdx.y];
+  const View v = view(E, img);
+  ExState* st = E.st;
+  int* Lfg = E.Lfg; int* Lbg = E.Lbg;
+  const int W = v.W, H = v.H;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->n_cont = 0; st->cursor = 0; st->n_rays = 0; st->chosen = -1;
     if (!keep_fog) { st->skip_fog = 0; st->overflow = 0; st->n_front = 0; }
   }
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < H; y += gridDim.x * wpb) {
-    const uint8_t* row = img + (size_t)y * W;
+    const uint8_t* row = v.p + (size_t)y * W;
     const int base = y * W;
     int carry_fg = -1, carry_bg = -1;                 // column where a run that reaches the chunk boundary started
     const unsigned below = (1u << lane) - 1;
@@ -95,9 +149,13 @@ ccl_init2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __
   }
 }
 // stitch: a pixel unions with the row above only where a NEW overlap between runs begins; also clears the per-label flags
-__global__ void ccl_merge2_kernel(const uint8_t* __restrict__ img, int* __restrict__ Lfg, int* __restrict__ Lbg, uint8_t* __restrict__ outer,
-                                  uint8_t* __restrict__ hashole, uint8_t* __restrict__ nbm, int W, int H) {
-  const int n = W * H;
+__global__ void ccl_merge2_kernel(const ExEnv* __restrict__ envs, int id, int want_hashole) {
+  const ExEnv& E = envs[blockIdx.y];
+  const View v = view(E, id);
+  const uint8_t* __restrict__ img = v.p;
+  int* Lfg = E.Lfg; int* Lbg = E.Lbg;
+  uint8_t* outer = E.outer; uint8_t* hashole = want_hashole ? E.hashole : nullptr; uint8_t* nbm = E.nbm;
+  const int W = v.W, H = v.H, n = W * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     outer[i] = 0;
     if (hashole) hashole[i] = 0;
@@ -129,47 +187,62 @@ __global__ void ccl_merge2_kernel(const uint8_t* __restrict__ img, int* __restri
     }
   }
 }
-__global__ void ccl_flatten2_kernel(int* __restrict__ Lfg, int* __restrict__ Lbg, int n) {
+__global__ void ccl_flatten2_kernel(const ExEnv* __restrict__ envs, int id) {
+  const ExEnv& E = envs[blockIdx.y];
+  const View v = view(E, id);
+  int* Lfg = E.Lfg; int* Lbg = E.Lbg;
+  const int n = v.W * v.H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (Lfg[i] >= 0) Lfg[i] = uf_find(Lfg, i); else Lbg[i] = uf_find(Lbg, i);
   }
 }
-// background components touching the image frame are the "outer" background (the frame is background for Suzuki)
-__global__ void bg_outer_kernel(const int* __restrict__ Lbg, uint8_t* __restrict__ outer, int W, int H) {
+// background components touching the image frame are the "outer" background (the frame is background for Suzuki).
+// mark_exterior: foreground components touching an S-frame edge that is not a grid edge continue outside the frame -- they are
+// (part of) the unexplored exterior, whose contourArea is far above any absorb threshold: flagged like hole-enclosing components.
+__global__ void bg_outer_kernel(const ExEnv* __restrict__ envs, int id, int mark_exterior) {
+  const ExEnv& E = envs[blockIdx.y];
+  const View v = view(E, id);
+  const int W = v.W, H = v.H;
   const int per = 2 * (W + H);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
-    int x, y;
-    if (t < W) { x = t; y = 0; } else if (t < 2 * W) { x = t - W; y = H - 1; }
-    else if (t < 2 * W + H) { x = 0; y = t - 2 * W; } else { x = W - 1; y = t - 2 * W - H; }
-    const int l = Lbg[y * W + x];
-    if (l >= 0) outer[l] = 1;
+    int x, y, ext;
+    if (t < W) { x = t; y = 0; ext = E.ext_t; } else if (t < 2 * W) { x = t - W; y = H - 1; ext = E.ext_b; }
+    else if (t < 2 * W + H) { x = 0; y = t - 2 * W; ext = E.ext_l; } else { x = W - 1; y = t - 2 * W - H; ext = E.ext_r; }
+    const int l = E.Lbg[y * W + x];
+    if (l >= 0) E.outer[l] = 1;
+    else if (mark_exterior && ext) E.hashole[E.Lfg[y * W + x]] = 1;
   }
 }
-__global__ void collect_roots_kernel(const int* __restrict__ Lfg, const int* __restrict__ Lbg, const uint8_t* __restrict__ outer,
-                                     int W, int H, Contour* __restrict__ cont, ExState* st) {
-  const int n = W * H;
+__global__ void collect_roots_kernel(const ExEnv* __restrict__ envs, int id) {
+  const ExEnv& E = envs[blockIdx.y];
+  const View v = view(E, id);
+  const int* __restrict__ Lfg = E.Lfg; const int* __restrict__ Lbg = E.Lbg; const uint8_t* __restrict__ outer = E.outer;
+  const int W = v.W, n = v.W * v.H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (Lfg[i] != i) continue;                      // roots only (= raster-first pixel of the component)
     const int y = i / W, x = i - y * W;
     bool top = true;
     if (x > 0) { const int lb = Lbg[i - 1]; top = lb >= 0 && outer[lb]; }
     if (!top) continue;                             // nested inside a hole of another component: not external
-    const int k = atomicAdd(&st->n_cont, 1);
-    if (k < EX_MAXC) { cont[k].start = i; cont[k].ed = 0; } else st->overflow = 1;
+    const int k = atomicAdd(&E.st->n_cont, 1);
+    if (k < EX_MAXC) { E.cont[k].start = i; E.cont[k].ed = 0; } else E.st->overflow = 1;
   }
 }
 // a foreground component that directly encloses a background region (a hole): flag its root
-__global__ void mark_holes_kernel(const int* __restrict__ Lfg, const int* __restrict__ Lbg, const uint8_t* __restrict__ outer,
-                                  uint8_t* __restrict__ hashole, int W, int H) {
-  const int n = W * H;
+__global__ void mark_holes_kernel(const ExEnv* __restrict__ envs, int id) {
+  const ExEnv& E = envs[blockIdx.y];
+  const View v = view(E, id);
+  const int W = v.W, n = v.W * v.H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (Lbg[i] != i || outer[i]) continue;            // raster-first pixel of an enclosed background region
+    if (E.Lbg[i] != i || E.outer[i]) continue;        // raster-first pixel of an enclosed background region
     const int x = i % W;
-    if (x > 0 && Lfg[i - 1] >= 0) hashole[Lfg[i - 1]] = 1;
+    if (x > 0 && E.Lfg[i - 1] >= 0) E.hashole[E.Lfg[i - 1]] = 1;
   }
 }
-// reverse raster order (cv2 returns the last-found contour first); one block, bitonic sort in shared memory
-__global__ void __launch_bounds__(1024) sort_roots_kernel(Contour* __restrict__ cont, ExState* st) {
+// reverse raster order (cv2 returns the last-found contour first); one block per environment, bitonic sort in shared memory
+__global__ void __launch_bounds__(1024) sort_roots_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  Contour* cont = E.cont; ExState* st = E.st;
   __shared__ int keys[EX_MAXC];
   int n = st->n_cont;
   if (n > EX_MAXC) n = EX_MAXC;
@@ -231,19 +304,25 @@ __device__ int trace_border(const uint8_t* __restrict__ nbm, int W, int x0, int 
   if (WRITE) { c->x0 = minx; c->x1 = maxx; c->y0 = miny; c->y1 = maxy; }
   return n;
 }
+
 // mode 0: trace every contour; 1: only when more than one contour exists (component selection); 2: skip components
-// that enclose a hole (their filled polygon contains a zero cell, so F1 can never absorb them)
-__global__ void trace_kernel(const uint8_t* __restrict__ nbm, int W, int H, Contour* __restrict__ cont, int2* __restrict__ chain,
-                             int cap, ExState* st, int mode, const uint8_t* __restrict__ hashole) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= st->n_cont || c >= gridDim.x * blockDim.x) return;
-  const int s = cont[c].start, y0 = s / W, x0 = s - y0 * W;
-  if ((mode == 1 && st->n_cont <= 1) || (mode == 2 && hashole[s])) { cont[c].off = 0; cont[c].len = 0; return; }
-  const int n = trace_border<false>(nbm, W, x0, y0, nullptr, nullptr, cont[c].ed);
-  const int off = atomicAdd(&st->cursor, n);
-  if (off + n > cap) { st->overflow = 1; cont[c].off = 0; cont[c].len = 0; return; }
-  cont[c].off = off; cont[c].len = n;
-  trace_border<true>(nbm, W, x0, y0, chain + off, &cont[c], cont[c].ed);
+// flagged in hashole (they enclose a hole -- their filled polygon contains a zero cell -- or reach the exterior: F1 can never
+// absorb them)
+__global__ void trace_kernel(const ExEnv* __restrict__ envs, int id, int mode) {
+  const ExEnv& E = envs[blockIdx.y];
+  const View v = view(E, id);
+  ExState* st = E.st;
+  const int W = v.W;
+  const int nc = min(st->n_cont, E.maxc);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const int s = E.cont[c].start, y0 = s / W, x0 = s - y0 * W;
+    if ((mode == 1 && st->n_cont <= 1) || (mode == 2 && E.hashole[s])) { E.cont[c].off = 0; E.cont[c].len = 0; continue; }
+    const int n = trace_border<false>(E.nbm, W, x0, y0, nullptr, nullptr, E.cont[c].ed);
+    const int off = atomicAdd(&st->cursor, n);
+    if (off + n > E.chain_cap) { st->overflow = 1; E.cont[c].off = 0; E.cont[c].len = 0; continue; }
+    E.cont[c].off = off; E.cont[c].len = n;
+    trace_border<true>(E.nbm, W, x0, y0, E.chain + off, &E.cont[c], E.cont[c].ed);
+  }
 }
 
 // CHAIN_APPROX_SIMPLE: point i of a chain is kept iff the step into it differs from the step out of it
@@ -282,18 +361,28 @@ __device__ double ppt_distance(const int2* p, int n, int ptx, int pty) {
   return (counter & 1) ? r : -r;
 }
 
+
 // ------------------------------------------------------------------------------ scan conversion ----
-// planes: tog / orb, `pw` 32-bit words per row, rows [0, H)
-__global__ void zero_planes_kernel(uint32_t* tog, uint32_t* orb, int words) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) { tog[i] = 0; orb[i] = 0; }
+// planes: tog / orb, `pw` 32-bit words per row of the frame
+__device__ __forceinline__ void frame_dims(const ExEnv& E, int frame, int& W, int& H) {
+  if (frame == FRAME_WIN) { W = E.W0; H = E.W0; } else { W = E.Sw; H = E.Sh; }
 }
-// chain polygon: every edge is a unit step; outline = the chain points
-__global__ void chain_edges_kernel(const Contour* __restrict__ cont, const int* __restrict__ which, const int2* __restrict__ chain,
-                                   uint32_t* tog, uint32_t* orb, int W, int H, int pw, const ExState* st) {
-  const int ci = which ? *which : blockIdx.y;
-  if (ci < 0 || ci >= st->n_cont) return;
-  const Contour c = cont[ci];
-  const int2* p = chain + c.off;
+__global__ void zero_planes_kernel(const ExEnv* __restrict__ envs, int frame) {
+  const ExEnv& E = envs[blockIdx.y];
+  int W, H; frame_dims(E, frame, W, H);
+  const int words = ((W + 31) / 32) * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) { E.tog[i] = 0; E.orb[i] = 0; }
+}
+// chain polygon: every edge is a unit step; outline = the chain points.  Contour index = *E.which.
+__global__ void chain_edges_kernel(const ExEnv* __restrict__ envs, int frame) {
+  const ExEnv& E = envs[blockIdx.y];
+  int W, H; frame_dims(E, frame, W, H);
+  const int pw = (W + 31) / 32;
+  const int ci = *E.which;
+  if (ci < 0 || ci >= E.st->n_cont) return;
+  const Contour c = E.cont[ci];
+  const int2* p = E.chain + c.off;
+  uint32_t* tog = E.tog; uint32_t* orb = E.orb;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.len; i += gridDim.x * blockDim.x) {
     const int2 a = p[i], b = p[i + 1 == c.len ? 0 : i + 1];
     atomicOr(&orb[a.y * pw + (a.x >> 5)], 1u << (a.x & 31));
@@ -306,26 +395,38 @@ __global__ void chain_edges_kernel(const Contour* __restrict__ cont, const int* 
   }
 }
 // rows -> image: img[cell] = value where filled; optionally everything else := 0 (clear_rest)
-__global__ void planes_to_image_kernel(const uint32_t* __restrict__ tog, const uint32_t* __restrict__ orb, uint8_t* __restrict__ img, int W,
-                                       int H, int pw, int value, int clear_rest, const int* __restrict__ enable) {
-  if (enable && *enable < 0) return;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < H; r += gridDim.x * blockDim.x) {
-    uint32_t carry = 0;
-    for (int w = 0; w < pw; ++w) {
-      const uint32_t t = tog[r * pw + w];
-      uint32_t x = t;
-      x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
-      x ^= carry;
-      if (__popc(t) & 1) carry = ~carry;
-      const uint32_t f = x | orb[r * pw + w];
-      for (int bq = 0; bq < 32; ++bq) {
-        const int col = w * 32 + bq;
-        if (col >= W) break;
-        if ((f >> bq) & 1u) img[r * W + col] = (uint8_t)value;
-        else if (clear_rest) img[r * W + col] = 0;
-      }
+__device__ __forceinline__ void planes_row_to_image(const uint32_t* __restrict__ tog, const uint32_t* __restrict__ orb, uint8_t* __restrict__ img,
+                                                    int W, int pw, int r, int value, int clear_rest) {
+  uint32_t carry = 0;
+  for (int w = 0; w < pw; ++w) {
+    const uint32_t t = tog[r * pw + w];
+    uint32_t x = t;
+    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+    x ^= carry;
+    if (__popc(t) & 1) carry = ~carry;
+    const uint32_t f = x | orb[r * pw + w];
+    for (int bq = 0; bq < 32; ++bq) {
+      const int col = w * 32 + bq;
+      if (col >= W) break;
+      if ((f >> bq) & 1u) img[r * W + col] = (uint8_t)value;
+      else if (clear_rest) img[r * W + col] = 0;
     }
   }
+}
+// dst: 0 = cone (window), 1 = newexp (window), 2 = exS (S frame); gated by *E.which >= 0 when `gated`
+__global__ void planes_to_image_kernel(const ExEnv* __restrict__ envs, int dst, int clear_rest, int gated) {
+  const ExEnv& E = envs[blockIdx.y];
+  if (gated && *E.which < 0) return;
+  int W, H; frame_dims(E, dst == 2 ? FRAME_S : FRAME_WIN, W, H);
+  uint8_t* img = dst == 0 ? E.cone : (dst == 1 ? E.newexp : E.exS);
+  const int pw = (W + 31) / 32;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < H; r += gridDim.x * blockDim.x) planes_row_to_image(E.tog, E.orb, img, W, pw, r, 1, clear_rest);
+}
+__global__ void planes_to_image_plain_kernel(const uint32_t* __restrict__ tog, const uint32_t* __restrict__ orb, uint8_t* __restrict__ img, int W, int H, int pw) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < H; r += gridDim.x * blockDim.x) planes_row_to_image(tog, orb, img, W, pw, r, 1, 1);
+}
+__global__ void zero_planes_plain_kernel(uint32_t* tog, uint32_t* orb, int words) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) { tog[i] = 0; orb[i] = 0; }
 }
 
 // cv::clipLine(Size2l(W, H), pt1, pt2) (oracle/cv_prims.py::clip_line): Cohen-Sutherland, intersections in double, truncated
@@ -351,6 +452,7 @@ __device__ bool clip_line(long long W, long long H, long long& x1, long long& y1
   return (c1 | c2) == 0;
 }
 
+
 // cv2.ellipse filled sector: polygon (x, y in 16.16, last vertex = centre) from the host; CollectPolyEdges +
 // FillEdgeCollection (oracle/cv_draw.py::fill_poly_fixed / poly_edge).  One block; the image is the GW x GH grid, of which the
 // W x H window at (ox, oy) is rasterised (the window may hang over the grid edge: those cells are masked by the caller).
@@ -368,8 +470,9 @@ __device__ __forceinline__ void plot_line8(uint32_t* orb, int pw, int W, int H, 
     if (ymaj) { y += sy; x += m ? 1 : 0; } else { x += 1; y += m ? sy : 0; }
   }
 }
-__global__ void sector_edges_kernel(const long long* __restrict__ v, int nv, int ox, int oy, int GW, int GH, uint32_t* tog, uint32_t* orb,
-                                    int W, int H, int pw) {
+
+__device__ void sector_edges(const long long* __restrict__ v, int nv, int ox, int oy, int GW, int GH, uint32_t* tog, uint32_t* orb,
+                             int W, int H, int pw) {
   for (int e = threadIdx.x; e < nv; e += blockDim.x) {
     const int e0 = e == 0 ? nv - 1 : e - 1;
     const long long x0 = v[2 * e0], x1 = v[2 * e];                                                 // 16.16 columns
@@ -403,6 +506,13 @@ __global__ void sector_edges_kernel(const long long* __restrict__ v, int nv, int
     }
   }
 }
+__global__ void sector_edges_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  sector_edges(E.verts, E.nv, E.ox, E.oy, E.G, E.G, E.tog, E.orb, E.W0, E.W0, (E.W0 + 31) / 32);
+}
+__global__ void sector_edges_plain_kernel(const long long* __restrict__ v, int nv, int R, uint32_t* tog, uint32_t* orb, int pw) {
+  sector_edges(v, nv, 0, 0, R, R, tog, orb, R, R, pw);
+}
 
 // ValueMap confidence cone (value_map.py:321-355): sector(0/1 byte image) x remap(cos^2(remap(atan2(|dc|,|dr|), 0, fov/2, 0, pi/2)),
 // 0, 1, min_conf, 1) in float64 with numpy's operation order, cast to float32.
@@ -418,81 +528,90 @@ __global__ void cone_template_kernel(const uint8_t* __restrict__ sector, float* 
 }
 
 // --------------------------------------------------------------------------------- window images ----
-// blocked = cone & !nav ; visible = cone & nav   (window W0 x W0 at grid origin (ox, oy))
-__global__ void fog_masks_kernel(const uint8_t* __restrict__ cone, const uint8_t* __restrict__ nav, int G, int ox, int oy, int W0,
-                                 uint8_t* __restrict__ blocked, uint8_t* __restrict__ visible) {
+// blocked = cone & !nav ; visible = cone & nav   (window W0 x W0 at grid origin (ox, oy)); also clears cut and newexp
+__global__ void fog_masks_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int W0 = E.W0, G = E.G;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W0 * W0; i += gridDim.x * blockDim.x) {
     const int y = i / W0, x = i - y * W0;
-    const int gx = ox + x, gy = oy + y;
-    if ((unsigned)gx >= (unsigned)G || (unsigned)gy >= (unsigned)G) { blocked[i] = 0; visible[i] = 0; continue; }   // cv2 clips at the grid edge
-    const uint8_t c = cone[i], nv = nav[(size_t)gy * G + gx];
-    blocked[i] = c && !nv; visible[i] = c && nv;
+    const int gx = E.ox + x, gy = E.oy + y;
+    E.cut[i] = 0; E.newexp[i] = 0;
+    if ((unsigned)gx >= (unsigned)G || (unsigned)gy >= (unsigned)G) { E.blocked[i] = 0; E.visible[i] = 0; continue; }   // cv2 clips at the grid edge
+    const uint8_t c = E.cone[i], nv = E.nav[(size_t)gy * G + gx];
+    E.blocked[i] = c && !nv; E.visible[i] = c && nv;
   }
 }
 
 // CHAIN_APPROX_SIMPLE vertex list of every contour, compacted in order (one warp per contour)
-__global__ void simple_vertices_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, int2* __restrict__ sv,
-                                       int* __restrict__ nsv, const ExState* st) {
-  const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (ci >= st->n_cont) return;
-  const Contour c = cont[ci];
-  const int2* p = chain + c.off;
-  int2* o = sv + c.off;
-  int cnt = 0;
-  for (int b = 0; b < c.len; b += 32) {
-    const int i = b + lane;
-    const bool keep = i < c.len && simple_vertex(p, c.len, i);
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (keep) o[cnt + __popc(m & ((1u << lane) - 1))] = p[i];
-    cnt += __popc(m);
+__global__ void simple_vertices_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = E.st->n_cont;
+  for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < nc; ci += nw) {
+    const Contour c = E.cont[ci];
+    const int2* p = E.chain + c.off;
+    int2* o = E.sv + c.off;
+    int cnt = 0;
+    for (int b = 0; b < c.len; b += 32) {
+      const int i = b + lane;
+      const bool keep = i < c.len && simple_vertex(p, c.len, i);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) o[cnt + __popc(m & ((1u << lane) - 1))] = p[i];
+      cnt += __popc(m);
+    }
+    if (lane == 0) E.nsv[ci] = cnt;
   }
-  if (lane == 0) nsv[ci] = cnt;
 }
 // R3/R4: obstacle contours -> ray list (x0,y0,x1,y1 in window coordinates); one warp per contour
-__global__ void rays_kernel(const Contour* __restrict__ cont, const int2* __restrict__ sv, const int* __restrict__ nsv, int4* __restrict__ rays,
-                            int cap, int sx, int sy, int ox, int oy, double heading_deg, double ray_len, ExState* st) {
-  const int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (ci >= st->n_cont) return;
-  const int2* v = sv + cont[ci].off;
-  const int nv = nsv[ci];
-  // cv2.isContourConvex on the SIMPLE vertices (oracle/contours.py::is_convex): every turn has the same strict sign
-  int orient = 0;
-  for (int j = lane; j < nv; j += 32) {
-    const int2 a = v[(j + 2 * nv - 2) % nv], b = v[(j + nv - 1) % nv], c = v[j];
-    const long long dx0 = b.x - a.x, dy0 = b.y - a.y, dx = c.x - b.x, dy = c.y - b.y;
-    const long long dxdy0 = dx * dy0, dydx0 = dy * dx0;
-    orient |= dydx0 > dxdy0 ? 1 : (dydx0 < dxdy0 ? 2 : 3);
-  }
-  orient = __reduce_or_sync(0xffffffffu, orient);
-  const bool convex = nv > 0 && orient != 3;
-  auto emit = [&](int qx, int qy) {
-    const double ang = atan2((double)(qy - sy), (double)(qx - sx));
-    // astype(np.int32) truncates toward zero in GRID coordinates (the window origin is subtracted afterwards)
-    const int ex = (int)((double)(qx + ox) + ray_len * cos(ang)) - ox, ey = (int)((double)(qy + oy) + ray_len * sin(ang)) - oy;
-    const int k = atomicAdd(&st->n_rays, 1);
-    if (k < cap) rays[k] = make_int4(qx, qy, ex, ey); else st->overflow = 1;
-  };
-  if (convex) {
-    // _extreme_bearing_points: the heading in DEGREES is used as radians, as in the restated package; np.argmin /
-    // np.argmax return the FIRST extreme vertex
-    const double cs = cos(-heading_deg), sn = sin(-heading_deg);
-    double amin = 1e300, amax = -1e300; int imin = 0x7fffffff, imax = 0x7fffffff;
+__global__ void rays_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  ExState* st = E.st;
+  const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nc = st->n_cont, sx = E.sx, sy = E.sy, ox = E.ox, oy = E.oy, cap = E.rays_cap;
+  const double heading_deg = E.heading_deg, ray_len = E.ray_len;
+  int4* rays = E.rays;
+  for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < nc; ci += nw) {
+    const int2* v = E.sv + E.cont[ci].off;
+    const int nv = E.nsv[ci];
+    // cv2.isContourConvex on the SIMPLE vertices (oracle/contours.py::is_convex): every turn has the same strict sign
+    int orient = 0;
     for (int j = lane; j < nv; j += 32) {
-      const double qx = (double)(v[j].x - sx), qy = (double)(v[j].y - sy);
-      const double rx = qx * cs + qy * sn, ry = qx * (-sn) + qy * cs;
-      const double a = atan2(ry, rx);
-      if (a < amin) { amin = a; imin = j; }
-      if (a > amax) { amax = a; imax = j; }
+      const int2 a = v[(j + 2 * nv - 2) % nv], b = v[(j + nv - 1) % nv], c = v[j];
+      const long long dx0 = b.x - a.x, dy0 = b.y - a.y, dx = c.x - b.x, dy = c.y - b.y;
+      const long long dxdy0 = dx * dy0, dydx0 = dy * dx0;
+      orient |= dydx0 > dxdy0 ? 1 : (dydx0 < dxdy0 ? 2 : 3);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double a1 = __shfl_xor_sync(0xffffffffu, amin, o), a2 = __shfl_xor_sync(0xffffffffu, amax, o);
-      const int i1 = __shfl_xor_sync(0xffffffffu, imin, o), i2 = __shfl_xor_sync(0xffffffffu, imax, o);
-      if (a1 < amin || (a1 == amin && i1 < imin)) { amin = a1; imin = i1; }
-      if (a2 > amax || (a2 == amax && i2 < imax)) { amax = a2; imax = i2; }
+    orient = __reduce_or_sync(0xffffffffu, orient);
+    const bool convex = nv > 0 && orient != 3;
+    auto emit = [&](int qx, int qy) {
+      const double ang = atan2((double)(qy - sy), (double)(qx - sx));
+      // astype(np.int32) truncates toward zero in GRID coordinates (the window origin is subtracted afterwards)
+      const int ex = (int)((double)(qx + ox) + ray_len * cos(ang)) - ox, ey = (int)((double)(qy + oy) + ray_len * sin(ang)) - oy;
+      const int k = atomicAdd(&st->n_rays, 1);
+      if (k < cap) rays[k] = make_int4(qx, qy, ex, ey); else st->overflow = 1;
+    };
+    if (convex) {
+      // _extreme_bearing_points: the heading in DEGREES is used as radians, as in the restated package; np.argmin /
+      // np.argmax return the FIRST extreme vertex
+      const double cs = cos(-heading_deg), sn = sin(-heading_deg);
+      double amin = 1e300, amax = -1e300; int imin = 0x7fffffff, imax = 0x7fffffff;
+      for (int j = lane; j < nv; j += 32) {
+        const double qx = (double)(v[j].x - sx), qy = (double)(v[j].y - sy);
+        const double rx = qx * cs + qy * sn, ry = qx * (-sn) + qy * cs;
+        const double a = atan2(ry, rx);
+        if (a < amin) { amin = a; imin = j; }
+        if (a > amax) { amax = a; imax = j; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double a1 = __shfl_xor_sync(0xffffffffu, amin, o), a2 = __shfl_xor_sync(0xffffffffu, amax, o);
+        const int i1 = __shfl_xor_sync(0xffffffffu, imin, o), i2 = __shfl_xor_sync(0xffffffffu, imax, o);
+        if (a1 < amin || (a1 == amin && i1 < imin)) { amin = a1; imin = i1; }
+        if (a2 > amax || (a2 == amax && i2 < imax)) { amax = a2; imax = i2; }
+      }
+      if (lane == 0) { emit(v[imin].x, v[imin].y); emit(v[imax].x, v[imax].y); }
+    } else {
+      for (int j = lane; j < nv; j += 32) emit(v[j].x, v[j].y);
     }
-    if (lane == 0) { emit(v[imin].x, v[imin].y); emit(v[imax].x, v[imax].y); }
-  } else {
-    for (int j = lane; j < nv; j += 32) emit(v[j].x, v[j].y);
   }
 }
 
@@ -530,10 +649,8 @@ __device__ void line2_fixed(const CutWin& c, int G, long long x1, long long y1, 
   }
 }
 __device__ __forceinline__ long long pick4(const long long (&a)[4], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3])); }
-__global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __restrict__ cut, int W, int H, int ox, int oy, int G, const ExState* st) {
-  const int ri = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ri >= st->n_rays) return;
-  const int4 r = rays[ri];
+
+__device__ void thick_ray(const int4 r, uint8_t* __restrict__ cut, int W, int H, int ox, int oy, int G) {
   const CutWin cw{cut, W, H, ox, oy};
   // ThickLine (cv2 4.13): the integer centre line is first clipped to the image grown by the thickness on every side
   long long px0 = r.x + ox + 2, py0 = r.y + oy + 2, px1 = r.z + ox + 2, py1 = r.w + oy + 2;
@@ -604,139 +721,149 @@ __global__ void thick_rays_kernel(const int4* __restrict__ rays, uint8_t* __rest
     put_px(cw, cxs[k], cys[k] - 1); put_px(cw, cxs[k], cys[k] + 1);
   }
 }
-__global__ void apply_cut_kernel(uint8_t* __restrict__ visible, const uint8_t* __restrict__ cut, int n, const ExState* st) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) if (cut[i]) visible[i] = 0;
+
+__global__ void thick_rays_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int nr = min(E.st->n_rays, E.rays_cap);
+  for (int ri = blockIdx.x * blockDim.x + threadIdx.x; ri < nr; ri += gridDim.x * blockDim.x)
+    thick_ray(E.rays[ri], E.cut, E.W0, E.W0, E.ox, E.oy, E.G);
 }
-// no obstacle contour in the cone -> reveal_fog_of_war returns the (all-zero) input mask
-__global__ void fog_gate_kernel(ExState* st) { if (st->n_cont == 0) st->skip_fog = 1; }
+// visible &= !cut; no obstacle contour in the cone -> reveal_fog_of_war returns the (all-zero) input mask
+__global__ void apply_cut_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int n = E.W0 * E.W0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) if (E.cut[i]) E.visible[i] = 0;
+}
+__global__ void fog_gate_kernel(const ExEnv* __restrict__ envs) { ExState* st = envs[blockIdx.y].st; if (threadIdx.x == 0 && st->n_cont == 0) st->skip_fog = 1; }
 
 // R5: pick the contour with the smallest |pointPolygonTest| to the agent; > 3 px -> nothing revealed
-__global__ void pick_nearest_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, double* __restrict__ dist, int sx, int sy,
-                                    ExState* st, int phase) {
-  if (phase == 0) {
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= st->n_cont) return;
-    dist[ci] = ppt_distance(chain + cont[ci].off, cont[ci].len, sx, sy);
-  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+// obstacle_map.py:133-146: more than one external contour -> keep the first (cv2 order) that contains the agent (dist >= 0),
+// else the nearest; the kept one is redrawn FILLED.   what: 0 = fog (R5), 1 = component selection
+__global__ void contour_dist_kernel(const ExEnv* __restrict__ envs, int what) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int nc = E.st->n_cont;
+  if (what == 1 && nc <= 1) return;
+  const int px = what == 0 ? E.sx : E.ax - E.fx0, py = what == 0 ? E.sy : E.ay - E.fy0;
+  for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < nc; ci += gridDim.x * blockDim.x)
+    E.dist[ci] = ppt_distance(E.chain + E.cont[ci].off, E.cont[ci].len, px, py);
+}
+__global__ void contour_pick_kernel(const ExEnv* __restrict__ envs, int what) {
+  const ExEnv& E = envs[blockIdx.y];
+  if (threadIdx.x != 0) return;
+  ExState* st = E.st;
+  if (what == 0) {
     int best = -1; double bd = INFINITY;
-    for (int i = 0; i < st->n_cont; ++i) { const double d = fabs(dist[i]); if (d < bd) { bd = d; best = i; } }
+    for (int i = 0; i < st->n_cont; ++i) { const double d = fabs(E.dist[i]); if (d < bd) { bd = d; best = i; } }
     st->chosen = (st->skip_fog || bd > 3.0) ? -1 : best;
     if (st->chosen < 0) st->skip_fog = 1;
-  }
-}
-
-// new = dilate3(newexp); explored |= new (window); then explored &= nav over the obstacle-update window
-__global__ void explored_update_kernel(const uint8_t* __restrict__ newexp, int W0, int ox, int oy, uint8_t* __restrict__ explored,
-                                       const uint8_t* __restrict__ nav, int G, int rx0, int ry0, int rw, int rh, const ExState* st) {
-  const int n = rw * rh;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int gy = ry0 + i / rw, gx = rx0 + i % rw;
-    uint8_t e = explored[(size_t)gy * G + gx];
-    if (!st->skip_fog) {
-      const int wx = gx - ox, wy = gy - oy;
-      bool hit = false;
-      for (int dy = -1; dy <= 1 && !hit; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int x = wx + dx, y = wy + dy;
-          if ((unsigned)x < (unsigned)W0 && (unsigned)y < (unsigned)W0 && newexp[y * W0 + x]) { hit = true; break; }
-        }
-      if (hit) e = 1;
-    }
-    if (nav[(size_t)gy * G + gx] == 0) e = 0;
-    explored[(size_t)gy * G + gx] = e;
-  }
-}
-
-// obstacle_map.py:133-146: more than one external contour -> keep the first (cv2 order) that contains the agent
-// (dist >= 0), else the nearest; the kept one is redrawn FILLED
-__global__ void select_component_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, double* __restrict__ dist, int ax, int ay,
-                                        ExState* st, int* __restrict__ which, int phase) {
-  if (phase == 0) {
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= st->n_cont || st->n_cont <= 1) return;
-    dist[ci] = ppt_distance(chain + cont[ci].off, cont[ci].len, ax, ay);
-  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *E.which = st->skip_fog ? -1 : st->chosen;
+  } else {
     int best = -1;
     if (st->n_cont > 1) {
       double md = INFINITY; best = 0;
       for (int i = 0; i < st->n_cont; ++i) {
-        const double d = dist[i];
+        const double d = E.dist[i];
         if (d >= 0) { best = i; break; }
         if (fabs(d) < md) { md = fabs(d); best = i; }
       }
     }
-    *which = best;      // -1: a single contour, explored area stays as it is
+    *E.which = best;      // -1: a single contour, explored area stays as it is
   }
 }
 
-// k x k box dilation of a 0/1 byte image (whole image; used for the 5x5 growth of the explored area)
-__global__ void dilate_full_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int H, int k) {
-  const int r = k / 2, n = W * H;
+// S frame images of this step:  exS = ((explored | dilate3(newexp)) & nav) , navS = nav   (obstacle_map.py:125-127; outside the
+// S frame explored is 0, so masking the S frame is masking the whole grid)
+__global__ void explored_update_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int Sw = E.Sw, n = E.Sw * E.Sh, G = E.G, W0 = E.W0;
+  const bool fog = !E.st->skip_fog;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int y = i / W, x = i - y * W;
-    uint8_t m = 0;
-    for (int dy = -r; dy <= r && !m; ++dy) {
-      const int yy = y + dy;
-      if ((unsigned)yy >= (unsigned)H) continue;
-      for (int dx = -r; dx <= r; ++dx) { const int xx = x + dx; if ((unsigned)xx < (unsigned)W && src[yy * W + xx]) { m = 1; break; } }
+    const int gy = E.fy0 + i / Sw, gx = E.fx0 + i % Sw;
+    uint8_t e = E.explored[(size_t)gy * G + gx];
+    if (fog && !e) {
+      const int wx = gx - E.ox, wy = gy - E.oy;
+      bool hit = false;
+      for (int dy = -1; dy <= 1 && !hit; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = wx + dx, y = wy + dy;
+          if ((unsigned)x < (unsigned)W0 && (unsigned)y < (unsigned)W0 && E.newexp[y * W0 + x]) { hit = true; break; }
+        }
+      if (hit) e = 1;
     }
-    dst[i] = m;
+    const uint8_t nv = E.nav[(size_t)gy * G + gx];
+    if (nv == 0) e = 0;
+    E.exS[i] = e; E.navS[i] = nv;
   }
 }
-// unexplored = nav & !grown
-__global__ void unexplored_kernel(const uint8_t* __restrict__ nav, const uint8_t* __restrict__ grown, uint8_t* __restrict__ out, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (nav[i] && !grown[i]) ? 1 : 0;
+// explored[S frame] = exS ; grown = dilate5(exS) ; unexp = nav & !grown ; ex2 = grown   (obstacle_map.py:159-163 + F1's input)
+__global__ void paste_grow_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int W = E.Sw, H = E.Sh, n = W * H, G = E.G;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    E.explored[(size_t)(E.fy0 + y) * G + E.fx0 + x] = E.exS[i];
+    uint8_t m = 0;
+    for (int dy = -2; dy <= 2 && !m; ++dy) {
+      const int yy = y + dy;
+      if ((unsigned)yy >= (unsigned)H) continue;
+      for (int dx = -2; dx <= 2; ++dx) { const int xx = x + dx; if ((unsigned)xx < (unsigned)W && E.exS[yy * W + xx]) { m = 1; break; } }
+    }
+    E.grown[i] = m; E.ex2[i] = m;
+    E.unexp[i] = (E.navS[i] && !m) ? 1 : 0;
+  }
 }
 
 // F1: small unexplored pockets (contourArea < thresh, filled mask only covers unexplored cells) are absorbed
 // into the explored mask as 255.  One block per contour; cells of the bounding box are tested against the chain polygon.
-__global__ void absorb_small_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, const uint8_t* __restrict__ unexplored,
-                                    uint8_t* __restrict__ explored2, int W, int H, double area_thresh, const ExState* st) {
-  const int ci = blockIdx.x;
-  if (ci >= st->n_cont) return;
-  const Contour c = cont[ci];
-  if (c.len == 0) return;                       // not traced: the component encloses a hole
-  const int2* p = chain + c.off;
+__global__ void absorb_small_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int W = E.Sw;
+  const int nc = E.st->n_cont;
   __shared__ long long s_a2;
   __shared__ int s_bad;
-  if (threadIdx.x == 0) { s_a2 = 0; s_bad = 0; }
-  __syncthreads();
-  long long acc = 0;                                             // shoelace (twice the signed area), exact in integers
-  for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
-    const int2 q = p[i == 0 ? c.len - 1 : i - 1], b = p[i];
-    acc += (long long)q.x * b.y - (long long)b.x * q.y;
-  }
-  atomicAdd(reinterpret_cast<unsigned long long*>(&s_a2), (unsigned long long)acc);
-  __syncthreads();
-  const double area = fabs((double)s_a2 * 0.5);
-  if (!(area < area_thresh)) return;
-  const int bw = c.x1 - c.x0 + 1, bh = c.y1 - c.y0 + 1;
-  // pass 1: every cell drawContours would fill must be an unexplored (== 1) cell
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
-      const int x = c.x0 + i % bw, y = c.y0 + i / bw;
-      // even-odd with the exact-hit rule (unit edges: intercept is the lower endpoint's column) + outline
-      int less = 0; bool exact = false;
-      for (int e = 0; e < c.len; ++e) {
-        const int2 a = p[e], b = p[e + 1 == c.len ? 0 : e + 1];
-        if (a.x == x && a.y == y) exact = true;
-        if (a.y == b.y) continue;
-        const int ya = min(a.y, b.y), xa = a.y < b.y ? a.x : b.x;
-        if (ya != y) continue;
-        if (xa < x) ++less; else if (xa == x) exact = true;
-      }
-      if (exact || (less & 1)) {
-        if (pass == 0) { if (unexplored[y * W + x] != 1) s_bad = 1; }
-        else explored2[y * W + x] = 255;
-      }
-    }
+  for (int ci = blockIdx.x; ci < nc; ci += gridDim.x) {
+    const Contour c = E.cont[ci];
+    if (c.len == 0) continue;                     // not traced: the component encloses a hole or reaches the exterior
+    const int2* p = E.chain + c.off;
     __syncthreads();
-    if (s_bad) return;
+    if (threadIdx.x == 0) { s_a2 = 0; s_bad = 0; }
+    __syncthreads();
+    long long acc = 0;                                             // shoelace (twice the signed area), exact in integers
+    for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
+      const int2 q = p[i == 0 ? c.len - 1 : i - 1], b = p[i];
+      acc += (long long)q.x * b.y - (long long)b.x * q.y;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_a2), (unsigned long long)acc);
+    __syncthreads();
+    const double area = fabs((double)s_a2 * 0.5);
+    if (!(area < E.area_thresh)) continue;
+    const int bw = c.x1 - c.x0 + 1, bh = c.y1 - c.y0 + 1;
+    // pass 0: every cell drawContours would fill must be an unexplored (== 1) cell; pass 1: write
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
+        const int x = c.x0 + i % bw, y = c.y0 + i / bw;
+        // even-odd with the exact-hit rule (unit edges: intercept is the lower endpoint's column) + outline
+        int less = 0; bool exact = false;
+        for (int e = 0; e < c.len; ++e) {
+          const int2 a = p[e], b = p[e + 1 == c.len ? 0 : e + 1];
+          if (a.x == x && a.y == y) exact = true;
+          if (a.y == b.y) continue;
+          const int ya = min(a.y, b.y), xa = a.y < b.y ? a.x : b.x;
+          if (ya != y) continue;
+          if (xa < x) ++less; else if (xa == x) exact = true;
+        }
+        if (exact || (less & 1)) {
+          if (pass == 0) { if (E.unexp[y * W + x] != 1) s_bad = 1; }
+          else E.ex2[y * W + x] = 255;
+        }
+      }
+      __syncthreads();
+      if (s_bad) break;
+    }
   }
 }
 
-// F2-F4 (oracle/explore_oracle.py::_interpolate/_split/_midpoint): one thread walks every external contour of the
-// grown+absorbed explored mask in cv2 order and emits the frontier midpoints.
+// F2-F4 (oracle/explore_oracle.py::_interpolate/_split/_midpoint)
 __device__ __forceinline__ bool blur_zero(const uint8_t* nav, const uint8_t* ex2, int W, int H, int x, int y) {
   // cv2.blur 3x3 of 255*(nav & !explored2) is 0 iff all nine (BORDER_REFLECT_101) cells are 0
   for (int dy = -1; dy <= 1; ++dy)
@@ -748,11 +875,12 @@ __device__ __forceinline__ bool blur_zero(const uint8_t* nav, const uint8_t* ex2
     }
   return true;
 }
-__device__ void emit_midpoint(const int2* p, int n, int a, int b, int a2, int b2, double* out, int maxf, ExState* st) {
-  // the frontier is q[a..b) followed by q[a2..b2) (second range empty unless merged); q[k] = p[(k+1)/2 mod n]
+
+// arc-length midpoint of the frontier q[a..b) followed by q[a2..b2) (second range empty unless merged); q[k] = p[(k+1)/2 mod n];
+// written in GRID coordinates ((fx0, fy0) = S-frame origin) at out[0..1]
+__device__ void midpoint(const int2* p, int n, int a, int b, int a2, int b2, int fx0, int fy0, double* out) {
   auto Q = [&](int k) { return p[((k + 1) >> 1) % n]; };
   const int len1 = b - a, len2 = b2 - a2, len = len1 + len2;
-  if (len < 2) return;
   auto at = [&](int i) { return i < len1 ? Q(a + i) : Q(a2 + (i - len1)); };
   double total = 0.0;
   for (int i = 0; i + 1 < len; ++i) { const int2 u = at(i), v = at(i + 1); total += sqrt((double)((u.x - v.x) * (u.x - v.x) + (u.y - v.y) * (u.y - v.y))); }
@@ -769,101 +897,143 @@ __device__ void emit_midpoint(const int2* p, int n, int a, int b, int a2, int b2
   const int2 u = at(seg), v = at(seg + 1);
   const double l = sqrt((double)((u.x - v.x) * (u.x - v.x) + (u.y - v.y) * (u.y - v.y)));
   const double t = (half - before) / l;
-  const int k = st->n_front;
-  if (k < maxf) { out[2 * k] = u.x + t * (v.x - u.x); out[2 * k + 1] = u.y + t * (v.y - u.y); st->n_front = k + 1; } else st->overflow = 1;
-}
-// F3 "bad" test of every traced border point at once (the serial walk below only reads the flags)
-__global__ void bad_flags_kernel(const int2* __restrict__ chain, const uint8_t* __restrict__ nav, const uint8_t* __restrict__ ex2, int W, int H,
-                                 uint8_t* __restrict__ flags, const ExState* st) {
-  const int n = st->cursor;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    flags[i] = blur_zero(nav, ex2, W, H, chain[i].x, chain[i].y) ? 1 : 0;
-}
-__global__ void frontier_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, const uint8_t* __restrict__ flags,
-                                double* __restrict__ out, int maxf, ExState* st) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  st->n_front = 0;
-  for (int ci = 0; ci < st->n_cont; ++ci) {
-    const int2* p = chain + cont[ci].off;
-    const uint8_t* fl = flags + cont[ci].off;
-    const int n = cont[ci].len, m = 2 * n;              // interpolated sequence q has 2n entries
-    if (n == 0) continue;
-    auto bad = [&](int k) { return fl[((k + 1) >> 1) % n] != 0; };
-    // bad indices split q; piece 0 = [0, b0), piece j = [b_{j-1}, b_j) minus its first element, last = [b_last, m)
-    int nbad = 0, first_bad = -1, last_bad = -1;
-    for (int k = 0; k < m; ++k) if (bad(k)) { if (first_bad < 0) first_bad = k; last_bad = k; ++nbad; }
-    const bool wrap = nbad > 0 && first_bad != 0 && last_bad < m - 2;
-    if (nbad == 0) { if (m > 2) emit_midpoint(p, n, 0, m, 0, 0, out, maxf, st); continue; }   // a single piece is kept iff len > 2
-    // collect kept pieces in order; with wrap the LAST kept piece is prepended to the FIRST kept piece
-    // pass 1: find first kept piece and last kept piece
-    int fk_a = -1, fk_b = -1, lk_a = -1, lk_b = -1, nkept = 0;
-    {
-      int prev = 0, idx = 0;
-      for (int k = 0; k <= m; ++k) {
-        if (k == m || bad(k)) {
-          const int a = prev, b = k, len = b - a;
-          const bool keep = (len > 2) || (idx == 0 && wrap);
-          if (keep) {
-            const int ka = idx == 0 ? a : a + 1;
-            if (nkept == 0) { fk_a = ka; fk_b = b; }
-            lk_a = ka; lk_b = b; ++nkept;
-          }
-          prev = k; ++idx;
-        }
-      }
-    }
-    if (nkept == 0) continue;
-    const bool merge = nkept > 1 && wrap;
-    // pass 2: emit in order
-    {
-      int prev = 0, idx = 0, seen = 0;
-      for (int k = 0; k <= m; ++k) {
-        if (k == m || bad(k)) {
-          const int a = prev, b = k, len = b - a;
-          const bool keep = (len > 2) || (idx == 0 && wrap);
-          if (keep) {
-            const int ka = idx == 0 ? a : a + 1;
-            ++seen;
-            if (merge && seen == 1) { if ((lk_b - lk_a) + (fk_b - fk_a) >= 2) emit_midpoint(p, n, lk_a, lk_b, fk_a, fk_b, out, maxf, st); }
-            else if (merge && seen == nkept) { /* consumed by the merge */ }
-            else if (b - ka >= 2) emit_midpoint(p, n, ka, b, 0, 0, out, maxf, st);
-          }
-          prev = k; ++idx;
-        }
-      }
-    }
-  }
+  out[0] = (double)(u.x + fx0) + t * (double)(v.x - u.x); out[1] = (double)(u.y + fy0) + t * (double)(v.y - u.y);
 }
 
+// F3 "bad" test of every traced border point at once (the walk below only reads the flags)
+__global__ void bad_flags_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int n = min(E.st->cursor, E.chain_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    E.flags[i] = blur_zero(E.navS, E.ex2, E.Sw, E.Sh, E.chain[i].x, E.chain[i].y) ? 1 : 0;
+}
+constexpr int FRONTIER_THREADS = 256;
+// ordered compaction step: every thread of the block calls it; returns this thread's slot (or -1); `running` (identical in all
+// threads) advances by the number of flagged threads
+__device__ __forceinline__ int block_rank(bool flag, int* s_warp, int& running) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_warp[w] = __popc(m);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < FRONTIER_THREADS / 32; ++i) { const int c = s_warp[i]; if (i < w) before += c; total += c; }
+  const int slot = flag ? running + before + __popc(m & ((1u << lane) - 1)) : -1;
+  running += total;
+  __syncthreads();
+  return slot;
+}
+// One block per environment walks the external contours of the grown + absorbed explored mask in cv2 order: bad points split the
+// (twice-interpolated) contour into pieces; pieces with <= 2 points are dropped, first and last merge when the contour start is
+// not a bad point; every kept piece yields its arc-length midpoint.  The piece list is built by ordered block compactions and the
+// midpoints are computed one thread per piece (each walk is a few hundred points).
+__global__ void __launch_bounds__(FRONTIER_THREADS) frontier_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  ExState* st = E.st;
+  __shared__ int s_warp[FRONTIER_THREADS / 32];
+  int* blist = reinterpret_cast<int*>(E.sv);            // scratch: the SIMPLE-vertex buffer is free by now
+  const int cap_ints = 2 * E.chain_cap;
+  int n_front = 0;                                     // identical in all threads
+  const int nc = st->n_cont;
+  for (int ci = 0; ci < nc; ++ci) {
+    const int2* p = E.chain + E.cont[ci].off;
+    const uint8_t* fl = E.flags + E.cont[ci].off;
+    const int n = E.cont[ci].len, m = 2 * n;            // the interpolated sequence q has 2n entries
+    if (n == 0) continue;
+    __syncthreads();                                   // the previous contour's lists are no longer read
+    int nbad = 0;
+    for (int base = 0; base < m; base += FRONTIER_THREADS) {
+      const int k = base + threadIdx.x;
+      const bool bd = k < m && fl[((k + 1) >> 1) % n] != 0;
+      const int slot = block_rank(bd, s_warp, nbad);
+      if (slot >= 0 && slot < cap_ints) blist[slot] = k;
+    }
+    if (nbad == 0) {                                   // a single piece, kept iff len > 2
+      if (m > 2) {
+        if (threadIdx.x == 0) { if (n_front < E.maxf) midpoint(p, n, 0, m, 0, 0, E.fx0, E.fy0, E.frontiers + 2 * n_front); else st->overflow = 1; }
+        ++n_front;
+      }
+      continue;
+    }
+    if (3 * (long)nbad + 4 > cap_ints) { if (threadIdx.x == 0) st->overflow = 1; continue; }
+    __syncthreads();
+    // bad indices split q: piece 0 = [0, b0), piece j = [b_{j-1}, b_j) minus its first element, last = [b_last, m)
+    const int first_bad = blist[0], last_bad = blist[nbad - 1];
+    const bool wrap = first_bad != 0 && last_bad < m - 2;
+    int* klist = blist + nbad;                          // kept pieces (ka, b), in order
+    int nkept = 0;
+    for (int base = 0; base <= nbad; base += FRONTIER_THREADS) {
+      const int j = base + threadIdx.x;
+      bool keep = false; int ka = 0, b = 0;
+      if (j <= nbad) {
+        const int a = j == 0 ? 0 : blist[j - 1];
+        b = j == nbad ? m : blist[j];
+        keep = (b - a > 2) || (j == 0 && wrap);
+        ka = j == 0 ? a : a + 1;
+      }
+      const int slot = block_rank(keep, s_warp, nkept);
+      if (slot >= 0) { klist[2 * slot] = ka; klist[2 * slot + 1] = b; }
+    }
+    if (nkept == 0) continue;
+    __syncthreads();
+    // with wrap the LAST kept piece is prepended to the FIRST kept piece (and comes first in the output)
+    const bool merge = nkept > 1 && wrap;
+    const int nslots = merge ? nkept - 1 : nkept;
+    int nout = 0;
+    for (int base = 0; base < nslots; base += FRONTIER_THREADS) {
+      const int s = base + threadIdx.x;
+      bool em = false; int a = 0, b = 0, a2 = 0, b2 = 0;
+      if (s < nslots) {
+        if (merge && s == 0) { a = klist[2 * (nkept - 1)]; b = klist[2 * (nkept - 1) + 1]; a2 = klist[0]; b2 = klist[1]; em = (b - a) + (b2 - a2) >= 2; }
+        else { a = klist[2 * s]; b = klist[2 * s + 1]; em = b - a >= 2; }
+      }
+      const int slot = block_rank(em, s_warp, nout);
+      if (slot >= 0) {
+        const int k = n_front + slot;
+        if (k < E.maxf) midpoint(p, n, a, b, a2, b2, E.fx0, E.fy0, E.frontiers + 2 * k); else st->overflow = 1;
+      }
+    }
+    n_front += nout;
+  }
+  if (threadIdx.x == 0) st->n_front = n_front < E.maxf ? n_front : E.maxf;
+}
+
+
 // ---------------------------------------------------------------- fill_small_holes (img_utils.py:361-390) ----
-__global__ void zero_mask_kernel(const float* __restrict__ depth, uint8_t* __restrict__ mask, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mask[i] = depth[i] == 0.f ? 1 : 0;
+// mask = (depth == 0) into the S-frame `unexp` plane (frame = the depth image), filled := 0
+__global__ void zero_mask_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int n = E.Sw * E.Sh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { E.unexp[i] = E.depth[i] == 0.f ? 1 : 0; E.filled[i] = 0; }
 }
 // RETR_TREE: the outer border of EVERY component and the border of every hole
-__global__ void collect_all_kernel(const int* __restrict__ Lfg, const int* __restrict__ Lbg, const uint8_t* __restrict__ outer, int W, int H,
-                                   Contour* __restrict__ cont, int maxc, ExState* st) {
-  const int n = W * H;
+__global__ void collect_all_kernel(const ExEnv* __restrict__ envs) {
+  const ExEnv& E = envs[blockIdx.y];
+  const int n = E.Sw * E.Sh;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int start = -1, ed = 0;
-    if (Lfg[i] == i) { start = i; ed = 0; }
-    else if (Lbg[i] == i && !outer[i]) { start = i - 1; ed = 4; }     // hole: the pixel west of its raster-first cell, entered from the east
+    if (E.Lfg[i] == i) { start = i; ed = 0; }
+    else if (E.Lbg[i] == i && !E.outer[i]) { start = i - 1; ed = 4; }     // hole: the pixel west of its raster-first cell, entered from the east
     if (start < 0) continue;
-    const int k = atomicAdd(&st->n_cont, 1);
-    if (k < maxc) { cont[k].start = start; cont[k].ed = ed; } else st->overflow = 1;
+    const int k = atomicAdd(&E.st->n_cont, 1);
+    if (k < E.maxc) { E.cont[k].start = start; E.cont[k].ed = ed; } else E.st->overflow = 1;
   }
 }
 // one block per contour: contourArea < thresh -> drawContours(filled, [cnt], 0, 1, -1); bounding-box scan conversion in
 // shared memory, processed in row bands when the box is tall
 __global__ void __launch_bounds__(256)
-fill_small_contours_kernel(const Contour* __restrict__ cont, const int2* __restrict__ chain, uint8_t* __restrict__ filled, int W, int H,
-                           double area_thresh, int smem_words, int maxc, const ExState* st) {
+fill_small_contours_kernel(const ExEnv* __restrict__ envs, int smem_words) {
+  const ExEnv& E = envs[blockIdx.y];
   extern __shared__ uint32_t fs_smem[];
   __shared__ long long s_a2;
-  const int nc = min(st->n_cont, maxc);
+  const int W = E.Sw;
+  const int nc = min(E.st->n_cont, E.maxc);
+  const double area_thresh = E.area_thresh;
+  uint8_t* filled = E.filled;
   for (int ci = blockIdx.x; ci < nc; ci += gridDim.x) {
-    const Contour c = cont[ci];
+    const Contour c = E.cont[ci];
     if (c.len == 0) continue;
-    const int2* p = chain + c.off;
+    const int2* p = E.chain + c.off;
     __syncthreads();
     if (threadIdx.x == 0) s_a2 = 0;
     __syncthreads();
@@ -915,15 +1085,13 @@ fill_small_contours_kernel(const Contour* __restrict__ cont, const int2* __restr
     }
   }
 }
-
-__global__ void sticky_status_kernel(const ExState* st, int32_t* status) { if (st->overflow) *status |= 1; }
-__global__ void reset_state_kernel(ExState* st, int keep_fog) {
-  st->n_cont = 0; st->cursor = 0; st->n_rays = 0; st->chosen = -1;
-  if (!keep_fog) { st->skip_fog = 0; st->overflow = 0; st->n_front = 0; }
+// publish counters: frontier count / overflow flag (explore), sticky overflow status (holes)
+__global__ void publish_kernel(const ExEnv* __restrict__ envs, int sticky) {
+  const ExEnv& E = envs[blockIdx.x];
+  if (threadIdx.x != 0) return;
+  if (sticky) { if (E.st->overflow) *E.out_status |= 1; }
+  else { *E.out_count = E.st->n_front; *E.out_status = E.st->overflow; }
 }
-__global__ void clear_bytes_kernel(uint8_t* p, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0; }
-__global__ void copy_bytes_kernel(const uint8_t* s, uint8_t* d, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i]; }
-__global__ void fog_fill_gate_kernel(const ExState* st, int* which) { *which = st->skip_fog ? -1 : st->chosen; }
 
 }  // namespace vlfm
 
@@ -932,65 +1100,63 @@ using namespace vlfm;
 // -------------------------------------------------------------------------------------- host side ----
 namespace {
 
-struct Ws {       // carved from the caller's workspace
-  uint8_t *cone, *blocked, *visible, *cut, *newexp, *outer, *grown, *unexp, *ex2, *hashole, *nbm;
-  int *Lfg, *Lbg, *which;
-  Contour* cont; int2 *chain, *sv; int4* rays; double* dist; uint32_t *tog, *orb; long long* verts; ExState* st;
-  int* nsv; uint8_t* flags;
-  int chain_cap, rays_cap;
-};
 constexpr int WIN_MAX = 512;
 constexpr int CHAIN_CAP = 1 << 20, RAYS_CAP = 1 << 16, MAXF = 4096;
-
 constexpr int HOLES_MAXC = 1 << 16;   // fill_small_holes sees sensor speckle: many more (tiny) contours than a map does
-size_t carve(Ws* w, uint8_t* base, int G, int maxc = EX_MAXC) {
+
+// carve one environment's arrays out of its workspace slice; `frame_cells` = cells of the largest frame (G*G or H*W)
+size_t carve(ExEnv* e, uint8_t* base, size_t frame_cells, int frame_side, int maxc, bool explore) {
   size_t o = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base ? base + o : nullptr; o += (bytes + 255) & ~(size_t)255; return p; };
-  const size_t n = (size_t)G * G, wn = (size_t)WIN_MAX * WIN_MAX;
+  const size_t wn = explore ? (size_t)WIN_MAX * WIN_MAX : 0;
+  const size_t n = frame_cells > wn ? frame_cells : wn;                // label / flag arrays serve the window images too
   uint8_t* p;
-  p = take(wn); if (w) w->cone = p;
-  p = take(wn); if (w) w->blocked = p;
-  p = take(wn); if (w) w->visible = p;
-  p = take(wn); if (w) w->cut = p;
-  p = take(wn); if (w) w->newexp = p;
-  p = take(n); if (w) w->outer = p;
-  p = take(n); if (w) w->grown = p;
-  p = take(n); if (w) w->unexp = p;
-  p = take(n); if (w) w->ex2 = p;
-  p = take(n); if (w) w->hashole = p;
-  p = take(n); if (w) w->nbm = p;
-  p = take(n * 4); if (w) w->Lfg = (int*)p;
-  p = take(n * 4); if (w) w->Lbg = (int*)p;
-  p = take(sizeof(Contour) * (size_t)maxc); if (w) w->cont = (Contour*)p;
-  p = take(sizeof(int2) * (size_t)CHAIN_CAP); if (w) w->chain = (int2*)p;
-  p = take(sizeof(int2) * (size_t)CHAIN_CAP); if (w) w->sv = (int2*)p;
-  p = take((size_t)CHAIN_CAP); if (w) w->flags = p;
-  p = take(sizeof(int) * (size_t)maxc); if (w) w->nsv = (int*)p;
-  p = take(sizeof(int4) * (size_t)RAYS_CAP); if (w) w->rays = (int4*)p;
-  p = take(sizeof(double) * EX_MAXC); if (w) w->dist = (double*)p;
-  const size_t pw = ((size_t)G + 31) / 32;
-  p = take(pw * G * 4); if (w) w->tog = (uint32_t*)p;
-  p = take(pw * G * 4); if (w) w->orb = (uint32_t*)p;
-  p = take(64 * 2 * 8); if (w) w->verts = (long long*)p;
-  p = take(sizeof(ExState)); if (w) w->st = (ExState*)p;
-  p = take(64); if (w) w->which = (int*)p;
-  if (w) { w->chain_cap = CHAIN_CAP; w->rays_cap = RAYS_CAP; }
+  p = take(wn); if (e) e->cone = p;
+  p = take(wn); if (e) e->blocked = p;
+  p = take(wn); if (e) e->visible = p;
+  p = take(wn); if (e) e->cut = p;
+  p = take(wn); if (e) e->newexp = p;
+  p = take(explore ? frame_cells : 0); if (e) e->exS = p;
+  p = take(explore ? frame_cells : 0); if (e) e->navS = p;
+  p = take(explore ? frame_cells : 0); if (e) e->grown = p;
+  p = take(frame_cells); if (e) e->unexp = p;
+  p = take(explore ? frame_cells : 0); if (e) e->ex2 = p;
+  p = take(n); if (e) e->outer = p;
+  p = take(n); if (e) e->hashole = p;
+  p = take(n); if (e) e->nbm = p;
+  p = take(n * 4); if (e) e->Lfg = (int*)p;
+  p = take(n * 4); if (e) e->Lbg = (int*)p;
+  p = take(sizeof(Contour) * (size_t)maxc); if (e) e->cont = (Contour*)p;
+  p = take(sizeof(int2) * (size_t)CHAIN_CAP); if (e) e->chain = (int2*)p;
+  p = take(explore ? sizeof(int2) * (size_t)CHAIN_CAP : 0); if (e) e->sv = (int2*)p;
+  p = take(explore ? (size_t)CHAIN_CAP : 0); if (e) e->flags = p;
+  p = take(explore ? sizeof(int) * (size_t)maxc : 0); if (e) e->nsv = (int*)p;
+  p = take(explore ? sizeof(int4) * (size_t)RAYS_CAP : 0); if (e) e->rays = (int4*)p;
+  p = take(explore ? sizeof(double) * EX_MAXC : 0); if (e) e->dist = (double*)p;
+  const int side = frame_side > WIN_MAX || !explore ? frame_side : WIN_MAX;
+  const size_t pw = ((size_t)side + 31) / 32;
+  p = take(explore ? pw * side * 4 : 0); if (e) e->tog = (uint32_t*)p;
+  p = take(explore ? pw * side * 4 : 0); if (e) e->orb = (uint32_t*)p;
+  p = take(sizeof(ExState)); if (e) e->st = (ExState*)p;
+  p = take(64); if (e) e->which = (int*)p;
+  if (e) { e->chain_cap = CHAIN_CAP; e->rays_cap = RAYS_CAP; e->maxc = maxc; e->maxf = MAXF; }
   return o;
 }
 
-inline int nblk(long n, int t = 256) { long b = (n + t - 1) / t; return (int)(b < 1 ? 1 : (b > 2368 ? 2368 : b)); }
+inline int nblk(long n, int t = 256, int cap = 2368) { long b = (n + t - 1) / t; return (int)(b < 1 ? 1 : (b > cap ? cap : b)); }
 
-// external contours of `img` (W x H): CCL fg/bg, top-level roots in cv2 order, traced chains
-void contours(const Ws& w, const uint8_t* img, int W, int H, cudaStream_t st, int keep_fog, int mode = 0) {
-  const int n = W * H;
-  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(img, w.Lfg, w.Lbg, W, H, w.st, keep_fog);
-  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(img, w.Lfg, w.Lbg, w.outer, mode == 2 ? w.hashole : nullptr, w.nbm, W, H);
-  ccl_flatten2_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, n);
-  bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
-  collect_roots_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, w.st);
-  sort_roots_kernel<<<1, 1024, 0, st>>>(w.cont, w.st);
-  if (mode == 2) mark_holes_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, w.hashole, W, H);
-  trace_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.nbm, W, H, w.cont, w.chain, w.chain_cap, w.st, mode, w.hashole);
+// external contours of image `id` of every environment: CCL fg/bg, top-level roots in cv2 order, traced chains.
+// n_max / h_max / per_max: the largest image over the environments of the call.
+void contours(const ExEnv* d_envs, int B, int id, long n_max, int h_max, int per_max, cudaStream_t st, int keep_fog, int mode, int mark_exterior) {
+  const int bx = nblk(n_max, 256, B > 8 ? 592 : 2368);
+  ccl_init2_kernel<<<dim3(nblk(h_max, 8, 592), B), 256, 0, st>>>(d_envs, id, keep_fog);
+  ccl_merge2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id, mode == 2);
+  ccl_flatten2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id);
+  bg_outer_kernel<<<dim3(nblk(per_max), B), 256, 0, st>>>(d_envs, id, mark_exterior);
+  collect_roots_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id);
+  sort_roots_kernel<<<dim3(1, B), 1024, 0, st>>>(d_envs);
+  if (mode == 2) mark_holes_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id);
+  trace_kernel<<<dim3(EX_MAXC / 64, B), 64, 0, st>>>(d_envs, id, mode);
   count_launch(mode == 2 ? 8 : 7);
 }
 
@@ -1027,121 +1193,193 @@ int sector_polygon(int cx, int cy, int radius, double start_deg, double end_deg,
   return nv;
 }
 
+
 }  // namespace
 
-extern "C" int vlfm_explore_workspace_bytes(int G, size_t* bytes) {
-  if (!bytes || G < 1) { set_error("vlfm_explore_workspace_bytes: bad argument"); return VLFM_E_INVALID; }
-  *bytes = carve(nullptr, nullptr, G);
+extern "C" size_t vlfm_explore_env_record_bytes(void) { return sizeof(ExEnv); }
+
+extern "C" int vlfm_explore_batch_workspace_bytes(int G, int batch, size_t* bytes) {
+  if (!bytes || G < 8 || batch < 1) { set_error("vlfm_explore_batch_workspace_bytes: bad argument"); return VLFM_E_INVALID; }
+  const size_t per = carve(nullptr, nullptr, (size_t)G * G, G, EX_MAXC, true);
+  *bytes = per * (size_t)batch + (((size_t)batch * sizeof(ExEnv) + 255) & ~(size_t)255);
   return VLFM_OK;
 }
 
+// Batched explore step.  h_envs: `batch` VlfmExploreEnv records (host memory).  d_explored / d_nav: [nslots, G, G] uint8.
+// d_frontiers [batch, 4096, 2] float64 (x = col, y = row), d_count / d_status [batch] int32 (in call order).
+extern "C" int vlfm_explore_update_batch(int G, int batch, const VlfmExploreEnv* h_envs, uint8_t* d_explored, const uint8_t* d_nav,
+                                         double* d_frontiers, int32_t* d_count, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                                         void* h_pinned, size_t h_pinned_bytes, void* stream) {
+  if (!h_envs || !d_explored || !d_nav || !d_frontiers || !d_count || !d_status || !d_workspace || G < 8 || batch < 1 || batch > 65535) {
+    set_error("vlfm_explore_update_batch: bad argument"); return VLFM_E_INVALID; }
+  size_t need = 0;
+  vlfm_explore_batch_workspace_bytes(G, batch, &need);
+  if (workspace_bytes < need) { set_error("vlfm_explore_update_batch: workspace %zu < %zu bytes", workspace_bytes, need); return VLFM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per = carve(nullptr, nullptr, (size_t)G * G, G, EX_MAXC, true);
+  uint8_t* wsb = (uint8_t*)d_workspace;
+  ExEnv* d_envs = (ExEnv*)(wsb + per * (size_t)batch);
+  // the environment records are staged in the caller's page-locked buffer when one is given (a pageable source makes
+  // cudaMemcpyAsync wait for the stream first)
+  std::vector<ExEnv> pageable;
+  ExEnv* envs;
+  if (h_pinned && h_pinned_bytes >= sizeof(ExEnv) * (size_t)batch) envs = (ExEnv*)h_pinned;
+  else { pageable.resize((size_t)batch); envs = pageable.data(); }
+  int w0_max = 0, sh_max = 0; long sn_max = 0; int sper_max = 0;
+  for (int b = 0; b < batch; ++b) {
+    const VlfmExploreEnv& in = h_envs[b];
+    ExEnv& e = envs[b];
+    memset(&e, 0, sizeof(ExEnv));
+    carve(&e, wsb + per * (size_t)b, (size_t)G * G, G, EX_MAXC, true);
+    const int L = (int)in.max_line_len, W0 = 2 * L + 9;
+    if (W0 > WIN_MAX || L < 1) { set_error("vlfm_explore_update_batch: max_line_len %d unsupported (window %d > %d)", L, W0, WIN_MAX); return VLFM_E_UNSUPPORTED; }
+    int x0 = in.frame[0], y0 = in.frame[1], x1 = in.frame[2], y1 = in.frame[3];
+    if (x0 < 0 || y0 < 0 || x1 > G || y1 > G || x1 - x0 < 1 || y1 - y0 < 1 || in.slot < 0) { set_error("vlfm_explore_update_batch: bad frame / slot (env %d)", b); return VLFM_E_INVALID; }
+    e.G = G;
+    e.explored = d_explored + (size_t)in.slot * G * G; e.nav = d_nav + (size_t)in.slot * G * G;
+    e.frontiers = d_frontiers + (size_t)b * MAXF * 2; e.out_count = d_count + b; e.out_status = d_status + b;
+    // the window is centred on the agent and may hang over the grid edge: cv2 clips the cone and the rays there
+    e.ox = in.agent_col - L - 4; e.oy = in.agent_row - L - 4; e.W0 = W0; e.sx = in.agent_col - e.ox; e.sy = in.agent_row - e.oy;
+    e.ax = in.agent_col; e.ay = in.agent_row;
+    e.fx0 = x0; e.fy0 = y0; e.Sw = x1 - x0; e.Sh = y1 - y0;
+    e.ext_l = x0 > 0; e.ext_t = y0 > 0; e.ext_r = x1 < G; e.ext_b = y1 < G;
+    e.heading_deg = in.heading_deg; e.ray_len = in.max_line_len * 1.05; e.area_thresh = in.area_thresh_px;
+    e.nv = sector_polygon(in.agent_col, in.agent_row, L, in.heading_deg - in.fov_deg / 2, in.heading_deg + in.fov_deg / 2, e.verts);   // R1
+    if (W0 > w0_max) w0_max = W0;
+    if (e.Sh > sh_max) sh_max = e.Sh;
+    if ((long)e.Sw * e.Sh > sn_max) sn_max = (long)e.Sw * e.Sh;
+    if (2 * (e.Sw + e.Sh) > sper_max) sper_max = 2 * (e.Sw + e.Sh);
+  }
+  int rc = check_cuda(cudaMemcpyAsync(d_envs, envs, sizeof(ExEnv) * (size_t)batch, cudaMemcpyHostToDevice, st), "explore: environment records");
+  if (rc) return rc;
+  const int B = batch;
+  const long wn = (long)w0_max * w0_max;
+  const int capx = B > 8 ? 592 : 2368;
+  const int bw = nblk(wn, 256, capx), bs = nblk(sn_max, 256, capx);
+  // ---- R1: cone sector (window)
+  zero_planes_kernel<<<dim3(nblk((long)((w0_max + 31) / 32) * w0_max), B), 256, 0, st>>>(d_envs, FRAME_WIN);
+  sector_edges_kernel<<<dim3(1, B), 64, 0, st>>>(d_envs);
+  planes_to_image_kernel<<<dim3(nblk(w0_max, 64), B), 64, 0, st>>>(d_envs, 0, 1, 0);
+  fog_masks_kernel<<<dim3(bw, B), 256, 0, st>>>(d_envs);
+  // ---- R2/R3/R4: obstacle contours -> rays -> cut
+  contours(d_envs, B, IMG_BLOCKED, wn, w0_max, 4 * w0_max, st, 0, 0, 0);
+  fog_gate_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs);
+  simple_vertices_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
+  rays_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
+  thick_rays_kernel<<<dim3(64, B), 64, 0, st>>>(d_envs);
+  apply_cut_kernel<<<dim3(bw, B), 256, 0, st>>>(d_envs);
+  // ---- R5: contours of the visible area, nearest to the agent, filled
+  contours(d_envs, B, IMG_VISIBLE, wn, w0_max, 4 * w0_max, st, 1, 0, 0);
+  contour_dist_kernel<<<dim3(EX_MAXC / 64, B), 64, 0, st>>>(d_envs, 0);
+  contour_pick_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs, 0);
+  zero_planes_kernel<<<dim3(nblk((long)((w0_max + 31) / 32) * w0_max), B), 256, 0, st>>>(d_envs, FRAME_WIN);
+  chain_edges_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, FRAME_WIN);
+  planes_to_image_kernel<<<dim3(nblk(w0_max, 64), B), 64, 0, st>>>(d_envs, 1, 0, 1);
+  // ---- explored |= dilate3(new); explored[nav == 0] = 0  -> S frame images
+  explored_update_kernel<<<dim3(bs, B), 256, 0, st>>>(d_envs);
+  // ---- component selection (obstacle_map.py:128-146)
+  contours(d_envs, B, IMG_EXS, sn_max, sh_max, sper_max, st, 1, 1, 0);
+  contour_dist_kernel<<<dim3(EX_MAXC / 64, B), 64, 0, st>>>(d_envs, 1);
+  contour_pick_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs, 1);
+  {
+    int sw_max = 0;
+    for (int b = 0; b < batch; ++b) if (envs[b].Sw > sw_max) sw_max = envs[b].Sw;
+    zero_planes_kernel<<<dim3(nblk((long)((sw_max + 31) / 32) * sh_max), B), 256, 0, st>>>(d_envs, FRAME_S);
+  }
+  chain_edges_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs, FRAME_S);
+  planes_to_image_kernel<<<dim3(nblk(sh_max, 64), B), 64, 0, st>>>(d_envs, 2, 1, 1);   // no-op when a single contour exists (which == -1)
+  // ---- frontiers (obstacle_map.py:155-169 -> detect_frontier_waypoints)
+  paste_grow_kernel<<<dim3(bs, B), 256, 0, st>>>(d_envs);
+  contours(d_envs, B, IMG_UNEXP, sn_max, sh_max, sper_max, st, 1, 2, 1);
+  absorb_small_kernel<<<dim3(128, B), 128, 0, st>>>(d_envs);
+  contours(d_envs, B, IMG_EX2, sn_max, sh_max, sper_max, st, 1, 1, 0);
+  bad_flags_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
+  frontier_kernel<<<dim3(1, B), FRONTIER_THREADS, 0, st>>>(d_envs);
+  publish_kernel<<<B, 32, 0, st>>>(d_envs, 0);
+  VLFM_CHECK_LAUNCH("vlfm_explore_update_batch");
+  count_launch(26);
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_explore_workspace_bytes(int G, size_t* bytes) { return vlfm_explore_batch_workspace_bytes(G, 1, bytes); }
+
+// one environment, whole-grid S frame (kept for callers that hold a single [G,G] pair)
 extern "C" int vlfm_explore_update(int G, uint8_t* d_explored, const uint8_t* d_nav, int agent_col, int agent_row, double heading_deg,
                                    double fov_deg, double max_line_len, double area_thresh_px, int nav_half, double* d_frontiers,
                                    int32_t* d_count, void* d_workspace, int32_t* d_status, void* stream) {
-  if (!d_explored || !d_nav || !d_frontiers || !d_count || !d_workspace || !d_status || G < 8) { set_error("vlfm_explore_update: bad argument"); return VLFM_E_INVALID; }
-  const int L = (int)max_line_len, W0 = 2 * L + 9;
-  if (W0 > WIN_MAX) { set_error("vlfm_explore_update: max_line_len %d too large (window %d > %d)", L, W0, WIN_MAX); return VLFM_E_UNSUPPORTED; }
-  // the window is centred on the agent and may hang over the grid edge: cv2 clips the cone and the rays there
-  // (clip_line rules above), cells outside the grid are masked out of the window images
-  const int ox = agent_col - L - 4, oy = agent_row - L - 4;
-  cudaStream_t st = (cudaStream_t)stream;
-  Ws w;
-  carve(&w, (uint8_t*)d_workspace, G);
-  const int n = G * G, wn = W0 * W0, pw0 = (W0 + 31) / 32, pwG = (G + 31) / 32;
-  const int sx = agent_col - ox, sy = agent_row - oy;
-
-  // ---- R1: cone sector (window)
-  long long hv[128];
-  const int nv = sector_polygon(agent_col, agent_row, L, heading_deg - fov_deg / 2, heading_deg + fov_deg / 2, hv);
-  int rc = check_cuda(cudaMemcpyAsync(w.verts, hv, sizeof(long long) * 2 * nv, cudaMemcpyHostToDevice, st), "explore: vertex upload");
+  (void)nav_half;
+  VlfmExploreEnv e;
+  e.slot = 0; e.agent_col = agent_col; e.agent_row = agent_row; e.frame[0] = 0; e.frame[1] = 0; e.frame[2] = G; e.frame[3] = G; e.pad = 0;
+  e.heading_deg = heading_deg; e.fov_deg = fov_deg; e.max_line_len = max_line_len; e.area_thresh_px = area_thresh_px;
+  size_t ws = 0;
+  int rc = vlfm_explore_batch_workspace_bytes(G, 1, &ws);
   if (rc) return rc;
-  zero_planes_kernel<<<nblk(pw0 * W0), 256, 0, st>>>(w.tog, w.orb, pw0 * W0);
-  sector_edges_kernel<<<1, 64, 0, st>>>(w.verts, nv, ox, oy, G, G, w.tog, w.orb, W0, W0, pw0);
-  planes_to_image_kernel<<<nblk(W0, 64), 64, 0, st>>>(w.tog, w.orb, w.cone, W0, W0, pw0, 1, 1, nullptr);
-  fog_masks_kernel<<<nblk(wn), 256, 0, st>>>(w.cone, d_nav, G, ox, oy, W0, w.blocked, w.visible);
-  // ---- R2/R3/R4: obstacle contours -> rays -> cut
-  contours(w, w.blocked, W0, W0, st, 0);
-  fog_gate_kernel<<<1, 1, 0, st>>>(w.st);
-  simple_vertices_kernel<<<EX_MAXC / 8, 256, 0, st>>>(w.cont, w.chain, w.sv, w.nsv, w.st);
-  rays_kernel<<<EX_MAXC / 8, 256, 0, st>>>(w.cont, w.sv, w.nsv, w.rays, w.rays_cap, sx, sy, ox, oy, heading_deg, max_line_len * 1.05, w.st);
-  clear_bytes_kernel<<<nblk(wn), 256, 0, st>>>(w.cut, wn);
-  thick_rays_kernel<<<RAYS_CAP / 64, 64, 0, st>>>(w.rays, w.cut, W0, W0, ox, oy, G, w.st);
-  apply_cut_kernel<<<nblk(wn), 256, 0, st>>>(w.visible, w.cut, wn, w.st);
-  // ---- R5: contours of the visible area, nearest to the agent, filled
-  contours(w, w.visible, W0, W0, st, 1);
-  pick_nearest_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.cont, w.chain, w.dist, sx, sy, w.st, 0);
-  pick_nearest_kernel<<<1, 1, 0, st>>>(w.cont, w.chain, w.dist, sx, sy, w.st, 1);
-  fog_fill_gate_kernel<<<1, 1, 0, st>>>(w.st, w.which);
-  clear_bytes_kernel<<<nblk(wn), 256, 0, st>>>(w.newexp, wn);
-  zero_planes_kernel<<<nblk(pw0 * W0), 256, 0, st>>>(w.tog, w.orb, pw0 * W0);
-  chain_edges_kernel<<<dim3(32, 1), 256, 0, st>>>(w.cont, w.which, w.chain, w.tog, w.orb, W0, W0, pw0, w.st);
-  planes_to_image_kernel<<<nblk(W0, 64), 64, 0, st>>>(w.tog, w.orb, w.newexp, W0, W0, pw0, 1, 0, w.which + 0);
-  // ---- explored |= dilate3(new); explored[nav == 0] = 0
-  int half = nav_half > L + 5 ? nav_half : L + 5;
-  int rx0 = agent_col - half, ry0 = agent_row - half, rx1 = agent_col + half + 1, ry1 = agent_row + half + 1;
-  if (rx0 < 0) rx0 = 0; if (ry0 < 0) ry0 = 0; if (rx1 > G) rx1 = G; if (ry1 > G) ry1 = G;
-  explored_update_kernel<<<nblk((long)(rx1 - rx0) * (ry1 - ry0)), 256, 0, st>>>(w.newexp, W0, ox, oy, d_explored, d_nav, G, rx0, ry0, rx1 - rx0,
-                                                                              ry1 - ry0, w.st);
-  // ---- component selection on the whole explored map (obstacle_map.py:128-146)
-  contours(w, d_explored, G, G, st, 1, 1);
-  select_component_kernel<<<EX_MAXC / 64, 64, 0, st>>>(w.cont, w.chain, w.dist, agent_col, agent_row, w.st, w.which, 0);
-  select_component_kernel<<<1, 1, 0, st>>>(w.cont, w.chain, w.dist, agent_col, agent_row, w.st, w.which, 1);
-  zero_planes_kernel<<<nblk(pwG * G), 256, 0, st>>>(w.tog, w.orb, pwG * G);
-  chain_edges_kernel<<<dim3(64, 1), 256, 0, st>>>(w.cont, w.which, w.chain, w.tog, w.orb, G, G, pwG, w.st);
-  planes_to_image_kernel<<<nblk(G, 64), 64, 0, st>>>(w.tog, w.orb, d_explored, G, G, pwG, 1, 1, w.which);   // no-op when a single contour exists (which == -1)
-  // ---- frontiers (obstacle_map.py:155-169 -> detect_frontier_waypoints)
-  dilate_full_kernel<<<nblk(n), 256, 0, st>>>(d_explored, w.grown, G, G, 5);
-  unexplored_kernel<<<nblk(n), 256, 0, st>>>(d_nav, w.grown, w.unexp, n);
-  copy_bytes_kernel<<<nblk(n), 256, 0, st>>>(w.grown, w.ex2, n);
-  contours(w, w.unexp, G, G, st, 1, 2);
-  absorb_small_kernel<<<EX_MAXC, 128, 0, st>>>(w.cont, w.chain, w.unexp, w.ex2, G, G, area_thresh_px, w.st);
-  contours(w, w.ex2, G, G, st, 1);
-  bad_flags_kernel<<<nblk(CHAIN_CAP / 64), 256, 0, st>>>(w.chain, d_nav, w.ex2, G, G, w.flags, w.st);
-  frontier_kernel<<<1, 32, 0, st>>>(w.cont, w.chain, w.flags, d_frontiers, MAXF, w.st);
-  rc = check_cuda(cudaMemcpyAsync(d_count, &w.st->n_front, sizeof(int), cudaMemcpyDeviceToDevice, st), "explore: count");
-  if (rc) return rc;
-  rc = check_cuda(cudaMemcpyAsync(d_status, &w.st->overflow, sizeof(int), cudaMemcpyDeviceToDevice, st), "explore: status");
-  if (rc) return rc;
-  VLFM_CHECK_LAUNCH("vlfm_explore_update");
-  count_launch(40);
-  return VLFM_OK;
+  return vlfm_explore_update_batch(G, 1, &e, d_explored, d_nav, d_frontiers, d_count, d_status, d_workspace, ws, nullptr, 0, stream);
 }
 
-extern "C" int vlfm_holes_workspace_bytes(int H, int W, size_t* bytes) {
-  if (!bytes || H < 1 || W < 1) { set_error("vlfm_holes_workspace_bytes: bad argument"); return VLFM_E_INVALID; }
-  int G = H > W ? H : W;
-  *bytes = carve(nullptr, nullptr, G, HOLES_MAXC);
+extern "C" int vlfm_holes_batch_workspace_bytes(int H, int W, int batch, size_t* bytes) {
+  if (!bytes || H < 1 || W < 1 || batch < 1) { set_error("vlfm_holes_batch_workspace_bytes: bad argument"); return VLFM_E_INVALID; }
+  const size_t per = carve(nullptr, nullptr, (size_t)H * W, H > W ? H : W, HOLES_MAXC, false);
+  *bytes = per * (size_t)batch + (((size_t)batch * sizeof(ExEnv) + 255) & ~(size_t)255);
   return VLFM_OK;
 }
+extern "C" int vlfm_holes_workspace_bytes(int H, int W, size_t* bytes) { return vlfm_holes_batch_workspace_bytes(H, W, 1, bytes); }
 
-// fill_small_holes (vlfm/utils/img_utils.py:361-390): d_filled[H,W] := 1 where the reference would write depth 1.0
-extern "C" int vlfm_fill_small_holes(const float* d_depth, int H, int W, double area_thresh, uint8_t* d_filled, void* d_workspace,
-                                     int32_t* d_status, void* stream) {
-  if (!d_depth || !d_filled || !d_workspace || !d_status || H < 1 || W < 1) { set_error("vlfm_fill_small_holes: bad argument"); return VLFM_E_INVALID; }
+// fill_small_holes (vlfm/utils/img_utils.py:361-390) for a batch of depth images: d_filled[b,H,W] := 1 where the reference
+// would write depth 1.0.  d_status [batch]: sticky overflow flags.
+extern "C" int vlfm_fill_small_holes_batch(const float* d_depth, int H, int W, int batch, double area_thresh, uint8_t* d_filled, void* d_workspace,
+                                           size_t workspace_bytes, int32_t* d_status, void* h_pinned, size_t h_pinned_bytes, void* stream) {
+  if (!d_depth || !d_filled || !d_workspace || !d_status || H < 1 || W < 1 || batch < 1 || batch > 65535) { set_error("vlfm_fill_small_holes_batch: bad argument"); return VLFM_E_INVALID; }
+  size_t need = 0;
+  vlfm_holes_batch_workspace_bytes(H, W, batch, &need);
+  if (workspace_bytes < need) { set_error("vlfm_fill_small_holes_batch: workspace %zu < %zu bytes", workspace_bytes, need); return VLFM_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  Ws w;
-  carve(&w, (uint8_t*)d_workspace, H > W ? H : W, HOLES_MAXC);
-  const int n = H * W;
-  uint8_t* mask = w.unexp;                       // scratch planes of the explore workspace layout
-  zero_mask_kernel<<<nblk(n), 256, 0, st>>>(d_depth, mask, n);
-  clear_bytes_kernel<<<nblk(n), 256, 0, st>>>(d_filled, n);
-  ccl_init2_kernel<<<nblk(H, 8), 256, 0, st>>>(mask, w.Lfg, w.Lbg, W, H, w.st, 0);
-  ccl_merge2_kernel<<<nblk(n), 256, 0, st>>>(mask, w.Lfg, w.Lbg, w.outer, nullptr, w.nbm, W, H);
-  ccl_flatten2_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, n);
-  bg_outer_kernel<<<nblk(2 * (W + H)), 256, 0, st>>>(w.Lbg, w.outer, W, H);
-  collect_all_kernel<<<nblk(n), 256, 0, st>>>(w.Lfg, w.Lbg, w.outer, W, H, w.cont, HOLES_MAXC, w.st);
-  trace_kernel<<<HOLES_MAXC / 64, 64, 0, st>>>(w.nbm, W, H, w.cont, w.chain, w.chain_cap, w.st, 0, w.hashole);
+  const size_t per = carve(nullptr, nullptr, (size_t)H * W, H > W ? H : W, HOLES_MAXC, false);
+  uint8_t* wsb = (uint8_t*)d_workspace;
+  ExEnv* d_envs = (ExEnv*)(wsb + per * (size_t)batch);
+  std::vector<ExEnv> pageable;
+  ExEnv* envs;
+  if (h_pinned && h_pinned_bytes >= sizeof(ExEnv) * (size_t)batch) envs = (ExEnv*)h_pinned;
+  else { pageable.resize((size_t)batch); envs = pageable.data(); }
+  for (int b = 0; b < batch; ++b) {
+    ExEnv& e = envs[b];
+    memset(&e, 0, sizeof(ExEnv));
+    carve(&e, wsb + per * (size_t)b, (size_t)H * W, H > W ? H : W, HOLES_MAXC, false);
+    e.G = W; e.Sw = W; e.Sh = H; e.W0 = 1;
+    e.depth = d_depth + (size_t)b * H * W; e.filled = d_filled + (size_t)b * H * W; e.out_status = d_status + b; e.out_count = d_status + b;
+    e.area_thresh = area_thresh;
+  }
+  int rc = check_cuda(cudaMemcpyAsync(d_envs, envs, sizeof(ExEnv) * (size_t)batch, cudaMemcpyHostToDevice, st), "holes: environment records");
+  if (rc) return rc;
+  const int B = batch;
+  const long n = (long)H * W;
+  const int bx = nblk(n, 256, B > 8 ? 592 : 2368);
+  zero_mask_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs);
+  ccl_init2_kernel<<<dim3(nblk(H, 8, 592), B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
+  ccl_merge2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
+  ccl_flatten2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, IMG_UNEXP);
+  bg_outer_kernel<<<dim3(nblk(2 * (W + H)), B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
+  collect_all_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs);
+  trace_kernel<<<dim3(128, B), 64, 0, st>>>(d_envs, IMG_UNEXP, 0);
   static bool cfg = false;
   const int smem_words = 24 * 1024;             // 96 KB of toggle / outline bit planes per block
   if (!cfg) {
-    int rc = check_cuda(cudaFuncSetAttribute(fill_small_contours_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_words * 4), "attr(fill_small_contours)");
+    rc = check_cuda(cudaFuncSetAttribute(fill_small_contours_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_words * 4), "attr(fill_small_contours)");
     if (rc) return rc; cfg = true;
   }
-  fill_small_contours_kernel<<<148 * 2, 256, smem_words * 4, st>>>(w.cont, w.chain, d_filled, W, H, area_thresh, smem_words, HOLES_MAXC, w.st);
-  sticky_status_kernel<<<1, 1, 0, st>>>(w.st, d_status);      // sticky: the host may poll it many steps later
-  VLFM_CHECK_LAUNCH("vlfm_fill_small_holes");
-  count_launch(11);
+  const int fb = B >= 8 ? 37 : (B >= 2 ? 148 : 296);
+  fill_small_contours_kernel<<<dim3(fb, B), 256, smem_words * 4, st>>>(d_envs, smem_words);
+  publish_kernel<<<B, 32, 0, st>>>(d_envs, 1);      // sticky: the host may poll it many steps later
+  VLFM_CHECK_LAUNCH("vlfm_fill_small_holes_batch");
+  count_launch(10);
   return VLFM_OK;
+}
+extern "C" int vlfm_fill_small_holes(const float* d_depth, int H, int W, double area_thresh, uint8_t* d_filled, void* d_workspace,
+                                     int32_t* d_status, void* stream) {
+  size_t ws = 0;
+  int rc = vlfm_holes_batch_workspace_bytes(H, W, 1, &ws);
+  if (rc) return rc;
+  return vlfm_fill_small_holes_batch(d_depth, H, W, 1, area_thresh, d_filled, d_workspace, ws, d_status, nullptr, 0, stream);
 }
 
 // Confidence-cone template of ValueMap (vlfm/mapping/value_map.py:321-355 `_get_confidence_mask` / `_get_blank_cone_mask`):
@@ -1158,13 +1396,13 @@ extern "C" int vlfm_value_cone_template(double fov, double max_depth, int ppm, d
   uint32_t* orb = tog + (size_t)R * pw;
   long long* verts = (long long*)(orb + (size_t)R * pw);
   const double deg = fov * 180.0 / 3.14159265358979323846;       // np.rad2deg
-  long long hv[128];
+  long long hv[2 * MAXV];
   const int nv = sector_polygon(half, half, half, -deg / 2 + 90, deg / 2 + 90, hv);
   int rc = check_cuda(cudaMemcpyAsync(verts, hv, sizeof(long long) * 2 * nv, cudaMemcpyHostToDevice, st), "cone template: vertex upload");
   if (rc) return rc;
-  zero_planes_kernel<<<nblk((long)pw * R), 256, 0, st>>>(tog, orb, pw * R);
-  sector_edges_kernel<<<1, 64, 0, st>>>(verts, nv, 0, 0, R, R, tog, orb, R, R, pw);
-  planes_to_image_kernel<<<nblk(R, 64), 64, 0, st>>>(tog, orb, sector, R, R, pw, 1, 1, nullptr);
+  zero_planes_plain_kernel<<<nblk((long)pw * R), 256, 0, st>>>(tog, orb, pw * R);
+  sector_edges_plain_kernel<<<1, 64, 0, st>>>(verts, nv, R, tog, orb, pw);
+  planes_to_image_plain_kernel<<<nblk(R, 64), 64, 0, st>>>(tog, orb, sector, R, R, pw);
   cone_template_kernel<<<nblk((long)R * R), 256, 0, st>>>(sector, d_out, R, fov, min_conf);
   rc = check_cuda(cudaStreamSynchronize(st), "cone template");   // hv is a stack buffer: the upload must finish before returning
   if (rc) return rc;

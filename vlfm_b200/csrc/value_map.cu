@@ -36,6 +36,7 @@
 namespace vlfm {
 
 constexpr int K1_THREADS = 256;
+constexpr int GEOM_THREADS = 1024;
 constexpr int K1_ROWS = 32;   // rows per chunk: 8 warps x 4 rows
 constexpr int K1_COLS = 128;  // 32 lanes x float4
 constexpr int K2_THREADS = 256;
@@ -126,6 +127,7 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
   uint32_t* wsb = ws + (size_t)b * p.wsWords;
   float* partial = reinterpret_cast<float*>(wsb);
   const float* img = depth + (size_t)b * p.H * p.W;
+  pdl_trigger();
 
   // ---- phase 1: column max over this block's 32 x 128 tile
   {
@@ -216,18 +218,18 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
     }
   }
 
-  // ---- last block of this environment?
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    unsigned t = atomicAdd(&wsb[p.offCounter], 1u);
-    s_last = (t == gridDim.x * gridDim.y - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (tid == 0) wsb[p.offCounter] = 0;  // re-arm for the next step
+}
+
+// K1b: one 1024-thread block per environment turns the column maxima into the occlusion polygon and rasterises it into the kill
+// bitmap.  Launched with programmatic dependent launch: the shared-memory planes are cleared while K1a drains.
+__global__ void __launch_bounds__(GEOM_THREADS)
+value_geom_kernel(ValueDev p, const double* __restrict__ tanv, uint32_t* __restrict__ ws) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t* wsb = ws + (size_t)b * p.wsWords;
+  const float* partial = reinterpret_cast<const float*>(wsb);
+  pdl_trigger();
 
   // ---- phase 2: geometry blob (one block per environment)
   const int R = p.R, W = p.W, WPR = p.WPR, E = W + 2;
@@ -236,9 +238,9 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
   uint32_t* orb = tog + R * WPR;                               // [R*WPR]
   int* longList = reinterpret_cast<int*>(orb + R * WPR);       // [E]
   __shared__ int s_nlong;
-  __syncthreads();  // phase-1 smem no longer read
 
-  for (int i = tid; i < R * WPR; i += K1_THREADS) { tog[i] = 0; orb[i] = 0; }
+  for (int i = tid; i < R * WPR; i += GEOM_THREADS) { tog[i] = 0; orb[i] = 0; }
+  pdl_wait();                                                  // the column maxima of K1a are visible from here on
   if (tid == 0) {
     s_nlong = 0;
     verts[0] = make_int2(0, R - 1);          // start = [[0, last_col]]  (value_map.py:255)
@@ -246,7 +248,7 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
   }
   const float half_f = (float)((double)R * 0.5);
   const double half_d = (double)R * 0.5;
-  for (int i = tid; i < W; i += K1_THREADS) {
+  for (int i = tid; i < W; i += GEOM_THREADS) {
     float m = ld_cg_f32(&partial[i]);
     for (int ch = 1; ch < p.nChunks; ++ch) m = fmaxf(m, ld_cg_f32(&partial[ch * W + i]));
     float far = __fadd_rn(__fmul_rn(m, p.dscale), p.doff);                   // :234 float32
@@ -258,7 +260,7 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
   __syncthreads();
 
   // edges: thread-per-edge for short ones, warp-cooperative for long ones
-  for (int e = tid; e < E; e += K1_THREADS) {
+  for (int e = tid; e < E; e += GEOM_THREADS) {
     int2 A = verts[e], B = verts[e + 1 == E ? 0 : e + 1];
     LineWalk lw(A.x, A.y, B.x, B.y);
     int dyabs = A.y > B.y ? A.y - B.y : B.y - A.y;
@@ -285,7 +287,7 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
     }
   }
   __syncthreads();
-  for (int li = warp; li < s_nlong; li += K1_THREADS / 32) {
+  for (int li = warp; li < s_nlong; li += GEOM_THREADS / 32) {
     int e = longList[li];
     int2 A = verts[e], B = verts[e + 1 == E ? 0 : e + 1];
     LineWalk lw(A.x, A.y, B.x, B.y);
@@ -303,7 +305,7 @@ value_depth_geom_kernel(ValueDev p, const float* __restrict__ depth, const doubl
 
   // publish the kill bitmap
   uint32_t* kill = wsb + p.offKill;
-  for (int r = tid; r < R; r += K1_THREADS) {
+  for (int r = tid; r < R; r += GEOM_THREADS) {
     uint32_t carry = 0;
     for (int w = 0; w < WPR; ++w) {
       uint32_t t = tog[r * WPR + w];
@@ -380,6 +382,7 @@ value_cone_fuse_kernel(ValueDev p, const int* __restrict__ slot, float* __restri
   extern __shared__ __align__(16) uint32_t smem[];
   const int b = blockIdx.y, tid = threadIdx.x;
   const uint32_t* wsb = ws + (size_t)b * p.wsWords;
+  pdl_wait();                                                  // geometry blob of K1a / K1b
   const int px = (int)wsb[p.offHeader + 0], py = (int)wsb[p.offHeader + 1];
   if (!wsb[p.offHeader + 2]) return;
   const int R = p.R, G = p.G, C = p.C, WPR = p.WPR;
@@ -473,12 +476,14 @@ __global__ void value_mask_unexplored_kernel(int G, int C, const int* __restrict
 // one block per (point, channel); bitonic sort of the <= CAP candidate values (CAP = 1024: radius <= 15 cells, 4096: <= 31).
 template <int CAP>
 __global__ void __launch_bounds__(256)
-value_disc_median_kernel(int G, int C, const float* __restrict__ valueS, const int* __restrict__ pts,
+value_disc_median_kernel(int G, int C, const float* __restrict__ valueAll, const int* __restrict__ pts, int with_slot,
                          int radius, const uint8_t* __restrict__ disc, double* __restrict__ out) {
   __shared__ float vals[CAP];
   __shared__ int s_n;
   const int pi = blockIdx.x, ch = blockIdx.y, tid = threadIdx.x;
-  const int row = pts[2 * pi], col = pts[2 * pi + 1];
+  // points are (row, col) or, for the batched entry, (slot, row, col): one launch scores the frontiers of every environment
+  const int row = with_slot ? pts[3 * pi + 1] : pts[2 * pi], col = with_slot ? pts[3 * pi + 2] : pts[2 * pi + 1];
+  const float* valueS = valueAll + (with_slot ? (size_t)pts[3 * pi] * G * G * C : 0);
   if (tid == 0) s_n = 0;
   for (int i = tid; i < CAP; i += 256) vals[i] = INFINITY;
   __syncthreads();
@@ -555,7 +560,7 @@ extern "C" int vlfm_value_update(const VlfmValueParams* p, int batch, const int3
   if (sm1 > 200 * 1024 || sm2 > 200 * 1024) { set_error("vlfm_value_update: template too large for shared memory"); return VLFM_E_UNSUPPORTED; }
   static size_t cfg1 = 0, cfg2 = 0;
   if (sm1 > 48 * 1024 && sm1 > cfg1) {
-    int rc = check_cuda(cudaFuncSetAttribute(value_depth_geom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1), "cudaFuncSetAttribute(K1)");
+    int rc = check_cuda(cudaFuncSetAttribute(value_geom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1), "cudaFuncSetAttribute(K1b)");
     if (rc) return rc; cfg1 = sm1;
   }
   if (sm2 > 48 * 1024 && sm2 > cfg2) {
@@ -563,8 +568,12 @@ extern "C" int vlfm_value_update(const VlfmValueParams* p, int batch, const int3
     if (rc) return rc; cfg2 = sm2;
   }
   dim3 g1(d.nColTiles, d.nChunks, batch);
-  value_depth_geom_kernel<<<g1, K1_THREADS, sm1, st>>>(d, d_depth, d_tf, d_tan, (uint32_t*)d_workspace, d_status);
+  value_depth_geom_kernel<<<g1, K1_THREADS, 8 * K1_COLS * 4, st>>>(d, d_depth, d_tf, d_tan, (uint32_t*)d_workspace, d_status);
   VLFM_CHECK_LAUNCH("value_depth_geom_kernel");
+  {
+    int rc = check_cuda(launch_pdl(value_geom_kernel, dim3(batch), dim3(GEOM_THREADS), sm1, st, d, d_tan, (uint32_t*)d_workspace), "value_geom_kernel");
+    if (rc) return rc;
+  }
   int rpt = p->rows_per_tile;
   if (rpt <= 0) {
     // aim for >= ~2 waves of 148 SMs while keeping the per-block blob load amortised
@@ -575,10 +584,12 @@ extern "C" int vlfm_value_update(const VlfmValueParams* p, int batch, const int3
     if (rpt < 4) rpt = 4;
   }
   dim3 g2((d.R + rpt - 1) / rpt, batch);
-  value_cone_fuse_kernel<<<g2, K2_THREADS, sm2, st>>>(d, d_slot, d_conf, d_value, d_values, d_template,
-                                                     d_explored, (const uint32_t*)d_workspace, rpt);
-  VLFM_CHECK_LAUNCH("value_cone_fuse_kernel");
-  count_launch(2);
+  {
+    int rc = check_cuda(launch_pdl(value_cone_fuse_kernel, g2, dim3(K2_THREADS), sm2, st, d, d_slot, d_conf, d_value, d_values, d_template,
+                                   d_explored, (const uint32_t*)d_workspace, rpt), "value_cone_fuse_kernel");
+    if (rc) return rc;
+  }
+  count_launch(3);
   return VLFM_OK;
 }
 
@@ -602,10 +613,23 @@ extern "C" int vlfm_value_disc_median(int G, int C, int slot, const float* d_val
   dim3 g(npoints, C);
   if (radius <= 15)
     value_disc_median_kernel<1024><<<g, 256, 0, (cudaStream_t)stream>>>(G, C, d_value + (size_t)slot * G * G * C,
-                                                                       d_points, radius, d_disc, d_out);
+                                                                       d_points, 0, radius, d_disc, d_out);
   else
     value_disc_median_kernel<4096><<<g, 256, 0, (cudaStream_t)stream>>>(G, C, d_value + (size_t)slot * G * G * C,
-                                                                       d_points, radius, d_disc, d_out);
+                                                                       d_points, 0, radius, d_disc, d_out);
+  VLFM_CHECK_LAUNCH("value_disc_median_kernel");
+  count_launch();
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_value_disc_median_batch(int G, int C, const float* d_value, const int32_t* d_points_srl, int npoints, int radius,
+                                            const uint8_t* d_disc, double* d_out, void* stream) {
+  if (!d_value || !d_points_srl || !d_disc || !d_out || radius < 0 || radius > 31 || C < 1) {
+    set_error("vlfm_value_disc_median_batch: bad argument (radius must be <= 31 cells)"); return VLFM_E_INVALID; }
+  if (npoints <= 0) return VLFM_OK;
+  dim3 g(npoints, C);
+  if (radius <= 15) value_disc_median_kernel<1024><<<g, 256, 0, (cudaStream_t)stream>>>(G, C, d_value, d_points_srl, 1, radius, d_disc, d_out);
+  else value_disc_median_kernel<4096><<<g, 256, 0, (cudaStream_t)stream>>>(G, C, d_value, d_points_srl, 1, radius, d_disc, d_out);
   VLFM_CHECK_LAUNCH("value_disc_median_kernel");
   count_launch();
   return VLFM_OK;

@@ -1,0 +1,240 @@
+"""B environments' obstacle / navigable / explored grids in one set of tensors; one launch SEQUENCE per step for all of them.
+
+Reference: vlfm/mapping/obstacle_map.py:55-169 (``ObstacleMap.update_map`` + ``_get_frontiers``), one instance per environment
+in the reference (base_objectnav_policy.py:86-92); the environments are independent, so a vectorised
+caller updates them together: fill_small_holes (10 launches), obstacle scatter + dilate (2), explore half + frontiers (~60) --
+for the whole batch.  ``ObstacleMap`` (obstacle_map.py here) is the batch-1 instance behind the reference's class surface.
+
+Host-side state per environment: whether the navigable map exists yet, and the COVER rectangle -- the union of every
+obstacle-update window and every fog-of-war window of the episode -- from which the S frame of the explore step is derived
+(csrc/explore.cu, include/vlfm_b200.h ``VlfmExploreEnv.frame``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+MAX_FRONTIERS = 4096
+S_MARGIN = 8
+
+
+def wrap_heading(h: float) -> float:
+    return (h + np.pi) % (2 * np.pi) - np.pi
+
+
+class ObstacleMapBatch:
+    def __init__(self, batch: int, min_height: float, max_height: float, agent_radius: float, area_thresh: float = 3.0,
+                 hole_area_thresh: int = 100000, size: int = 1000, pixels_per_meter: int = 20,
+                 device: Union[str, torch.device, None] = None) -> None:
+        if not torch.cuda.is_available():
+            raise _lib.VlfmError("vlfm_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        self.batch, self.size, self.ppm = batch, size, pixels_per_meter
+        dev = self.device
+        self.obst = torch.zeros((batch, size, size), dtype=torch.uint8, device=dev)
+        self.nav = torch.zeros((batch, size, size), dtype=torch.uint8, device=dev)
+        self.explored = torch.zeros((batch, size, size), dtype=torch.uint8, device=dev)
+        self.status = torch.zeros((batch,), dtype=torch.int32, device=dev)          # scatter out of bounds (IndexError in the reference)
+        self.min_height, self.max_height = min_height, max_height
+        self.area_thresh_px = area_thresh * (pixels_per_meter ** 2)                 # obstacle_map.py:41
+        self.hole_area_thresh = hole_area_thresh
+        k = pixels_per_meter * agent_radius * 2                                     # :43-46
+        self.kernel = int(k) + (int(k) % 2 == 0)
+        self.nav_valid = [False] * batch
+        self.cover: List[Optional[Tuple[int, int, int, int]]] = [None] * batch
+        # explore outputs, indexed by SLOT
+        self.frontiers = torch.zeros((batch, MAX_FRONTIERS, 2), dtype=torch.float64, device=dev)
+        self.count = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        self.ex_status = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        self._call_front = torch.zeros((batch, MAX_FRONTIERS, 2), dtype=torch.float64, device=dev)   # call-order staging
+        self._call_count = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        self._call_status = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        n = ctypes.c_size_t(0)
+        _lib.check(self.lib.vlfm_explore_batch_workspace_bytes(size, batch, ctypes.byref(n)), "vlfm_explore_batch_workspace_bytes")
+        self._ex_ws = torch.zeros((n.value + 3) // 4, dtype=torch.int32, device=dev)
+        rec = int(self.lib.vlfm_explore_env_record_bytes())
+        self._pin = [torch.zeros(rec * batch, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._pin_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self._pin_used = [False, False]
+        self._pin_i = 0
+        self._envs = (_lib.ExploreEnv * batch)()
+        self._fill: Optional[torch.Tensor] = None
+        self._fill_ws: Optional[torch.Tensor] = None
+        self._fill_status = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        self._slot_ids = torch.arange(batch, dtype=torch.int32, device=dev)
+
+    # ---------------------------------------------------------------- helpers ----
+    def _pinned(self) -> torch.Tensor:
+        i = self._pin_i
+        self._pin_i ^= 1
+        if self._pin_used[i]:
+            self._pin_ev[i].synchronize()       # the copy issued from this buffer two calls ago has executed
+        self._pin_used[i] = True
+        self._cur_pin = i
+        return self._pin[i]
+
+    def _pinned_done(self) -> None:
+        self._pin_ev[self._cur_pin].record()
+
+    def xy_to_px(self, xy: np.ndarray) -> np.ndarray:                              # base_map.py:35-46
+        px = np.rint(xy[:, ::-1] * self.ppm) + np.array([self.size // 2, self.size // 2])
+        px[:, 0] = self.size - px[:, 0]
+        return px.astype(int)
+
+    def _cover_add(self, slot: int, r: Tuple[int, int, int, int]) -> None:
+        g = self.size
+        r = (max(r[0], 0), max(r[1], 0), min(r[2], g), min(r[3], g))
+        if r[2] <= r[0] or r[3] <= r[1]:
+            return
+        c = self.cover[slot]
+        self.cover[slot] = r if c is None else (min(c[0], r[0]), min(c[1], r[1]), max(c[2], r[2]), max(c[3], r[3]))
+
+    def _frame(self, slot: int) -> Tuple[int, int, int, int]:
+        """S frame of the explore step: cover + margin, each side snapped to the grid edge when closer than D to it."""
+        g = self.size
+        c = self.cover[slot]
+        if c is None:
+            return (0, 0, g, g)
+        d = int(math.ceil(self.area_thresh_px / max(g - 1, 1))) + 2
+        x0, y0, x1, y1 = c[0] - S_MARGIN, c[1] - S_MARGIN, c[2] + S_MARGIN, c[3] + S_MARGIN
+        x0 = 0 if x0 < d else x0
+        y0 = 0 if y0 < d else y0
+        x1 = g if x1 > g - d else x1
+        y1 = g if y1 > g - d else y1
+        return (x0, y0, x1, y1)
+
+    # ------------------------------------------------------------------ update ----
+    def update(self, depth: Optional[torch.Tensor], tf_host: np.ndarray, tf_dev: torch.Tensor, min_depth: float, max_depth: float,
+               fx: float, fy: float, topdown_fov: float, slots: Optional[Sequence[int]] = None, explore: bool = True,
+               update_obstacles: bool = True) -> None:
+        """depth [n,H,W] float32 (device) or None, tf_host [n,4,4] float64 (numpy: the pose scalars of the explore half are
+        derived on the host exactly as the reference derives them), tf_dev [n,16] float64 (device, read by the obstacle
+        kernels).  ``slots``: grid index of each row (default 0..n-1).  Asynchronous; IndexError conditions are polled by
+        ``check_index_error``."""
+        n = len(tf_host)
+        slots = list(range(n)) if slots is None else [int(s) for s in slots]
+        assert n <= self.batch and len(slots) == n
+        g, ppm = self.size, self.ppm
+        st = _lib.stream_ptr()
+        agents = self.xy_to_px(np.asarray(tf_host, dtype=np.float64)[:, :2, 3])     # (col, row) per env, obstacle_map.py:115-116
+        with torch.cuda.device(self.device):
+            slot_t = None
+            if slots != list(range(n)):
+                slot_t = torch.tensor(slots, dtype=torch.int32, device=self.device)
+            if update_obstacles:
+                assert depth is not None and depth.dtype == torch.float32 and depth.is_contiguous() and depth.shape[0] == n
+                h, w = int(depth.shape[1]), int(depth.shape[2])
+                half = int(math.ceil(max_depth * ppm * math.sqrt(1.0 + (w / 2.0 / fx) ** 2))) + self.kernel // 2 + 2
+                first = any(not self.nav_valid[s] for s in slots)
+                p = _lib.ObstacleParams(h, w, g, ppm, float(np.float32(max_depth - min_depth)), float(np.float32(min_depth)),
+                                        float(np.float32(max_depth)), float(fx), float(fy), float(self.min_height), float(self.max_height),
+                                        self.kernel, 1 if first else 0, half)
+                fill = None
+                if self.hole_area_thresh != -1:          # fill_small_holes (img_utils.py:361-390) on the device
+                    if self._fill is None or self._fill.shape[1:] != (h, w):
+                        nb = ctypes.c_size_t(0)
+                        _lib.check(self.lib.vlfm_holes_batch_workspace_bytes(h, w, self.batch, ctypes.byref(nb)), "vlfm_holes_batch_workspace_bytes")
+                        self._fill = torch.zeros((self.batch, h, w), dtype=torch.uint8, device=self.device)
+                        self._fill_ws = torch.zeros((nb.value + 3) // 4, dtype=torch.int32, device=self.device)
+                    pin = self._pinned()
+                    rc = self.lib.vlfm_fill_small_holes_batch(_lib.ptr(depth), h, w, n, float(self.hole_area_thresh), _lib.ptr(self._fill),
+                                                              _lib.ptr(self._fill_ws), self._fill_ws.numel() * 4, _lib.ptr(self._fill_status),
+                                                              pin.data_ptr(), pin.numel(), st)
+                    self._pinned_done()
+                    _lib.check(rc, "vlfm_fill_small_holes_batch")
+                    fill = self._fill
+                rc = self.lib.vlfm_obstacle_update(ctypes.byref(p), n, _lib.ptr(slot_t), _lib.ptr(self.obst), _lib.ptr(self.nav),
+                                                   _lib.ptr(depth), _lib.ptr(tf_dev), _lib.ptr(fill), _lib.ptr(self.status), st)
+                _lib.check(rc, "vlfm_obstacle_update")
+                for i, s in enumerate(slots):
+                    col, row = int(agents[i][0]), int(agents[i][1])
+                    r = (col - half, row - half, col + half + 1, row + half + 1)
+                    if r[0] < 0 or r[1] < 0:     # near the low edges the scatter may wrap around (numpy negative indices): anything may change
+                        r = (0, 0, g, g)
+                    self._cover_add(s, r)
+                    self.nav_valid[s] = True
+                self._last_half = half
+            if not explore:
+                return
+            L = int(max_depth * ppm)
+            envs = self._envs
+            for i, s in enumerate(slots):
+                col, row = int(agents[i][0]), int(agents[i][1])
+                self._cover_add(s, (col - L - 4, row - L - 4, col + L + 5, row + L + 5))
+                tf = tf_host[i]
+                yaw = float(np.arctan2(tf[1, 0], tf[0, 0]))
+                e = envs[i]
+                e.slot, e.agent_col, e.agent_row = s, col, row
+                fr = self._frame(s)
+                e.frame[0], e.frame[1], e.frame[2], e.frame[3] = fr
+                e.heading_deg = float(np.rad2deg(wrap_heading(yaw + np.pi / 2)))     # current_angle = -yaw (:121)
+                e.fov_deg = float(np.rad2deg(topdown_fov))
+                e.max_line_len = float(max_depth * ppm)
+                e.area_thresh_px = float(self.area_thresh_px)
+            pin = self._pinned()
+            rc = self.lib.vlfm_explore_update_batch(g, n, envs, _lib.ptr(self.explored), _lib.ptr(self.nav), _lib.ptr(self._call_front),
+                                                    _lib.ptr(self._call_count), _lib.ptr(self._call_status), _lib.ptr(self._ex_ws),
+                                                    self._ex_ws.numel() * 4, pin.data_ptr(), pin.numel(), st)
+            self._pinned_done()
+            _lib.check(rc, "vlfm_explore_update_batch")
+            if slots == list(range(n)):
+                self.frontiers[:n].copy_(self._call_front[:n]); self.count[:n].copy_(self._call_count[:n]); self.ex_status[:n].copy_(self._call_status[:n])
+            else:
+                idx = slot_t.long()
+                self.frontiers[idx] = self._call_front[:n]; self.count[idx] = self._call_count[:n]; self.ex_status[idx] = self._call_status[:n]
+
+    # ----------------------------------------------------------------- readback ----
+    def check_fill(self, slot: int = 0) -> None:
+        if self._fill is not None and int(self._fill_status.max().item()) != 0:     # rows of the last call, not slots: any flag counts
+            self._fill_status.zero_()
+            raise _lib.VlfmError("fill_small_holes: a device scratch buffer overflowed (too many contours in the depth image)")
+
+    def index_error(self, slot: int) -> bool:
+        if int(self.status[slot].item()) & _lib.ST_SCATTER_OOB:
+            self.status[slot] = 0
+            return True
+        return False
+
+    def frontiers_px(self, slot: int) -> np.ndarray:
+        n = int(self.count[slot].item())
+        if int(self.ex_status[slot].item()) != 0:
+            raise _lib.VlfmError("explore: a device scratch buffer overflowed (too many contours / points)")
+        if n == 0:
+            return np.array([])
+        return self.frontiers[slot, :n].cpu().numpy()
+
+    def all_frontiers_px(self, n: Optional[int] = None) -> List[np.ndarray]:
+        """frontier lists of slots 0..n-1 with ONE device->host transfer (what a vectorised policy needs every step)"""
+        n = self.batch if n is None else n
+        cnt = self.count[:n].cpu().numpy()
+        if int(self.ex_status[:n].max().item()) != 0:
+            raise _lib.VlfmError("explore: a device scratch buffer overflowed (too many contours / points)")
+        m = int(cnt.max()) if n else 0
+        if m == 0:
+            return [np.array([]) for _ in range(n)]
+        fr = self.frontiers[:n, :m].cpu().numpy()
+        return [fr[i, : cnt[i]].copy() if cnt[i] else np.array([]) for i in range(n)]
+
+    def px_to_xy(self, px: np.ndarray) -> np.ndarray:                              # base_map.py:48-60
+        q = px.copy()
+        q[:, 0] = self.size - q[:, 0]
+        return ((q - np.array([self.size // 2, self.size // 2])) / self.ppm)[:, ::-1]
+
+    def reset(self, slot: Optional[int] = None) -> None:
+        sl = slice(None) if slot is None else slot
+        self.obst[sl].zero_(); self.nav[sl].zero_(); self.explored[sl].zero_()
+        if slot is None:
+            self.status.zero_(); self.count.zero_(); self.ex_status.zero_()
+            self.nav_valid = [False] * self.batch
+            self.cover = [None] * self.batch
+        else:
+            self.status[slot] = 0; self.count[slot] = 0; self.ex_status[slot] = 0
+            self.nav_valid[slot] = False
+            self.cover[slot] = None

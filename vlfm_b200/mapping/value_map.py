@@ -152,6 +152,18 @@ class ValueMapBatch:
         _lib.check(rc, "vlfm_value_disc_median")
         return out.cpu().numpy()
 
+    def disc_median_batch(self, points_srl: np.ndarray, radius: int) -> np.ndarray:
+        """[(slot, row, col)] over any number of environments -> [npoints, C] medians with one launch and one read-back."""
+        if len(points_srl) == 0:
+            return np.zeros((0, self.channels))
+        pts = torch.from_numpy(np.ascontiguousarray(points_srl, dtype=np.int32)).to(self.device)
+        out = torch.empty((len(points_srl), self.channels), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.vlfm_value_disc_median_batch(self.size, self.channels, _lib.ptr(self.value), _lib.ptr(pts), len(points_srl), radius,
+                                                       _lib.ptr(_disc(radius, self.device)), _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "vlfm_value_disc_median_batch")
+        return out.cpu().numpy()
+
     def reset(self, slot: Optional[int] = None) -> None:
         if slot is None:
             self.conf.zero_(); self.value.zero_(); self.status.zero_()

@@ -25,7 +25,7 @@ def grid_bytes(h: int, w: int, g: int, ppm: int, channels: int = 1, max_depth: f
 class FullStep:
     def __init__(self, dev: torch.device, batch: int, h: int, w: int, grid: int, ppm: int, itm, gdino, frames_per_env: int,
                  seed0: int = 0, streams: int = 8, hole_thresh: int = 100000, bound_m: float = 15.0) -> None:
-        from ..mapping.obstacle_map import ObstacleMap
+        from ..mapping.obstacle_batch import ObstacleMapBatch
         from ..mapping.value_map import ValueMapBatch
         from .synthetic import focal_from_hfov, trajectory
 
@@ -33,9 +33,7 @@ class FullStep:
         self.itm, self.gd = itm, gdino
         self.ids = gdino.tokenizer.encode(CAPTION) if gdino is not None else None
         self.vmb = ValueMapBatch(batch, 1, size=grid, pixels_per_meter=ppm, use_max_confidence=False, device=dev)
-        self.oms = [ObstacleMap(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=hole_thresh, size=grid, pixels_per_meter=ppm, device=dev)
-                    for _ in range(batch)]
-        self.streams = [torch.cuda.Stream(dev) for _ in range(max(1, streams))]
+        self.omb = ObstacleMapBatch(batch, 0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=hole_thresh, size=grid, pixels_per_meter=ppm, device=dev)
         self.fx = focal_from_hfov(w)
         nf = frames_per_env
         self.frames = [trajectory(seed0 + e, nf, h=h, w=w, bound_m=bound_m, with_rgb=True) for e in range(batch)]
@@ -49,8 +47,9 @@ class FullStep:
                 self.rgb_pin[i, e].numpy()[...] = f.rgb
                 self.depth_pin[i, e].numpy()[...] = f.depth
                 self.tf_pin[i, e].numpy()[...] = f.tf.reshape(16)
-                f.depth = self.depth_pin[i, e].numpy()                    # ObstacleMap reads the same page-locked frame
+                f.depth = None
                 f.rgb = None
+        self.tf_host = [np.stack([self.frames[e][i].tf for e in range(batch)]) for i in range(nf)]
         self.rgb_dev, self.depth_dev, self.tf_dev = (torch.empty_like(t[0], device=dev) for t in (self.rgb_pin, self.depth_pin, self.tf_pin))
         self.names = ["h2d", "gdino", "itc", "obstacle+explore", "value_fuse", "frontier_scoring"]
         self.acc = {k: 0.0 for k in self.names}
@@ -74,22 +73,22 @@ class FullStep:
         ev[2].record()
         cos = self.itm.cosine_device(self.rgb_dev, PROMPT)
         ev[3].record()
-        for s in self.streams:
-            s.wait_stream(main)
-        for e in range(B):                                    # independent envs: round-robin over streams
-            with torch.cuda.stream(self.streams[e % len(self.streams)]):
-                self.oms[e].update_map(self.frames[e][i].depth, self.frames[e][i].tf, MIN_D, MAX_D, self.fx, self.fx, FOV)
-        for s in self.streams:
-            main.wait_stream(s)
+        # all environments' obstacle + explore update: ONE launch sequence (hole fill, scatter, dilate, fog-of-war, frontiers)
+        self.omb.update(self.depth_dev, self.tf_host[i], self.tf_dev, MIN_D, MAX_D, self.fx, self.fx, FOV)
         ev[4].record()
         self.vmb.update(cos.double().view(B, 1), self.depth_dev, self.tf_dev.view(B, 4, 4), MIN_D, MAX_D, FOV)
         ev[5].record()
-        for e in range(B):                                    # ITMPolicy._sort_frontiers_by_value: D2H of the frontier list + disc medians
-            fr = self.oms[e].frontiers
-            self.n_front += len(fr)
-            if len(fr):
-                px = self.oms[e]._xy_to_px(fr[:, :2])
-                self.vmb.disc_median(e, np.stack([px[:, 1], px[:, 0]], axis=1), int(0.5 * self.ppm))
+        # ITMPolicy._sort_frontiers_by_value for every environment: one D2H of the frontier lists, one disc-median launch, one D2H
+        fronts = self.omb.all_frontiers_px(B)
+        pts = []
+        for e, px in enumerate(fronts):
+            self.n_front += len(px)
+            if len(px):
+                xy = self.omb.px_to_xy(px)                     # ObstacleMap.frontiers (metres) ...
+                q = self.omb.xy_to_px(xy[:, :2])                # ... and back to cells, as the policy does through sort_waypoints
+                pts.append(np.stack([np.full(len(q), e), q[:, 1], q[:, 0]], axis=1))
+        if pts:
+            self.vmb.disc_median_batch(np.concatenate(pts), int(0.5 * self.ppm))
         ev[6].record()
         torch.cuda.synchronize()
         if timed:
@@ -132,18 +131,9 @@ class FullStep:
         ach = gb["value"] * B / (ms * 1e-3) / 1e9
         out["value_update"] = {"kernels": "value_depth_geom_kernel + value_cone_fuse_kernel", "ms": ms, "envs": B, "bytes_per_env": gb["value"],
                                "achieved_gbs": ach, "peak_gbs": hbm_gbs, "frac": ach / hbm_gbs, "bound": "hbm"}
-        # obstacle + explore: per-env objects over the stream pool, as in step()
-        i = 0
-        main = torch.cuda.current_stream()
-
+        # obstacle + explore: the batched launch sequence of step(), depth already in HBM
         def obst():
-            for s in self.streams:
-                s.wait_stream(main)
-            for e in range(B):
-                with torch.cuda.stream(self.streams[e % len(self.streams)]):
-                    self.oms[e].update_map(self.frames[e][i].depth, self.frames[e][i].tf, MIN_D, MAX_D, self.fx, self.fx, FOV)
-            for s in self.streams:
-                main.wait_stream(s)
+            self.omb.update(self.depth_dev, self.tf_host[0], self.tf_dev, MIN_D, MAX_D, self.fx, self.fx, FOV)
 
         obst()
         torch.cuda.synchronize()
@@ -154,7 +144,7 @@ class FullStep:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         ach = gb["obstacle"] * B / (ms * 1e-3) / 1e9
-        out["obstacle_explore"] = {"kernels": "fill_small_holes + obstacle_scatter/dilate + explore (fog-of-war, component, frontiers), incl. H2D of depth",
+        out["obstacle_explore"] = {"kernels": "fill_small_holes + obstacle_scatter/dilate + explore (fog-of-war, component, frontiers), one launch sequence for all envs",
                                    "ms": ms, "envs": B, "bytes_per_env": gb["obstacle"], "achieved_gbs": ach, "peak_gbs": hbm_gbs,
                                    "frac": ach / hbm_gbs, "bound": "hbm (latency-bound border following in practice)"}
         return out
