@@ -586,7 +586,8 @@ __global__ void rays_kernel(const ExEnv* __restrict__ envs) {
     auto emit = [&](int qx, int qy) {
       const double ang = atan2((double)(qy - sy), (double)(qx - sx));
       // astype(np.int32) truncates toward zero in GRID coordinates (the window origin is subtracted afterwards)
-      const int ex = (int)((double)(qx + ox) + ray_len * cos(ang)) - ox, ey = (int)((double)(qy + oy) + ray_len * sin(ang)) - oy;
+      // numpy evaluates pts + length * cos(ang) as a rounded product and a rounded sum: no fused multiply-add
+      const int ex = (int)__dadd_rn((double)(qx + ox), __dmul_rn(ray_len, cos(ang))) - ox, ey = (int)__dadd_rn((double)(qy + oy), __dmul_rn(ray_len, sin(ang))) - oy;
       const int k = atomicAdd(&st->n_rays, 1);
       if (k < cap) rays[k] = make_int4(qx, qy, ex, ey); else st->overflow = 1;
     };
@@ -1292,7 +1293,7 @@ extern "C" int vlfm_explore_update_batch(int G, int batch, const VlfmExploreEnv*
   paste_grow_kernel<<<dim3(bs, B), 256, 0, st>>>(d_envs);
   contours(d_envs, B, IMG_UNEXP, sn_max, sh_max, sper_max, st, 1, 2, 1);
   absorb_small_kernel<<<dim3(128, B), 128, 0, st>>>(d_envs);
-  contours(d_envs, B, IMG_EX2, sn_max, sh_max, sper_max, st, 1, 1, 0);
+  contours(d_envs, B, IMG_EX2, sn_max, sh_max, sper_max, st, 1, 0, 0);     // every external contour is walked (mode 0)
   bad_flags_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
   frontier_kernel<<<dim3(1, B), FRONTIER_THREADS, 0, st>>>(d_envs);
   publish_kernel<<<B, 32, 0, st>>>(d_envs, 0);

@@ -31,24 +31,34 @@ struct ObstDev {
   int k, full, half;
 };
 
-__device__ __forceinline__ void obst_point(const ObstDev& p, const double* T, uint8_t* obst, int* status,
+// One depth pixel.  The evaluation order of every output is numpy's (see the header); what is reorganised is only WHICH outputs are
+// evaluated: the height test (:196-197) needs ez alone, so ex / ey (and the lateral division feeding them) are computed for the
+// few pixels that pass it.  `lazy_y`: T[9] == 0, so ez does not depend on the lateral coordinate (fma(0, py, acc) == acc);
+// `affine`: the last row of T is (0, 0, 0, 1), so the homogeneous divisor is exactly 1.0 and x / 1.0 == x.  Both hold for every
+// camera->episodic transform the policies build (xyz_yaw_to_tf_matrix); otherwise the general path runs.  FP64 divisions per pixel:
+// 5 -> ~1.05 (B200 retires 64 FP64 FMA/clk/SM; a division costs ~20 of them -- the kernel was division-bound).
+__device__ __forceinline__ void obst_point(const ObstDev& p, const double* T, bool lazy_y, bool affine, uint8_t* obst, int* status,
                                            int b, int u, int v, float d, const uint8_t* fill) {
   if (fill) { if (fill[v * p.W + u]) d = 1.f; }                  // fill_small_holes mask (:91, img_utils.py:388)
   else if (d == 0.f) d = 1.f;                                    // hole_area_thresh == -1 (:88-89)
   float z32 = __fadd_rn(__fmul_rn(d, p.dscale), p.doff);         // :92 float32
   if (!(z32 < p.maxd)) return;                                   // :93
   // get_point_cloud: int64 * float32 -> float64, then / fx  (geometry_utils.py:230-234)
-  double z = (double)z32;
-  double xc = __ddiv_rn(__dmul_rn((double)(u - p.W / 2), z), p.fx);
-  double yc = __ddiv_rn(__dmul_rn((double)(v - p.H / 2), z), p.fy);
-  double px = z, py = -xc, pz = -yc;                             // cloud = (z, -x, -y)
+  const double z = (double)z32;
+  const double yc = __ddiv_rn(__dmul_rn((double)(v - p.H / 2), z), p.fy);
+  const double px = z, pz = -yc;                                 // cloud = (z, -x, -y)
+  double py = 0.0;
+  if (!lazy_y) py = -__ddiv_rn(__dmul_rn((double)(u - p.W / 2), z), p.fx);
   // transform_points: np.dot(T, [p,1]) -- BLAS dgemm accumulates k=0..3 with FMA
+  double ew = 1.0;
+  if (!affine) ew = fma(T[15], 1.0, fma(T[14], pz, fma(T[13], py, __dmul_rn(T[12], px))));
+  double ez = fma(T[11], 1.0, fma(T[10], pz, fma(T[9], py, __dmul_rn(T[8], px))));
+  if (!affine) ez = __ddiv_rn(ez, ew);
+  if (!(ez >= p.minh && ez <= p.maxh)) return;                   // obstacle_map.py:196-197
+  if (lazy_y) py = -__ddiv_rn(__dmul_rn((double)(u - p.W / 2), z), p.fx);
   double ex = fma(T[3], 1.0, fma(T[2], pz, fma(T[1], py, __dmul_rn(T[0], px))));
   double ey = fma(T[7], 1.0, fma(T[6], pz, fma(T[5], py, __dmul_rn(T[4], px))));
-  double ez = fma(T[11], 1.0, fma(T[10], pz, fma(T[9], py, __dmul_rn(T[8], px))));
-  double ew = fma(T[15], 1.0, fma(T[14], pz, fma(T[13], py, __dmul_rn(T[12], px))));
-  ex = __ddiv_rn(ex, ew); ey = __ddiv_rn(ey, ew); ez = __ddiv_rn(ez, ew);
-  if (!(ez >= p.minh && ez <= p.maxh)) return;                   // obstacle_map.py:196-197
+  if (!affine) { ex = __ddiv_rn(ex, ew); ey = __ddiv_rn(ey, ew); }
   // _xy_to_px (base_map.py:44-46): px = rint(xy[::-1]*ppm) + origin; px[:,0] = G - px[:,0]
   long long c0 = (long long)rint(__dmul_rn(ey, (double)p.ppm)) + p.G / 2;
   long long r0 = (long long)rint(__dmul_rn(ex, (double)p.ppm)) + p.G / 2;
@@ -70,6 +80,8 @@ obstacle_scatter_kernel(ObstDev p, const int* __restrict__ slot, uint8_t* __rest
   __shared__ double T[16];
   if (threadIdx.x < 16) T[threadIdx.x] = tf[(size_t)b * 16 + threadIdx.x];
   __syncthreads();
+  const bool lazy_y = T[9] == 0.0;
+  const bool affine = T[12] == 0.0 && T[13] == 0.0 && T[14] == 0.0 && T[15] == 1.0;
   const int s = slot ? slot[b] : b;
   uint8_t* obst = obstAll + (size_t)s * p.G * p.G;
   const float* img = depth + (size_t)b * p.H * p.W;
@@ -79,15 +91,15 @@ obstacle_scatter_kernel(ObstDev p, const int* __restrict__ slot, uint8_t* __rest
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
       float4 d = __ldg(reinterpret_cast<const float4*>(img) + i);
       int pix = i << 2, v = pix / p.W, u = pix - v * p.W;
-      obst_point(p, T, obst, status, b, u + 0, v, d.x, fill);
-      obst_point(p, T, obst, status, b, u + 1, v, d.y, fill);
-      obst_point(p, T, obst, status, b, u + 2, v, d.z, fill);
-      obst_point(p, T, obst, status, b, u + 3, v, d.w, fill);
+      obst_point(p, T, lazy_y, affine, obst, status, b, u + 0, v, d.x, fill);
+      obst_point(p, T, lazy_y, affine, obst, status, b, u + 1, v, d.y, fill);
+      obst_point(p, T, lazy_y, affine, obst, status, b, u + 2, v, d.z, fill);
+      obst_point(p, T, lazy_y, affine, obst, status, b, u + 3, v, d.w, fill);
     }
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       int v = i / p.W, u = i - v * p.W;
-      obst_point(p, T, obst, status, b, u, v, __ldg(img + i), fill);
+      obst_point(p, T, lazy_y, affine, obst, status, b, u, v, __ldg(img + i), fill);
     }
   }
 }
