@@ -19,9 +19,9 @@ import numpy as np
 import torch
 
 from .. import _lib
+from . import sframe as _sf
 
 MAX_FRONTIERS = 4096
-S_MARGIN = 8
 
 
 def wrap_heading(h: float) -> float:
@@ -89,26 +89,11 @@ class ObstacleMapBatch:
         return px.astype(int)
 
     def _cover_add(self, slot: int, r: Tuple[int, int, int, int]) -> None:
-        g = self.size
-        r = (max(r[0], 0), max(r[1], 0), min(r[2], g), min(r[3], g))
-        if r[2] <= r[0] or r[3] <= r[1]:
-            return
-        c = self.cover[slot]
-        self.cover[slot] = r if c is None else (min(c[0], r[0]), min(c[1], r[1]), max(c[2], r[2]), max(c[3], r[3]))
+        self.cover[slot] = _sf.cover_add(self.cover[slot], r, self.size)
 
     def _frame(self, slot: int) -> Tuple[int, int, int, int]:
-        """S frame of the explore step: cover + margin, each side snapped to the grid edge when closer than D to it."""
-        g = self.size
-        c = self.cover[slot]
-        if c is None:
-            return (0, 0, g, g)
-        d = int(math.ceil(self.area_thresh_px / max(g - 1, 1))) + 2
-        x0, y0, x1, y1 = c[0] - S_MARGIN, c[1] - S_MARGIN, c[2] + S_MARGIN, c[3] + S_MARGIN
-        x0 = 0 if x0 < d else x0
-        y0 = 0 if y0 < d else y0
-        x1 = g if x1 > g - d else x1
-        y1 = g if y1 > g - d else y1
-        return (x0, y0, x1, y1)
+        """S frame of the explore step (mapping/sframe.py): cover + margin, sides snapped to the grid edge when closer than D to it."""
+        return _sf.sframe(self.cover[slot], self.size, self.area_thresh_px)
 
     # ------------------------------------------------------------------ update ----
     def update(self, depth: Optional[torch.Tensor], tf_host: np.ndarray, tf_dev: torch.Tensor, min_depth: float, max_depth: float,
@@ -155,10 +140,7 @@ class ObstacleMapBatch:
                 _lib.check(rc, "vlfm_obstacle_update")
                 for i, s in enumerate(slots):
                     col, row = int(agents[i][0]), int(agents[i][1])
-                    r = (col - half, row - half, col + half + 1, row + half + 1)
-                    if r[0] < 0 or r[1] < 0:     # near the low edges the scatter may wrap around (numpy negative indices): anything may change
-                        r = (0, 0, g, g)
-                    self._cover_add(s, r)
+                    self._cover_add(s, _sf.obstacle_window(col, row, half, g))
                     self.nav_valid[s] = True
                 self._last_half = half
             if not explore:
@@ -167,7 +149,7 @@ class ObstacleMapBatch:
             envs = self._envs
             for i, s in enumerate(slots):
                 col, row = int(agents[i][0]), int(agents[i][1])
-                self._cover_add(s, (col - L - 4, row - L - 4, col + L + 5, row + L + 5))
+                self._cover_add(s, _sf.fog_window(col, row, L))
                 tf = tf_host[i]
                 yaw = float(np.arctan2(tf[1, 0], tf[0, 0]))
                 e = envs[i]
