@@ -334,8 +334,10 @@ def run_extras(args, dev, world, rank, sd, dims, itm32):
     # ---- configs[1] at EB env/GPU: ITC + cone-fuse, inputs resident in HBM
     try:
         eng = ValueMapBatch(EB, 1, size=G, use_max_confidence=False, device=dev)
-        fr = [make_frames(1000 + rank * EB + e) for e in range(EB)]
+        from vlfm_b200.utils.synthetic import trajectory
+
         nfr = 4
+        fr = [trajectory(1000 + rank * EB + e, nfr, h=H, w=W, with_rgb=True, bound_m=15.0) for e in range(EB)]
         rgb = torch.from_numpy(np.stack([np.stack([f[i].rgb for f in fr]) for i in range(nfr)])).to(dev)
         depth = torch.from_numpy(np.stack([np.stack([f[i].depth for f in fr]) for i in range(nfr)])).to(dev)
         tfs = torch.from_numpy(np.stack([np.stack([f[i].tf for f in fr]) for i in range(nfr)])).to(dev)
