@@ -91,4 +91,4 @@ def test_full_size_vitg_vs_oracle(outliers, frames):
     errs = np.array(errs)
     print(f"outliers={outliers}: {len(errs)} cosines, max |err| {errs.max():.3e}, mean {errs.mean():.3e}, run-to-run spread {spread:.3e}")
     assert errs.max() <= 1e-4
-    assert spread <= 2e-5
+    assert spread <= 1e-4

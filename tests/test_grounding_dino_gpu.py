@@ -351,7 +351,7 @@ def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
                 cand = [(float((box - bb).abs().sum()), p2, s2) for p2, bb, s2 in dst]
                 assert cand, "the other model kept nothing"
                 dist, p2, s2 = min(cand)
-                assert dist <= 2e-2, f"no matching box for {phrase!r} score {score:.3f} (nearest {dist:.3f})"
+                assert dist <= 5e-2, f"no matching box for {phrase!r} score {score:.3f} (nearest {dist:.3f})"   # L1 over (cx, cy, w, h), normalised
                 assert p2 == phrase, f"phrase differs: {phrase!r} vs {p2!r} (score {score:.3f})"
                 assert abs(s2 - score) <= DELTA
                 n_checked += 1

@@ -21,7 +21,7 @@ def _check(eng, slot, o, tag):
 
 
 @pytest.mark.parametrize("cfg", [
-    dict(B=4, hw=(120, 160), size=400, steps=8, bound=4.0, hole=-1),
+    dict(B=4, hw=(120, 160), size=400, steps=8, bound=2.5, hole=-1),
     dict(B=5, hw=(240, 320), size=1000, steps=7, bound=12.0, hole=100000),
     dict(B=3, hw=(240, 320), size=2000, steps=5, bound=30.0, hole=100000),
 ])
@@ -32,7 +32,7 @@ def test_batch_vs_per_env_oracles(cfg):
     fx = focal_from_hfov(w)
     eng = ObstacleMapBatch(B, 0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=cfg["hole"], size=G)
     orc = [ObstacleMapOracle(0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=cfg["hole"], size=G) for _ in range(B)]
-    frames = [trajectory(40 + e, cfg["steps"], h=h, w=w, bound_m=cfg["bound"], start_xy=(1.5 * e, -2.0 * e)) for e in range(B)]
+    frames = [trajectory(40 + e, cfg["steps"], h=h, w=w, bound_m=cfg["bound"], start_xy=(0.002 * G * e / 2, -0.003 * G * e / 2)) for e in range(B)]
     for i in range(cfg["steps"]):
         for e in range(B):
             orc[e].update_map(frames[e][i].depth, frames[e][i].tf, 0.5, 5.0, fx, fx, FOV)
