@@ -423,8 +423,10 @@ def gemm_roofline(engine, B, dims):
         calls.append((a, w, bias, epi, out))
         orig(a, w, bias, epi, out)
 
+    # the replay times the GEMM launches alone: residual GEMMs are replayed with the plain residual epilogue (same tiles and
+    # split-K plan as the step's partial-sum epilogue; the reduce/LayerNorm launches are not GEMMs and are not replayed)
     orig_fuse = engine.fuse_ln
-    engine.fuse_ln = False          # the replay times the GEMMs alone (LayerNorm launched separately, not replayed)
+    engine.fuse_ln = False
     engine._gemm = rec
     mid = torch.empty(B, H, dims.image, 3, dtype=torch.uint8, device=engine.dev)
     img = torch.zeros(B, H, W, 3, dtype=torch.uint8, device=engine.dev)

@@ -157,13 +157,19 @@ int vlfm_fill_small_holes(const float* d_depth, int H, int W, double area_thresh
  * (start, setup done, dependency wait done, first stage landed, last MMA issued, accumulator ready,
  * epilogue done) and %globaltimer into d_buf8[0..7]; NULL disables. */
 void vlfm_gemm_debug_timeline(unsigned long long* d_buf8);
+#define VLFM_EPI_PARTIAL_F32 5   /* internal to vlfm_gemm_f16_resid_ln: split-K partial sums stored side by side */
 /* x[M,N] (fp32 residual stream) += A @ W^T + bias, then LayerNorm(x) -> d_out16 (fp16) and/or d_out32 (fp32, may
- * alias x for the post-LN Q-Former blocks).  When the GEMM is a single wave the LayerNorm runs inside the same
- * kernel after a grid-wide barrier (d_sync2: two zero-initialised uint32 owned by the caller); otherwise it is
- * launched as a second kernel.  Replaces `x = x + proj(...)` followed by `layer_norm` in the BLIP-2 forward. */
+ * alias x for the post-LN Q-Former blocks).  BITWISE REPRODUCIBLE: when the tile plan splits K, the splits store their
+ * partial sums in d_partials (>= splits * M * N floats, splits <= 8; no atomics) and the LayerNorm launch adds them to x in
+ * split order before normalising; without d_partials (or when it is too small) the splits fall back to red.global.add into x.
+ * Replaces `x = x + proj(...)` followed by `layer_norm` in the BLIP-2 forward (blip2itm.py:52 through lavis).            */
 int vlfm_gemm_f16_resid_ln(const void* d_A, const void* d_W, const float* d_bias, float* d_x, int M, int N, int K,
-                           int lda, int ldw, int ldx, const float* d_gamma, const float* d_beta, void* d_out16,
-                           int ld16, float* d_out32, int ld32, float eps, uint32_t* d_sync2, void* stream);
+                           int lda, int ldw, int ldx, const float* d_gamma, const float* d_beta, void* d_out16, int ld16,
+                           float* d_out32, int ld32, float eps, float* d_partials, size_t partial_bytes, void* stream);
+/* the reduction + LayerNorm launch on its own: x += sum_s partials[s] (s ascending), out = LayerNorm(x) */
+int vlfm_layernorm_reduce(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                          const float* d_beta, void* d_out16, float* d_out32, int rows, int D, int ldx, int ldo16, int ldo32,
+                          float eps, void* stream);
 int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
                   int K, int lda, int ldw, int ldo, int epilogue, void* stream);
 
@@ -241,6 +247,27 @@ int vlfm_biattn_f16(const void* d_q, const void* d_k, const void* d_v, void* d_o
 int vlfm_cast_f32_f16(const float* d_in, void* d_out16, long n, void* stream);
 /* out_x16 = fp16(x), out_xp16 = fp16(x + pos) (query/key = hidden + position embedding); n % 4 == 0; either output may be NULL. */
 int vlfm_cast_addpos_f16(const float* d_x, const float* d_pos, void* d_out_x16, void* d_out_xp16, long n, void* stream);
+
+/* ------------------------------------------------- GroundingDINO model-level glue ---- */
+/* The parts of groundingdino's `model(image, captions=[caption])` (vlfm/vlm/grounding_dino.py:61-67) that sit between the
+ * backbone and the (boxes, logits) pair and outside the encoder / decoder layers (vlm/gdino_forward.py; module graph:
+ * HF GroundingDinoModel.forward / GroundingDinoForObjectDetection.forward).
+ * groupnorm_rows: torch.nn.GroupNorm of the neck on NHWC rows y [B,HW,C] -> d_out[b, row_off + i, :] of a [B,S,C] buffer.
+ * im2col3x3s2: rows [B,h,w,C] fp32 -> fp16 [B*ho*wo, 9*C] ((ky,kx,c) order) for the fourth level's 3x3 stride-2 conv.
+ * mask_rows_f16: fp32 rows -> fp16 GEMM operand with invalid rows zeroed (generate_encoder_output_proposals).
+ * proposal_scores: score[b,s] = max_t <q[b,s,:], text[b,t,:]> (encoder_output_class_embed + max(-1)).
+ * topk_rows: indices of the k best scores per image, descending, ties to the lower index (torch.topk; S <= 16384).
+ * gather_rows: dst[b,i,:] = src[b, idx[b,i], :] (torch.gather).
+ * box_finish: sigmoid(delta + logit(ref, eps=1e-5)).   contrastive_sigmoid: sigmoid(<hs, text>) padded with 0 to L.       */
+int vlfm_groupnorm_rows(const float* d_y, int B, int HW, int C, int groups, const float* d_gamma, const float* d_beta, float eps,
+                        float* d_out, int row_off, int S, void* stream);
+int vlfm_im2col3x3s2(const float* d_x, void* d_col16, int B, int h, int w, int C, void* stream);
+int vlfm_mask_rows_f16(const float* d_x, const uint8_t* d_valid, void* d_out16, long rows, int D, void* stream);
+int vlfm_proposal_scores(const float* d_q, const float* d_text, int B, int S, int T, int D, float* d_scores, void* stream);
+int vlfm_topk_rows(const float* d_scores, int B, int S, int k, long long* d_idx, void* stream);
+int vlfm_gather_rows(const float* d_src, const long long* d_idx, int B, int S, int K, int C, float* d_dst, void* stream);
+int vlfm_box_finish(const float* d_delta, const float* d_ref, float* d_out, long n, void* stream);
+int vlfm_contrastive_sigmoid(const float* d_hs, const float* d_text, int B, int Q, int T, int D, int L, float* d_out, void* stream);
 
 /* ------------------------------------------------------------- explore half ---- */
 /* Replaces ObstacleMap.update_map's explore half (vlfm/mapping/obstacle_map.py:114-153) and _get_frontiers

@@ -48,15 +48,19 @@ torch.cuda.synchronize()
 d, tfh, tfd = load(a.warm)
 gb = grid_bytes(H, W, G, a.ppm)
 if a.time:
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     reps = 20
-    tv = to = 0.0
-    for _ in range(reps):
-        ev[0].record(); vm.update(vals, d, tfd.view(B, 4, 4), 0.5, 5.0, FOV); ev[1].record()
-        om.update(d, tfh, tfd, 0.5, 5.0, fx, fx, FOV); ev[2].record()
-        torch.cuda.synchronize()
-        tv += ev[0].elapsed_time(ev[1]); to += ev[1].elapsed_time(ev[2])
-    tv, to = tv / reps, to / reps
+
+    def loop(fn):          # back-to-back launches, one pair of events around the loop (no host sync inside)
+        fn(); torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(reps):
+            fn()
+        ev[1].record(); torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / reps
+
+    tv = loop(lambda: vm.update(vals, d, tfd.view(B, 4, 4), 0.5, 5.0, FOV))
+    to = loop(lambda: om.update(d, tfh, tfd, 0.5, 5.0, fx, fx, FOV))
     fr = om._frame(0)
     print(f"B={B} G={G} ppm={a.ppm} {W}x{H}: value update {tv*1e3:.1f} us ({gb['value']*B/tv/1e6:.0f} GB/s algorithmic), "
           f"obstacle+explore {to*1e3:.1f} us ({gb['obstacle']*B/to/1e6:.0f} GB/s algorithmic); S frame of env 0: {fr[2]-fr[0]}x{fr[3]-fr[1]}; "

@@ -66,8 +66,8 @@ def test_full_size_vitg_vs_oracle(outliers, frames):
     """ViT-g/14 (39 layers, 1408) + 12-layer Q-Former at full size, seeded synthetic weights (plain Gaussian, and with
     trained-checkpoint-like LayerNorm outlier channels / massive activations): BLIP2ITM.cosine within the north-star 1e-4 of
     the fp32 oracle on every one of frames x 3 prompts (fp16 tensor-core operands, fp32 accumulation / residual stream /
-    statistics; lavis runs the ViT under fp16 autocast and the Q-Former in fp32).  Also bounds the run-to-run spread of the
-    cosine (split-K red.add order inside the CUDA graph)."""
+    statistics; lavis runs the ViT under fp16 autocast and the Q-Former in fp32).  The cosine is bitwise reproducible run to
+    run (split-K partial sums are reduced in a fixed order; round 1's red.add reduction spread ~6e-5)."""
     from vlfm_b200.vlm.blip2itm import BLIP2ITM, HashTokenizer, pre_caption
 
     torch.set_num_threads(max(1, (torch.get_num_threads())))
@@ -91,4 +91,4 @@ def test_full_size_vitg_vs_oracle(outliers, frames):
     errs = np.array(errs)
     print(f"outliers={outliers}: {len(errs)} cosines, max |err| {errs.max():.3e}, mean {errs.mean():.3e}, run-to-run spread {spread:.3e}")
     assert errs.max() <= 1e-4
-    assert spread <= 1e-4
+    assert spread == 0.0            # deterministic split-K reduction: bitwise reproducible

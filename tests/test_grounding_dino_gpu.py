@@ -322,6 +322,7 @@ def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
     orc, g = pair_calibrated
     DELTA = 0.01
     n_checked = n_exempt = 0
+    bad, worst_box, worst_score = [], 0.0, 0.0
     for seed, caption in ((21, "chair . person . dog ."), (22, "couch . potted plant . tv ."), (23, "bed . toilet .")):
         img = make_rgb(np.random.default_rng(seed), 480, 640)
         ids = g.tokenizer.encode(caption)
@@ -338,7 +339,6 @@ def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
             v = l_row[1:len(ids) - 1]
             return bool(((v - text_thr).abs() < DELTA).any())
         for src, dst, src_l in ((a, b, ref_l), (b, a, got_l)):
-            rows = {id(d): None for d in src}
             for phrase, box, score in src:
                 if score < box_thr + DELTA:
                     n_exempt += 1
@@ -351,9 +351,84 @@ def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
                 cand = [(float((box - bb).abs().sum()), p2, s2) for p2, bb, s2 in dst]
                 assert cand, "the other model kept nothing"
                 dist, p2, s2 = min(cand)
-                assert dist <= 5e-2, f"no matching box for {phrase!r} score {score:.3f} (nearest {dist:.3f})"   # L1 over (cx, cy, w, h), normalised
-                assert p2 == phrase, f"phrase differs: {phrase!r} vs {p2!r} (score {score:.3f})"
-                assert abs(s2 - score) <= DELTA
+                worst_box, worst_score = max(worst_box, dist), max(worst_score, abs(s2 - score))
+                if dist > 5e-2 or p2 != phrase or abs(s2 - score) > DELTA:
+                    bad.append((phrase, p2, round(score, 4), round(s2, 4), round(dist, 4)))
                 n_checked += 1
+    print(f"decision test: worst matched box distance {worst_box:.4f} (L1, normalised), worst score difference {worst_score:.4f}; mismatches {bad[:8]}")
+    assert not bad, f"{len(bad)} of {n_checked} decisions differ"
     print(f"decision test: {n_checked} detections matched exactly, {n_exempt} within {DELTA} of a threshold (exempt)")
     assert n_checked >= 60 and n_exempt <= n_checked
+
+
+def test_head_kernels_vs_torch():
+    """csrc/gdino_head.cu through vlm/gdino_ops.py::LibOps against torch fp32: GroupNorm on NHWC rows, im2col of the 3x3 stride-2
+    conv, masked cast, proposal scores, top-k, gather, box / class heads."""
+    from vlfm_b200.vlm.gdino_ops import LibOps
+
+    ops = LibOps()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, h, w, C = 3, 15, 20, 768
+    # GroupNorm into a flattened buffer at an offset
+    y = torch.randn(B * h * w, 256, generator=g).cuda() * 3 + 0.5
+    gam, bet = torch.randn(256, generator=g).cuda(), torch.randn(256, generator=g).cuda()
+    S = h * w + 37
+    out = torch.zeros(B, S, 256, device="cuda")
+    ops.groupnorm_rows(y, B, h * w, 256, 32, gam, bet, 1e-5, out, 37, S)
+    ref = torch.nn.functional.group_norm(y.view(B, h * w, 256).permute(0, 2, 1), 32, gam, bet, 1e-5).permute(0, 2, 1)
+    assert float((out[:, 37:] - ref).abs().max()) <= 2e-5 and float(out[:, :37].abs().max()) == 0.0
+    # im2col (ky, kx, c) order == conv2d with the permuted weight
+    x = torch.randn(B * h * w, C, generator=g).cuda()
+    col = ops.im2col3x3s2(x, B, h, w).float()
+    wt = torch.randn(64, C, 3, 3, generator=g).cuda() * 0.02
+    ref = torch.nn.functional.conv2d(x.view(B, h, w, C).permute(0, 3, 1, 2), wt, stride=2, padding=1)
+    got = (col @ wt.permute(0, 2, 3, 1).reshape(64, -1).t()).view(B, ref.shape[2], ref.shape[3], 64).permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())          # fp16 operand rounding of x
+    # masked cast
+    valid = (torch.rand(B * h * w, generator=g) > 0.3).to(torch.uint8).cuda()
+    m = ops.mask_rows(x, valid).float()
+    assert torch.equal(m, (x * valid[:, None]).half().float())
+    # proposal scores / top-k / gather
+    Sq, T = 1234, 9
+    q = torch.randn(B * Sq, 256, generator=g).cuda()
+    text = torch.randn(B * T, 256, generator=g).cuda()
+    sc = ops.proposal_scores(q, text, B, Sq, T)
+    ref = (q.view(B, Sq, 256) @ text.view(B, T, 256).transpose(1, 2)).max(-1)[0]
+    assert float((sc - ref).abs().max()) <= 1e-3
+    idx = ops.topk_rows(sc, 900)
+    tv, ti = torch.topk(sc, 900, dim=1)
+    assert torch.equal(torch.gather(sc, 1, idx), tv)                                    # same scores in the same (descending) order
+    assert all(len(set(r.tolist())) == 900 for r in idx)
+    gat = ops.gather_rows(q.view(B, Sq, 256), idx)
+    assert torch.equal(gat, torch.gather(q.view(B, Sq, 256), 1, idx.unsqueeze(-1).repeat(1, 1, 256)))
+    # heads
+    delta, refp = torch.randn(B, 900, 4, generator=g).cuda(), torch.rand(B, 900, 4, generator=g).cuda()
+    refp[0, 0] = torch.tensor([0.0, 1.0, 0.5, 1e-7])
+    bx = ops.box_finish(delta, refp)
+    assert float((bx - (delta + torch.special.logit(refp, eps=1e-5)).sigmoid()).abs().max()) <= 1e-6
+    hs = torch.randn(B, 900, 256, generator=g).cuda() * 0.2
+    tx = text.view(B, T, 256)
+    lg = ops.contrastive_sigmoid(hs, tx, 256)
+    assert lg.shape == (B, 900, 256) and float(lg[..., T:].abs().max()) == 0.0
+    assert float((lg[..., :T] - (hs @ tx.transpose(1, 2)).sigmoid()).abs().max()) <= 1e-5
+
+
+def test_own_forward_matches_the_module_graph(pair):
+    """GroundingDINO.raw_outputs through vlm/gdino_forward.py (own model-level forward) vs the same weights through HF's
+    GroundingDinoModel.forward on the same kernels (VLFM_GDINO_OWN_FORWARD=0 path): same proposals, same outputs up to the fp16
+    operand rounding of the few ops that differ (neck GEMM instead of cuDNN conv)."""
+    orc, g = pair
+    assert g.fwd is not None
+    img = make_rgb(np.random.default_rng(9), 480, 640)
+    ids = g.tokenizer.encode("chair . person . dog .")
+    a_l, a_b = (t.clone() for t in g.raw_outputs(img, ids))
+    fwd, g.fwd = g.fwd, None
+    g._static.clear()
+    try:
+        b_l, b_b = (t.clone() for t in g.raw_outputs(img, ids))
+    finally:
+        g.fwd = fwd
+        g._static.clear()
+    d = (a_b[:, None, :] - b_b[None, :, :]).abs().sum(-1).min(dim=1)[0]
+    print("own forward vs module graph: box set distance mean", float(d.mean()), "logit mean abs diff", float((a_l - b_l).abs().mean()))
+    assert float(d.mean()) <= 2e-2 and float((a_l - b_l).abs().mean()) <= 1e-2

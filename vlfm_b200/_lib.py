@@ -64,7 +64,8 @@ _SIGNATURES = {
     "vlfm_holes_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_fill_small_holes": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]),
     "vlfm_gemm_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
-    "vlfm_gemm_f16_resid_ln": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 6 + [_P, _P, _P, C.c_int, _P, C.c_int, C.c_float, _P, _P]),
+    "vlfm_gemm_f16_resid_ln": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 6 + [_P, _P, _P, C.c_int, _P, C.c_int, C.c_float, _P, C.c_size_t, _P]),
+    "vlfm_layernorm_reduce": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, _P]),
     "vlfm_gemm_debug_timeline": (None, [_P]),
     "vlfm_preprocess_im2col": (C.c_int, [_P, _P, _P] + [C.c_int] * 7 + [_P, _P, C.c_int, _P, _P, C.c_int,
                                          C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
@@ -82,6 +83,14 @@ _SIGNATURES = {
     "vlfm_holes_batch_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_fill_small_holes_batch": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, C.c_size_t, _P, _P, C.c_size_t, _P]),
     "vlfm_itc_head": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "vlfm_groupnorm_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_float, _P, C.c_int, C.c_int, _P]),
+    "vlfm_im2col3x3s2": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vlfm_mask_rows_f16": (C.c_int, [_P, _P, _P, C.c_long, C.c_int, _P]),
+    "vlfm_proposal_scores": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "vlfm_topk_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "vlfm_gather_rows": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "vlfm_box_finish": (C.c_int, [_P, _P, _P, C.c_long, _P]),
+    "vlfm_contrastive_sigmoid": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vlfm_object_cloud_extract": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_double, C.c_double, _P, C.c_int, _P, _P,
                                             C.c_size_t, _P]),
     "vlfm_dbscan_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),

@@ -45,40 +45,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// LayerNorm of one row by one warp, reading the row from L2 (ld.cg) three times instead of holding it in
-// registers (used after a grid-wide barrier inside the residual GEMM, where register pressure matters).
-__device__ __forceinline__ void ln_row_warp(const float* __restrict__ xr, const float* __restrict__ gamma,
-                                            const float* __restrict__ beta, __half* o16, float* o32, int D, float eps, int lane) {
-  const int D4 = D >> 2;
-  const float4* x4 = reinterpret_cast<const float4*>(xr);
-  float s = 0.f;
-  for (int j = lane; j < D4; j += 32) { const float4 v = __ldcg(x4 + j); s += (v.x + v.y) + (v.z + v.w); }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)D;
-  float q = 0.f;
-  for (int j = lane; j < D4; j += 32) {
-    const float4 v = __ldcg(x4 + j);
-    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / (float)D + eps);
-  for (int j = lane; j < D4; j += 32) {
-    const float4 v = __ldcg(x4 + j);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j), bt = __ldg(reinterpret_cast<const float4*>(beta) + j);
-    float4 y;
-    y.x = (v.x - mean) * rstd * g.x + bt.x; y.y = (v.y - mean) * rstd * g.y + bt.y;
-    y.z = (v.z - mean) * rstd * g.z + bt.z; y.w = (v.w - mean) * rstd * g.w + bt.w;
-    if (o16) {
-      __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
-      *reinterpret_cast<uint2*>(o16 + 4 * j) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-    }
-    if (o32) *reinterpret_cast<float4*>(o32 + 4 * j) = y;
-  }
-}
-
 __device__ __forceinline__ float ld_cg_f32(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
 

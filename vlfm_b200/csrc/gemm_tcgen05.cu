@@ -94,9 +94,9 @@ struct GemmArgs {
   int M, N, K, ldo, epi;
   int kb_per_split;   // K-blocks per grid.z slice (split-K, residual epilogue only)
   unsigned long long* dbg;
-  // optional fused LayerNorm of the updated residual rows (grid-wide barrier, then warp-per-row LN)
-  const float* ln_gamma; const float* ln_beta; __half* ln_out16; float* ln_out32; unsigned* ln_sync;
-  int ln_ld16, ln_ld32; float ln_eps;
+  // VLFM_EPI_PARTIAL_F32 (deterministic split-K): split z stores its tile at out + z * split_stride (plain stores, no atomics);
+  // the consumer (layernorm_reduce_kernel) adds the partial sums to the residual stream in a fixed order
+  long long split_stride;
   // "tail rows": when M = 128*q + r with 1 <= r <= GEMM_TAIL_MAX (ViT: 257 tokens), only q row tiles are launched and the CTAs
   // of the last one also compute the r extra rows on CUDA cores from the W tiles already staged for the tensor core
   const __half* a_tail; int lda, tail_rows, tail_row0;
@@ -170,13 +170,14 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
         for (int j = 0; j < 32; ++j) if (n0 + j < g.N) o[j] = __float2half_rn(v[j]);   // static indices: keeps v[] in registers
       }
     } else {
-      float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + n0;
+      const bool partial = (g.epi == VLFM_EPI_PARTIAL_F32);
+      float* o = reinterpret_cast<float*>(g.out) + (partial ? (size_t)blockIdx.z * (size_t)g.split_stride : 0) + (size_t)row * g.ldo + n0;
       const bool add = (g.epi == VLFM_EPI_BIAS_RESID_F32);
       if (fullw) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (split) { red_add_f32x4(o + j, t.x, t.y, t.z, t.w); continue; }
+          if (split && !partial) { red_add_f32x4(o + j, t.x, t.y, t.z, t.w); continue; }
           if (add) {
             float4 old = *reinterpret_cast<const float4*>(o + j);
             t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (n0 + j < g.N) {
-            if (split) atomicAdd(o + j, v[j]);
+            if (split && !partial) atomicAdd(o + j, v[j]);
             else o[j] = add ? o[j] + v[j] : v[j];
           }
         }
@@ -243,7 +244,6 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) g.dbg[1] = clock64();
-  unsigned ln_epoch = 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -257,7 +257,6 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       pdl_wait();
       if (dbg) g.dbg[2] = clock64();
-      if (g.ln_sync) ln_epoch = *reinterpret_cast<volatile unsigned*>(g.ln_sync + 1);
       for (int kb = 0; kb < pre; ++kb)
         tma_load_2d(smem_u32(sA + kb * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * kb);
       int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
@@ -362,8 +361,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               else if (g.epi == VLFM_EPI_BIAS_RELU_F16) v = fmaxf(v, 0.f);
               reinterpret_cast<__half*>(g.out)[o] = __float2half_rn(v);
             } else {
-              float* po = reinterpret_cast<float*>(g.out) + o;
-              if (split) atomicAdd(po, v);
+              const bool partial = (g.epi == VLFM_EPI_PARTIAL_F32);
+              float* po = reinterpret_cast<float*>(g.out) + (partial ? (size_t)blockIdx.z * (size_t)g.split_stride : 0) + o;
+              if (split && !partial) atomicAdd(po, v);
               else *po = (g.epi == VLFM_EPI_BIAS_RESID_F32) ? *po + v : v;
             }
           }
@@ -377,36 +377,6 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (g.ln_sync) {
-    pdl_wait();
-    // ---- fused LayerNorm: every CTA's residual update is done -> grid barrier -> rows are normalised by all warps.
-    // All CTAs are co-resident (the host only fuses single-wave launches).
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-      const unsigned old = atomicAdd(g.ln_sync, 1u);
-      if (old == total - 1) {
-        g.ln_sync[0] = 0;
-        __threadfence();
-        atomicAdd(g.ln_sync + 1, 1u);
-      } else {
-        unsigned spin = 0;
-        while (*reinterpret_cast<volatile unsigned*>(g.ln_sync + 1) == ln_epoch) {
-          __nanosleep(64);
-          if (++spin > (1u << 24)) __trap();
-        }
-      }
-      __threadfence();
-    }
-    __syncthreads();
-    const unsigned nwarps = GEMM_THREADS / 32;
-    const unsigned gw = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * nwarps + warp;
-    const unsigned tw = gridDim.x * gridDim.y * gridDim.z * nwarps;
-    const float* xbase = reinterpret_cast<const float*>(g.out);
-    for (unsigned r = gw; r < (unsigned)g.M; r += tw)
-      ln_row_warp(xbase + (size_t)r * g.ldo, g.ln_gamma, g.ln_beta, g.ln_out16 ? g.ln_out16 + (size_t)r * g.ln_ld16 : nullptr,
-                  g.ln_out32 ? g.ln_out32 + (size_t)r * g.ln_ld32 : nullptr, g.N, g.ln_eps, lane);
-  }
   if (dbg && threadIdx.x == 0) g.dbg[6] = clock64();
   if (g.dbg && threadIdx.x == 0 && cta_lin < 2048) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[9 + 2 * cta_lin] = t; }
   if (warp == 1) {
@@ -751,7 +721,8 @@ static int launch_gemm_2cta_persistent(const CUtensorMap& ta, const void* W, int
 
 using namespace vlfm;
 
-static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, int lda, int ldw, GemmArgs g, void* stream, bool* fused);
+static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, int lda, int ldw, GemmArgs g, void* stream, float* d_partials,
+                         size_t partial_bytes, int* splits_out);
 
 extern "C" void vlfm_gemm_debug_timeline(unsigned long long* d_buf8) { vlfm::g_gemm_dbg = d_buf8; }
 
@@ -761,11 +732,13 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
     set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
   if (epilogue < 0 || epilogue > 4) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr, 0, 0, 0};
-  return gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, nullptr);
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, 0, nullptr, 0, 0, 0};
+  return gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, nullptr, 0, nullptr);
 }
 
-static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, int lda, int ldw, GemmArgs g, void* stream, bool* fused) {
+static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, int lda, int ldw, GemmArgs g, void* stream, float* d_partials,
+                         size_t partial_bytes, int* splits_out) {
+  if (splits_out) *splits_out = 1;
   const int epilogue = g.epi;
   CUtensorMap ta;
   int rc = make_map(&ta, d_A, M, K, lda, BM);
@@ -783,8 +756,6 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
     const long tiles128 = (long)mt * ((N + 127) / 128);
     if (two && tiles128 >= 296 && N >= 256) {
       g.kb_per_split = num_k;
-      g.ln_sync = nullptr;                       // multi-wave problem: the caller runs LayerNorm as its own launch
-      if (fused) *fused = false;
       static int persist = -1;
       if (persist < 0) { const char* e = getenv("VLFM_GEMM_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
       if (persist) return launch_gemm_2cta_persistent<256, 6>(ta, d_W, ldw, g, st);
@@ -797,7 +768,7 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
   static int tail_on = -1;
   if (tail_on < 0) { const char* e = getenv("VLFM_GEMM_TAIL"); tail_on = (e && e[0] == '0') ? 0 : 1; }
   const int rem = M % BM;
-  const bool tail = tail_on && M > BM && rem >= 1 && rem <= GEMM_TAIL_MAX && !g.ln_sync && num_k * BK <= GEMM_TAIL_KMAX;
+  const bool tail = tail_on && M > BM && rem >= 1 && rem <= GEMM_TAIL_MAX && num_k * BK <= GEMM_TAIL_KMAX;
   int best_bn = 128, best_s = 1, force_shallow = 0;
   double best_t = 1e30;
   bool best_tail = false;
@@ -849,9 +820,12 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
   if (shallow < 0) { const char* e = getenv("VLFM_GEMM_SHALLOW"); shallow = (e && e[0] == '1') ? 1 : 0; }  // measured slower on B200 (3 stages cannot cover the latency): off
   const bool one_wave = (long)(best_tail ? M / BM : mt) * ((N + best_bn - 1) / best_bn) * best_s <= 148;
   if (best_tail) { g.a_tail = (const __half*)d_A + (size_t)(M / BM) * BM * lda; g.lda = lda; g.tail_rows = rem; g.tail_row0 = (M / BM) * BM; }
-  if (g.ln_sync) {                               // grid-barrier fusion needs every CTA resident at once
-    if (one_wave) { if (fused) *fused = true; }
-    else { g.ln_sync = nullptr; if (fused) *fused = false; }
+  (void)one_wave;
+  // deterministic split-K: the splits store their partial sums side by side and the caller reduces them in a fixed order
+  const int launched_splits = (num_k + g.kb_per_split - 1) / g.kb_per_split;      // grid.z (can be below best_s when num_k is small)
+  if (d_partials && launched_splits > 1 && epilogue == VLFM_EPI_BIAS_RESID_F32 && (size_t)launched_splits * (size_t)M * (size_t)N * 4 <= partial_bytes) {
+    g.epi = VLFM_EPI_PARTIAL_F32; g.out = d_partials; g.ldo = N; g.split_stride = (long long)M * N;
+    if (splits_out) *splits_out = launched_splits;
   }
   if (((shallow && one_wave) || force_shallow) && best_bn != 96) {
     if (best_bn == 128) return launch_gemm<128, 3>(ta, d_W, ldw, g, st);
@@ -866,19 +840,25 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
 
 extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out16, float* d_out32,
                    int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream);
+extern "C" int vlfm_layernorm_reduce(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                                     const float* d_beta, void* d_out16, float* d_out32, int rows, int D, int ldx, int ldo16, int ldo32,
+                                     float eps, void* stream);
 
+// x += A @ W^T + bias ; out = LayerNorm(x) -- bitwise reproducible: when the plan splits K, the splits store their partial sums
+// in d_partials (no atomics) and the LayerNorm kernel adds them to x in split order before normalising; an unsplit GEMM adds
+// into x directly (one writer per element).  (Round 1 reduced the splits with red.global.add: the order of arrival varied from run
+// to run and the 39-layer residual stream amplified the last-bit differences to ~6e-5 on the cosine.)
 extern "C" int vlfm_gemm_f16_resid_ln(const void* d_A, const void* d_W, const float* d_bias, float* d_x, int M, int N, int K,
                                       int lda, int ldw, int ldx, const float* d_gamma, const float* d_beta, void* d_out16,
-                                      int ld16, float* d_out32, int ld32, float eps, uint32_t* d_sync2, void* stream) {
-  if (!d_A || !d_W || !d_x || !d_gamma || !d_beta || (!d_out16 && !d_out32) || !d_sync2 || M < 1 || N < 1 || K < 1) {
+                                      int ld16, float* d_out32, int ld32, float eps, float* d_partials, size_t partial_bytes, void* stream) {
+  if (!d_A || !d_W || !d_x || !d_gamma || !d_beta || (!d_out16 && !d_out32) || M < 1 || N < 1 || K < 1) {
     set_error("vlfm_gemm_f16_resid_ln: bad argument"); return VLFM_E_INVALID; }
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldx & 7) || (N & 3) || (ld16 & 3) || (ld32 & 3) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) ||
-      ((uintptr_t)d_x & 15)) { set_error("vlfm_gemm_f16_resid_ln: alignment (K, strides %% 8; N %% 4; 16-byte pointers)"); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, g_gemm_dbg,
-             d_gamma, d_beta, (__half*)d_out16, d_out32, d_sync2, ld16, ld32, eps};
-  bool fused = false;
-  int rc = gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, &fused);
+      ((uintptr_t)d_x & 15) || ((uintptr_t)d_partials & 15)) { set_error("vlfm_gemm_f16_resid_ln: alignment (K, strides %% 8; N %% 4; 16-byte pointers)"); return VLFM_E_INVALID; }
+  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, g_gemm_dbg, 0, nullptr, 0, 0, 0};
+  int splits = 1;
+  int rc = gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, d_partials, partial_bytes, &splits);
   if (rc) return rc;
-  if (!fused) return vlfm_layernorm(d_x, d_gamma, d_beta, d_out16, d_out32, M, N, ldx, ld16, ld32, eps, stream);
-  return VLFM_OK;
+  if (splits > 1) return vlfm_layernorm_reduce(d_x, d_partials, splits, (long long)M * N, d_gamma, d_beta, d_out16, d_out32, M, N, ldx, ld16, ld32, eps, stream);
+  return vlfm_layernorm(d_x, d_gamma, d_beta, d_out16, d_out32, M, N, ldx, ld16, ld32, eps, stream);
 }

@@ -134,6 +134,79 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
+// x_row += sum_s partial[s][row] (s = 0 .. splits-1, in that order), written back; then LayerNorm of the updated row.
+// The deterministic reduction of a split-K residual GEMM (vlfm_gemm_f16_resid_ln): same structure as layernorm_kernel.
+template <int MAXV4>
+__global__ void __launch_bounds__(128)
+layernorm_reduce_kernel(float* x, const float* __restrict__ partials, int splits, long long split_stride,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out16,
+                        float* out32, int rows, int D, int ldx, int ldo16, int ldo32, float eps) {   // out32 may alias x (post-LN blocks)
+  pdl_trigger();
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  float4 g[MAXV4], bt[MAXV4], v[MAXV4];
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {   // parameters do not depend on the predecessor kernel
+    const int j = lane + 32 * i;
+    g[i] = j < D4 ? __ldg(reinterpret_cast<const float4*>(gamma) + j) : make_float4(0, 0, 0, 0);
+    bt[i] = j < D4 ? __ldg(reinterpret_cast<const float4*>(beta) + j) : make_float4(0, 0, 0, 0);
+  }
+  pdl_wait();
+  if (row >= rows) return;
+  float4* xr = reinterpret_cast<float4*>(x + (size_t)row * ldx);
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = j < D4 ? xr[j] : make_float4(0, 0, 0, 0);
+  }
+  for (int sp = 0; sp < splits; ++sp) {          // fixed order: bitwise reproducible
+    const float4* pr = reinterpret_cast<const float4*>(partials + (size_t)sp * (size_t)split_stride + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < MAXV4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < D4) { const float4 t = __ldcg(pr + j); v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w; }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int j = lane + 32 * i;
+    if (j < D4) xr[j] = v[i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    if (lane + 32 * i < D4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int j = lane + 32 * i;
+    if (j < D4) {
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x;
+      y.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
+      y.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z;
+      y.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
+      if (out16) {
+        __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + 4 * j) = pk;
+      }
+      if (out32) *reinterpret_cast<float4*>(out32 + (size_t)row * ldo32 + 4 * j) = y;
+    }
+  }
+}
+
 // ------------------------------------------------------------------- attention ----
 __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -430,6 +503,25 @@ extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const floa
   else if (D <= 128 * 12) e = launch_pdl(layernorm_kernel<12>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
   else { set_error("vlfm_layernorm: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
   { int rc = check_cuda(e, "layernorm_kernel"); if (rc) return rc; }
+  count_launch();
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_layernorm_reduce(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                                     const float* d_beta, void* d_out16, float* d_out32, int rows, int D, int ldx, int ldo16, int ldo32,
+                                     float eps, void* stream) {
+  if (!d_x || !d_partials || !d_gamma || !d_beta || (!d_out16 && !d_out32) || rows < 1 || D < 1 || splits < 1 || splits > 16) {
+    set_error("vlfm_layernorm_reduce: bad argument"); return VLFM_E_INVALID; }
+  if ((D & 3) || (ldx & 3) || (ldo16 & 3) || (ldo32 & 3) || (split_stride & 3)) { set_error("vlfm_layernorm_reduce: D and strides must be multiples of 4"); return VLFM_E_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((rows + 3) / 4);
+  __half* o16 = (__half*)d_out16;
+  cudaError_t e;
+  if (D <= 128 * 2) e = launch_pdl(layernorm_reduce_kernel<2>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else if (D <= 128 * 6) e = launch_pdl(layernorm_reduce_kernel<6>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else if (D <= 128 * 12) e = launch_pdl(layernorm_reduce_kernel<12>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  else { set_error("vlfm_layernorm_reduce: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
+  { int rc = check_cuda(e, "layernorm_reduce_kernel"); if (rc) return rc; }
   count_launch();
   return VLFM_OK;
 }

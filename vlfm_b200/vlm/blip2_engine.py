@@ -42,9 +42,12 @@ class Blip2ITCEngine:
         self._load(state_dict)
         self._alloc(max_batch)
         self.text_feat = torch.zeros(dims.proj, dtype=F32, device=self.dev)
-        # measured on B200: the in-kernel grid barrier costs more than the separate LayerNorm launch (4.01 vs 3.38 ms/step): off
-        self.fuse_ln = os.environ.get("VLFM_FUSE_LN", "0") == "1"
-        self._sync = torch.zeros(2, dtype=torch.int32, device=self.dev)   # grid-barrier words of the fused GEMM+LN
+        # residual GEMM + LayerNorm as one C-ABI call with a deterministic split-K reduction (partial sums stored side by side, added
+        # to the residual stream in split order by the LayerNorm launch): the cosine is bitwise reproducible run to run.
+        # VLFM_DET_SPLITK=0 restores round 1's red.global.add reduction (order of arrival, ~6e-5 spread on the cosine).
+        self.fuse_ln = os.environ.get("VLFM_DET_SPLITK", "1") != "0"
+        rows = min(max_batch * dims.tokens, 1024)      # larger problems never split K (2-CTA 256x256 tiles)
+        self._partials = torch.empty(8 * rows * max(dims.v_hidden, dims.q_hidden), dtype=F32, device=self.dev)
 
     # ------------------------------------------------------------------ weights ----
     def _load(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -153,7 +156,7 @@ class Blip2ITCEngine:
         _lib.check(rc, "vlfm_gemm_f16")
 
     def _gemm_resid_ln(self, a, w, bias, x, g, b, out16, out32, eps):
-        """x += a @ w^T + bias ; LayerNorm(x) -> out16 / out32 (one launch when the GEMM is a single wave)."""
+        """x += a @ w^T + bias ; LayerNorm(x) -> out16 / out32 (GEMM launch + reduce/LayerNorm launch, bitwise reproducible)."""
         if not self.fuse_ln:
             self._gemm(a, w, bias, _lib.EPI_BIAS_RESID_F32, x)
             self._ln(x, g, b, out16, out32, eps)
@@ -162,7 +165,8 @@ class Blip2ITCEngine:
         rc = self.lib.vlfm_gemm_f16_resid_ln(a.data_ptr(), w.data_ptr(), _lib.ptr(bias), x.data_ptr(), M, w.shape[0], K, a.stride(0),
                                              w.stride(0), x.stride(0), g.data_ptr(), b.data_ptr(), _lib.ptr(out16),
                                              out16.stride(0) if out16 is not None else 0, _lib.ptr(out32),
-                                             out32.stride(0) if out32 is not None else 0, eps, self._sync.data_ptr(), _lib.stream_ptr())
+                                             out32.stride(0) if out32 is not None else 0, eps, self._partials.data_ptr(),
+                                             self._partials.numel() * 4, _lib.stream_ptr())
         _lib.check(rc, "vlfm_gemm_f16_resid_ln")
 
     def _ln(self, x, g, b, out16, out32, eps):

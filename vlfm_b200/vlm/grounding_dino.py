@@ -107,6 +107,14 @@ class GroundingDINO:
         self.model = model.to(device).eval()
         # feature enhancer / decoder: nn.Linear -> tcgen05 GEMM, deformable-attention sampling -> vlfm_msda_forward
         self.accel = accelerate(self.model) if os.environ.get("VLFM_GDINO_ACCEL", "1") != "0" else {}
+        # model-level glue (neck, proposal scoring, top-900 selection, heads) on the library's kernels; VLFM_GDINO_OWN_FORWARD=0 keeps
+        # HF's GroundingDinoModel.forward for A/B comparisons
+        self.fwd = None
+        if os.environ.get("VLFM_GDINO_OWN_FORWARD", "1") != "0":
+            from .gdino_forward import GdinoForward
+            from .gdino_ops import LibOps
+
+            self.fwd = GdinoForward(self.model, LibOps(), self.backbone)
         self.caption = caption
         self.box_threshold = box_threshold
         self.text_threshold = text_threshold
@@ -136,6 +144,10 @@ class GroundingDINO:
 
     def _forward_static(self, st):
         """One forward on the static buffers of ``st`` (eager or under CUDA-graph capture)."""
+        if self.fwd is not None:
+            st["logits"], st["boxes"] = self.fwd.forward(st["img"], st["key_ids"])
+            st["keep"] = self.fwd.last       # a captured graph reads the cached shape / caption constants by address: keep them alive
+            return
         self._features.maps = self.backbone.forward(st["img"])
         out = self.model(pixel_values=st["dummy"], input_ids=st["ids"], token_type_ids=st["tt"], attention_mask=st["am"], pixel_mask=st["pm"])
         st["logits"], st["boxes"] = out.logits.sigmoid(), out.pred_boxes
@@ -161,7 +173,7 @@ class GroundingDINO:
             ids = torch.tensor([list(key[3])], dtype=torch.long, device=self.device).expand(b, -1).contiguous()
             st = {"img": torch.empty_like(images), "ids": ids, "tt": torch.zeros_like(ids), "am": torch.ones_like(ids),
                   "dummy": torch.zeros(b, 3, h, w, device=self.device),   # only its shape is used (pixel mask); features come from our engine
-                  "pm": torch.ones(b, h, w, dtype=torch.long, device=self.device), "calls": 0, "graph": None}
+                  "pm": torch.ones(b, h, w, dtype=torch.long, device=self.device), "calls": 0, "graph": None, "key_ids": list(key[3])}
             if len(self._static) >= 4:
                 self._static.pop(next(iter(self._static)))
             self._static[key] = st

@@ -92,7 +92,13 @@ class SwinBackboneEngine:
         return self._bufs[key]
 
     @torch.inference_mode()
-    def forward(self, images: torch.Tensor) -> List[torch.Tensor]:
+    def forward_rows(self, images: torch.Tensor):
+        """images [B,H,W,3] uint8 (device) -> [(rows [B*h*w, C] fp32 in NHWC order, h, w)] per out stage: what the neck's row GEMMs
+        consume (vlm/gdino_forward.py) -- no NCHW permute / copy."""
+        return self.forward(images, rows=True)
+
+    @torch.inference_mode()
+    def forward(self, images: torch.Tensor, rows: bool = False) -> List[torch.Tensor]:
         """images [B,H,W,3] uint8 (device) -> feature maps [B,C_s,H_s,W_s] fp32 for the configured out stages."""
         B, H, W, _ = images.shape
         assert images.dtype == torch.uint8 and images.is_contiguous()
@@ -131,7 +137,7 @@ class SwinBackboneEngine:
                 if "out_ln" in stage:
                     o = torch.empty(n, C, dtype=F32, device=self.dev)
                     self._ln(x, stage["out_ln"], None, o)
-                    feats.append(o.view(B, h, w, C).permute(0, 3, 1, 2).contiguous())
+                    feats.append((o, h, w) if rows else o.view(B, h, w, C).permute(0, 3, 1, 2).contiguous())
                 if "merge_w" in stage:
                     h2, w2 = (h + 1) // 2, (w + 1) // 2
                     n2 = B * h2 * w2
