@@ -62,7 +62,17 @@ class GdinoForward:
         self.text_proj_b = core.text_projection.bias.detach().float().contiguous()
 
         def mlp(head):
-            return [(ops.weight(l.weight.detach()), l.bias.detach().float().contiguous()) for l in head.layers]
+            """3-layer box head as GEMM operands; the 4-wide last layer is zero-padded to 8 outputs (the GEMM's store granularity),
+            the caller keeps the first four columns."""
+            out = []
+            for l in head.layers:
+                w, b = l.weight.detach().float(), l.bias.detach().float()
+                if w.shape[0] % 8:
+                    pad = 8 - w.shape[0] % 8
+                    w = torch.cat([w, w.new_zeros(pad, w.shape[1])], 0)
+                    b = torch.cat([b, b.new_zeros(pad)], 0)
+                out.append((ops.weight(w), b.contiguous()))
+            return out
 
         self.enc_bbox = mlp(core.encoder_output_bbox_embed)
         self.last_bbox = mlp(model.bbox_embed[self.cfg.decoder_layers - 1])
@@ -180,7 +190,7 @@ class GdinoForward:
         for i, (w_, b_) in enumerate(self.enc_bbox):
             x = ops.linear(x, w_, b_, relu=i < len(self.enc_bbox) - 1)
         anchors = ops.gather_rows(sc["anchor_logits"], topk)                                           # [B, nq, 4]
-        reference_points = (x.view(B, self.nq, 4) + anchors).sigmoid()
+        reference_points = (x[:, :4].reshape(B, self.nq, 4) + anchors).sigmoid()
         target = core.query_position_embeddings.weight.detach().unsqueeze(0).repeat(B, 1, 1)
         # ---- decoder (HF module, accelerated layers)
         dec = core.decoder(inputs_embeds=target, vision_encoder_hidden_states=memory, vision_encoder_attention_mask=sc["mask_flatten"],
@@ -194,7 +204,7 @@ class GdinoForward:
         x = hs.reshape(B * self.nq, d)
         for i, (w_, b_) in enumerate(self.last_bbox):
             x = ops.linear(x, w_, b_, relu=i < len(self.last_bbox) - 1)
-        boxes = ops.box_finish(x.view(B, self.nq, 4), ref_last.contiguous())                           # sigmoid(delta + logit(ref, eps=1e-5))
+        boxes = ops.box_finish(x[:, :4].reshape(B, self.nq, 4).contiguous(), ref_last.contiguous())    # sigmoid(delta + logit(ref, eps=1e-5))
         logits = ops.contrastive_sigmoid(hs.contiguous(), text_mem.contiguous(), self.cfg.max_text_len)   # [B, nq, max_text_len]
         return logits, boxes
 
