@@ -306,6 +306,13 @@ int vlfm_explore_batch_workspace_bytes(int G, int batch, size_t* bytes);
 int vlfm_explore_update_batch(int G, int batch, const VlfmExploreEnv* h_envs, uint8_t* d_explored, const uint8_t* d_nav,
                               double* d_frontiers, int32_t* d_count, int32_t* d_status, void* d_workspace,
                               size_t workspace_bytes, void* h_pinned, size_t h_pinned_bytes, void* stream);
+/* The two halves of vlfm_explore_update_batch: `prepare` (host only) writes the per-environment device records into h_records
+ * (page-locked, >= batch * vlfm_explore_env_record_bytes()); `launch` uploads them and issues the launch sequence, whose geometry
+ * depends on `batch` only -- a caller can capture `launch` once in a CUDA graph and, every step, run `prepare` + replay.        */
+int vlfm_explore_prepare_batch(int G, int batch, const VlfmExploreEnv* h_envs, uint8_t* d_explored, const uint8_t* d_nav,
+                               double* d_frontiers, int32_t* d_count, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                               void* h_records, size_t h_records_bytes);
+int vlfm_explore_launch_batch(int G, int batch, void* d_workspace, const void* h_records, void* stream);
 /* fill_small_holes for a batch of depth images [batch,H,W] -> d_filled [batch,H,W]; d_status [batch] sticky overflow flags. */
 int vlfm_holes_batch_workspace_bytes(int H, int W, int batch, size_t* bytes);
 int vlfm_fill_small_holes_batch(const float* d_depth, int H, int W, int batch, double area_thresh, uint8_t* d_filled,

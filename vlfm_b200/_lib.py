@@ -80,6 +80,8 @@ _SIGNATURES = {
     "vlfm_explore_env_record_bytes": (C.c_size_t, []),
     "vlfm_explore_batch_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_explore_update_batch": (C.c_int, [C.c_int, C.c_int, C.POINTER(ExploreEnv), _P, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "vlfm_explore_prepare_batch": (C.c_int, [C.c_int, C.c_int, C.POINTER(ExploreEnv), _P, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t]),
+    "vlfm_explore_launch_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, _P]),
     "vlfm_holes_batch_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_fill_small_holes_batch": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, C.c_size_t, _P, _P, C.c_size_t, _P]),
     "vlfm_itc_head": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

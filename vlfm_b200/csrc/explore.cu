@@ -1145,15 +1145,19 @@ size_t carve(ExEnv* e, uint8_t* base, size_t frame_cells, int frame_side, int ma
 }
 
 inline int nblk(long n, int t = 256, int cap = 2368) { long b = (n + t - 1) / t; return (int)(b < 1 ? 1 : (b > cap ? cap : b)); }
+// Launch geometry of the batched sequences is FIXED (every kernel is grid-stride over its frame): the sequence of a call depends
+// on the batch size only, so a caller can capture it in a CUDA graph and replay it with new per-environment records.
+inline int gx_cells(int B) { return B >= 16 ? 148 : (B >= 4 ? 296 : 592); }     // blocks.x of the per-cell kernels
+constexpr int GX_ROWS = 74;                                                     // blocks.x of the per-row kernels (8 warps each)
 
 // external contours of image `id` of every environment: CCL fg/bg, top-level roots in cv2 order, traced chains.
 // n_max / h_max / per_max: the largest image over the environments of the call.
-void contours(const ExEnv* d_envs, int B, int id, long n_max, int h_max, int per_max, cudaStream_t st, int keep_fog, int mode, int mark_exterior) {
-  const int bx = nblk(n_max, 256, B > 8 ? 592 : 2368);
-  ccl_init2_kernel<<<dim3(nblk(h_max, 8, 592), B), 256, 0, st>>>(d_envs, id, keep_fog);
+void contours(const ExEnv* d_envs, int B, int id, cudaStream_t st, int keep_fog, int mode, int mark_exterior) {
+  const int bx = gx_cells(B);
+  ccl_init2_kernel<<<dim3(GX_ROWS, B), 256, 0, st>>>(d_envs, id, keep_fog);
   ccl_merge2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id, mode == 2);
   ccl_flatten2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id);
-  bg_outer_kernel<<<dim3(nblk(per_max), B), 256, 0, st>>>(d_envs, id, mark_exterior);
+  bg_outer_kernel<<<dim3(16, B), 256, 0, st>>>(d_envs, id, mark_exterior);
   collect_roots_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id);
   sort_roots_kernel<<<dim3(1, B), 1024, 0, st>>>(d_envs);
   if (mode == 2) mark_holes_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, id);
@@ -1206,36 +1210,32 @@ extern "C" int vlfm_explore_batch_workspace_bytes(int G, int batch, size_t* byte
   return VLFM_OK;
 }
 
-// Batched explore step.  h_envs: `batch` VlfmExploreEnv records (host memory).  d_explored / d_nav: [nslots, G, G] uint8.
+// Batched explore step = vlfm_explore_prepare_batch (host: per-environment records into page-locked staging) +
+// vlfm_explore_launch_batch (device: record upload + the launch sequence; CUDA-graph capturable, its launch geometry depends on
+// `batch` only).  h_envs: `batch` VlfmExploreEnv records (host memory).  d_explored / d_nav: [nslots, G, G] uint8.
 // d_frontiers [batch, 4096, 2] float64 (x = col, y = row), d_count / d_status [batch] int32 (in call order).
-extern "C" int vlfm_explore_update_batch(int G, int batch, const VlfmExploreEnv* h_envs, uint8_t* d_explored, const uint8_t* d_nav,
-                                         double* d_frontiers, int32_t* d_count, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
-                                         void* h_pinned, size_t h_pinned_bytes, void* stream) {
-  if (!h_envs || !d_explored || !d_nav || !d_frontiers || !d_count || !d_status || !d_workspace || G < 8 || batch < 1 || batch > 65535) {
-    set_error("vlfm_explore_update_batch: bad argument"); return VLFM_E_INVALID; }
+extern "C" int vlfm_explore_prepare_batch(int G, int batch, const VlfmExploreEnv* h_envs, uint8_t* d_explored, const uint8_t* d_nav,
+                                          double* d_frontiers, int32_t* d_count, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                                          void* h_records, size_t h_records_bytes) {
+  if (!h_envs || !d_explored || !d_nav || !d_frontiers || !d_count || !d_status || !d_workspace || !h_records || G < 8 || batch < 1 || batch > 65535) {
+    set_error("vlfm_explore_prepare_batch: bad argument"); return VLFM_E_INVALID; }
   size_t need = 0;
   vlfm_explore_batch_workspace_bytes(G, batch, &need);
-  if (workspace_bytes < need) { set_error("vlfm_explore_update_batch: workspace %zu < %zu bytes", workspace_bytes, need); return VLFM_E_INVALID; }
-  cudaStream_t st = (cudaStream_t)stream;
+  if (workspace_bytes < need || h_records_bytes < sizeof(ExEnv) * (size_t)batch) {
+    set_error("vlfm_explore_prepare_batch: workspace %zu < %zu bytes or staging %zu < %zu", workspace_bytes, need, h_records_bytes, sizeof(ExEnv) * (size_t)batch);
+    return VLFM_E_INVALID; }
   const size_t per = carve(nullptr, nullptr, (size_t)G * G, G, EX_MAXC, true);
   uint8_t* wsb = (uint8_t*)d_workspace;
-  ExEnv* d_envs = (ExEnv*)(wsb + per * (size_t)batch);
-  // the environment records are staged in the caller's page-locked buffer when one is given (a pageable source makes
-  // cudaMemcpyAsync wait for the stream first)
-  std::vector<ExEnv> pageable;
-  ExEnv* envs;
-  if (h_pinned && h_pinned_bytes >= sizeof(ExEnv) * (size_t)batch) envs = (ExEnv*)h_pinned;
-  else { pageable.resize((size_t)batch); envs = pageable.data(); }
-  int w0_max = 0, sh_max = 0; long sn_max = 0; int sper_max = 0;
+  ExEnv* envs = (ExEnv*)h_records;
   for (int b = 0; b < batch; ++b) {
     const VlfmExploreEnv& in = h_envs[b];
     ExEnv& e = envs[b];
     memset(&e, 0, sizeof(ExEnv));
     carve(&e, wsb + per * (size_t)b, (size_t)G * G, G, EX_MAXC, true);
     const int L = (int)in.max_line_len, W0 = 2 * L + 9;
-    if (W0 > WIN_MAX || L < 1) { set_error("vlfm_explore_update_batch: max_line_len %d unsupported (window %d > %d)", L, W0, WIN_MAX); return VLFM_E_UNSUPPORTED; }
+    if (W0 > WIN_MAX || L < 1) { set_error("vlfm_explore_prepare_batch: max_line_len %d unsupported (window %d > %d)", L, W0, WIN_MAX); return VLFM_E_UNSUPPORTED; }
     int x0 = in.frame[0], y0 = in.frame[1], x1 = in.frame[2], y1 = in.frame[3];
-    if (x0 < 0 || y0 < 0 || x1 > G || y1 > G || x1 - x0 < 1 || y1 - y0 < 1 || in.slot < 0) { set_error("vlfm_explore_update_batch: bad frame / slot (env %d)", b); return VLFM_E_INVALID; }
+    if (x0 < 0 || y0 < 0 || x1 > G || y1 > G || x1 - x0 < 1 || y1 - y0 < 1 || in.slot < 0) { set_error("vlfm_explore_prepare_batch: bad frame / slot (env %d)", b); return VLFM_E_INVALID; }
     e.G = G;
     e.explored = d_explored + (size_t)in.slot * G * G; e.nav = d_nav + (size_t)in.slot * G * G;
     e.frontiers = d_frontiers + (size_t)b * MAXF * 2; e.out_count = d_count + b; e.out_status = d_status + b;
@@ -1246,60 +1246,72 @@ extern "C" int vlfm_explore_update_batch(int G, int batch, const VlfmExploreEnv*
     e.ext_l = x0 > 0; e.ext_t = y0 > 0; e.ext_r = x1 < G; e.ext_b = y1 < G;
     e.heading_deg = in.heading_deg; e.ray_len = in.max_line_len * 1.05; e.area_thresh = in.area_thresh_px;
     e.nv = sector_polygon(in.agent_col, in.agent_row, L, in.heading_deg - in.fov_deg / 2, in.heading_deg + in.fov_deg / 2, e.verts);   // R1
-    if (W0 > w0_max) w0_max = W0;
-    if (e.Sh > sh_max) sh_max = e.Sh;
-    if ((long)e.Sw * e.Sh > sn_max) sn_max = (long)e.Sw * e.Sh;
-    if (2 * (e.Sw + e.Sh) > sper_max) sper_max = 2 * (e.Sw + e.Sh);
   }
-  int rc = check_cuda(cudaMemcpyAsync(d_envs, envs, sizeof(ExEnv) * (size_t)batch, cudaMemcpyHostToDevice, st), "explore: environment records");
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_explore_launch_batch(int G, int batch, void* d_workspace, const void* h_records, void* stream) {
+  if (!d_workspace || !h_records || G < 8 || batch < 1 || batch > 65535) { set_error("vlfm_explore_launch_batch: bad argument"); return VLFM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per = carve(nullptr, nullptr, (size_t)G * G, G, EX_MAXC, true);
+  ExEnv* d_envs = (ExEnv*)((uint8_t*)d_workspace + per * (size_t)batch);
+  int rc = check_cuda(cudaMemcpyAsync(d_envs, h_records, sizeof(ExEnv) * (size_t)batch, cudaMemcpyHostToDevice, st), "explore: environment records");
   if (rc) return rc;
   const int B = batch;
-  const long wn = (long)w0_max * w0_max;
-  const int capx = B > 8 ? 592 : 2368;
-  const int bw = nblk(wn, 256, capx), bs = nblk(sn_max, 256, capx);
+  const int bc = gx_cells(B);
   // ---- R1: cone sector (window)
-  zero_planes_kernel<<<dim3(nblk((long)((w0_max + 31) / 32) * w0_max), B), 256, 0, st>>>(d_envs, FRAME_WIN);
+  zero_planes_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, FRAME_WIN);
   sector_edges_kernel<<<dim3(1, B), 64, 0, st>>>(d_envs);
-  planes_to_image_kernel<<<dim3(nblk(w0_max, 64), B), 64, 0, st>>>(d_envs, 0, 1, 0);
-  fog_masks_kernel<<<dim3(bw, B), 256, 0, st>>>(d_envs);
+  planes_to_image_kernel<<<dim3(8, B), 64, 0, st>>>(d_envs, 0, 1, 0);
+  fog_masks_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
   // ---- R2/R3/R4: obstacle contours -> rays -> cut
-  contours(d_envs, B, IMG_BLOCKED, wn, w0_max, 4 * w0_max, st, 0, 0, 0);
+  contours(d_envs, B, IMG_BLOCKED, st, 0, 0, 0);
   fog_gate_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs);
   simple_vertices_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
   rays_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
   thick_rays_kernel<<<dim3(64, B), 64, 0, st>>>(d_envs);
-  apply_cut_kernel<<<dim3(bw, B), 256, 0, st>>>(d_envs);
+  apply_cut_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
   // ---- R5: contours of the visible area, nearest to the agent, filled
-  contours(d_envs, B, IMG_VISIBLE, wn, w0_max, 4 * w0_max, st, 1, 0, 0);
+  contours(d_envs, B, IMG_VISIBLE, st, 1, 0, 0);
   contour_dist_kernel<<<dim3(EX_MAXC / 64, B), 64, 0, st>>>(d_envs, 0);
   contour_pick_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs, 0);
-  zero_planes_kernel<<<dim3(nblk((long)((w0_max + 31) / 32) * w0_max), B), 256, 0, st>>>(d_envs, FRAME_WIN);
+  zero_planes_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, FRAME_WIN);
   chain_edges_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, FRAME_WIN);
-  planes_to_image_kernel<<<dim3(nblk(w0_max, 64), B), 64, 0, st>>>(d_envs, 1, 0, 1);
+  planes_to_image_kernel<<<dim3(8, B), 64, 0, st>>>(d_envs, 1, 0, 1);
   // ---- explored |= dilate3(new); explored[nav == 0] = 0  -> S frame images
-  explored_update_kernel<<<dim3(bs, B), 256, 0, st>>>(d_envs);
+  explored_update_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
   // ---- component selection (obstacle_map.py:128-146)
-  contours(d_envs, B, IMG_EXS, sn_max, sh_max, sper_max, st, 1, 1, 0);
+  contours(d_envs, B, IMG_EXS, st, 1, 1, 0);
   contour_dist_kernel<<<dim3(EX_MAXC / 64, B), 64, 0, st>>>(d_envs, 1);
   contour_pick_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs, 1);
-  {
-    int sw_max = 0;
-    for (int b = 0; b < batch; ++b) if (envs[b].Sw > sw_max) sw_max = envs[b].Sw;
-    zero_planes_kernel<<<dim3(nblk((long)((sw_max + 31) / 32) * sh_max), B), 256, 0, st>>>(d_envs, FRAME_S);
-  }
+  zero_planes_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs, FRAME_S);
   chain_edges_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs, FRAME_S);
-  planes_to_image_kernel<<<dim3(nblk(sh_max, 64), B), 64, 0, st>>>(d_envs, 2, 1, 1);   // no-op when a single contour exists (which == -1)
+  planes_to_image_kernel<<<dim3(64, B), 64, 0, st>>>(d_envs, 2, 1, 1);   // no-op when a single contour exists (which == -1)
   // ---- frontiers (obstacle_map.py:155-169 -> detect_frontier_waypoints)
-  paste_grow_kernel<<<dim3(bs, B), 256, 0, st>>>(d_envs);
-  contours(d_envs, B, IMG_UNEXP, sn_max, sh_max, sper_max, st, 1, 2, 1);
+  paste_grow_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
+  contours(d_envs, B, IMG_UNEXP, st, 1, 2, 1);
   absorb_small_kernel<<<dim3(128, B), 128, 0, st>>>(d_envs);
-  contours(d_envs, B, IMG_EX2, sn_max, sh_max, sper_max, st, 1, 0, 0);     // every external contour is walked (mode 0)
+  contours(d_envs, B, IMG_EX2, st, 1, 0, 0);     // every external contour is walked (mode 0)
   bad_flags_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
   frontier_kernel<<<dim3(1, B), FRONTIER_THREADS, 0, st>>>(d_envs);
   publish_kernel<<<B, 32, 0, st>>>(d_envs, 0);
-  VLFM_CHECK_LAUNCH("vlfm_explore_update_batch");
+  VLFM_CHECK_LAUNCH("vlfm_explore_launch_batch");
   count_launch(26);
   return VLFM_OK;
+}
+
+extern "C" int vlfm_explore_update_batch(int G, int batch, const VlfmExploreEnv* h_envs, uint8_t* d_explored, const uint8_t* d_nav,
+                                         double* d_frontiers, int32_t* d_count, int32_t* d_status, void* d_workspace, size_t workspace_bytes,
+                                         void* h_pinned, size_t h_pinned_bytes, void* stream) {
+  // without page-locked staging the records are built in a pageable buffer (cudaMemcpyAsync then waits for the stream first)
+  std::vector<ExEnv> pageable;
+  void* rec = h_pinned;
+  size_t rec_bytes = h_pinned_bytes;
+  if (!rec || rec_bytes < sizeof(ExEnv) * (size_t)batch) { if (batch < 1) { set_error("vlfm_explore_update_batch: bad argument"); return VLFM_E_INVALID; }
+    pageable.resize((size_t)batch); rec = pageable.data(); rec_bytes = sizeof(ExEnv) * (size_t)batch; }
+  int rc = vlfm_explore_prepare_batch(G, batch, h_envs, d_explored, d_nav, d_frontiers, d_count, d_status, d_workspace, workspace_bytes, rec, rec_bytes);
+  if (rc) return rc;
+  return vlfm_explore_launch_batch(G, batch, d_workspace, rec, stream);
 }
 
 extern "C" int vlfm_explore_workspace_bytes(int G, size_t* bytes) { return vlfm_explore_batch_workspace_bytes(G, 1, bytes); }
@@ -1353,13 +1365,12 @@ extern "C" int vlfm_fill_small_holes_batch(const float* d_depth, int H, int W, i
   int rc = check_cuda(cudaMemcpyAsync(d_envs, envs, sizeof(ExEnv) * (size_t)batch, cudaMemcpyHostToDevice, st), "holes: environment records");
   if (rc) return rc;
   const int B = batch;
-  const long n = (long)H * W;
-  const int bx = nblk(n, 256, B > 8 ? 592 : 2368);
+  const int bx = gx_cells(B);
   zero_mask_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs);
-  ccl_init2_kernel<<<dim3(nblk(H, 8, 592), B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
+  ccl_init2_kernel<<<dim3(GX_ROWS, B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
   ccl_merge2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
   ccl_flatten2_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs, IMG_UNEXP);
-  bg_outer_kernel<<<dim3(nblk(2 * (W + H)), B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
+  bg_outer_kernel<<<dim3(16, B), 256, 0, st>>>(d_envs, IMG_UNEXP, 0);
   collect_all_kernel<<<dim3(bx, B), 256, 0, st>>>(d_envs);
   trace_kernel<<<dim3(128, B), 64, 0, st>>>(d_envs, IMG_UNEXP, 0);
   static bool cfg = false;

@@ -69,6 +69,18 @@ class ObstacleMapBatch:
         self._fill_ws: Optional[torch.Tensor] = None
         self._fill_status = torch.zeros((batch,), dtype=torch.int32, device=dev)
         self._slot_ids = torch.arange(batch, dtype=torch.int32, device=dev)
+        # CUDA graph of the whole update (hole fill + scatter + dilate + explore): the launch geometry of every C-ABI call depends on
+        # the batch size only and the per-environment pose scalars travel in page-locked records, so after two eager calls with the
+        # same buffers the sequence is captured once and replayed (VLFM_MAP_GRAPH=0 disables; ~75 launches -> one graph launch)
+        import os
+
+        self.use_graph = os.environ.get("VLFM_MAP_GRAPH", "1") != "0"
+        self._graphs = {}
+        self._graph_key = None
+        self._graph_seen = 0
+        self._rec_pin = torch.zeros(rec * batch, dtype=torch.uint8).pin_memory()      # explore records read by the captured upload node
+        self._rec_ev = torch.cuda.Event()
+        self._rec_used = False
 
     # ---------------------------------------------------------------- helpers ----
     def _pinned(self) -> torch.Tensor:
@@ -96,23 +108,76 @@ class ObstacleMapBatch:
         return _sf.sframe(self.cover[slot], self.size, self.area_thresh_px)
 
     # ------------------------------------------------------------------ update ----
+    def _fill_envs(self, n: int, slots, agents, tf_host, max_depth: float, topdown_fov: float) -> None:
+        ppm = self.ppm
+        L = int(max_depth * ppm)
+        envs = self._envs
+        for i, s in enumerate(slots):
+            col, row = int(agents[i][0]), int(agents[i][1])
+            self._cover_add(s, _sf.fog_window(col, row, L))
+            tf = tf_host[i]
+            yaw = float(np.arctan2(tf[1, 0], tf[0, 0]))
+            e = envs[i]
+            e.slot, e.agent_col, e.agent_row = s, col, row
+            fr = self._frame(s)
+            e.frame[0], e.frame[1], e.frame[2], e.frame[3] = fr
+            e.heading_deg = float(np.rad2deg(wrap_heading(yaw + np.pi / 2)))     # current_angle = -yaw (:121)
+            e.fov_deg = float(np.rad2deg(topdown_fov))
+            e.max_line_len = float(max_depth * ppm)
+            e.area_thresh_px = float(self.area_thresh_px)
+
+    def _device_sequence(self, n: int, depth, tf_dev, p, slot_t, explore: bool, update_obstacles: bool, rec_pin: Optional[torch.Tensor]) -> None:
+        """the launches of one update on the current stream (eager or under CUDA-graph capture)"""
+        st = _lib.stream_ptr()
+        g = self.size
+        if update_obstacles:
+            h, w = int(depth.shape[1]), int(depth.shape[2])
+            fill = None
+            if self.hole_area_thresh != -1:          # fill_small_holes (img_utils.py:361-390) on the device
+                pin = self._pinned() if rec_pin is None else self._holes_pin
+                rc = self.lib.vlfm_fill_small_holes_batch(_lib.ptr(depth), h, w, n, float(self.hole_area_thresh), _lib.ptr(self._fill),
+                                                          _lib.ptr(self._fill_ws), self._fill_ws.numel() * 4, _lib.ptr(self._fill_status),
+                                                          pin.data_ptr(), pin.numel(), st)
+                if rec_pin is None:
+                    self._pinned_done()
+                _lib.check(rc, "vlfm_fill_small_holes_batch")
+                fill = self._fill
+            rc = self.lib.vlfm_obstacle_update(ctypes.byref(p), n, _lib.ptr(slot_t), _lib.ptr(self.obst), _lib.ptr(self.nav),
+                                               _lib.ptr(depth), _lib.ptr(tf_dev), _lib.ptr(fill), _lib.ptr(self.status), st)
+            _lib.check(rc, "vlfm_obstacle_update")
+        if not explore:
+            return
+        if rec_pin is None:
+            pin = self._pinned()
+            rc = self.lib.vlfm_explore_update_batch(g, n, self._envs, _lib.ptr(self.explored), _lib.ptr(self.nav), _lib.ptr(self._call_front),
+                                                    _lib.ptr(self._call_count), _lib.ptr(self._call_status), _lib.ptr(self._ex_ws),
+                                                    self._ex_ws.numel() * 4, pin.data_ptr(), pin.numel(), st)
+            self._pinned_done()
+            _lib.check(rc, "vlfm_explore_update_batch")
+        else:                                        # records already prepared in rec_pin by the caller
+            _lib.check(self.lib.vlfm_explore_launch_batch(g, n, _lib.ptr(self._ex_ws), rec_pin.data_ptr(), st), "vlfm_explore_launch_batch")
+        if slot_t is None:
+            self.frontiers[:n].copy_(self._call_front[:n]); self.count[:n].copy_(self._call_count[:n]); self.ex_status[:n].copy_(self._call_status[:n])
+        else:
+            idx = slot_t.long()
+            self.frontiers[idx] = self._call_front[:n]; self.count[idx] = self._call_count[:n]; self.ex_status[idx] = self._call_status[:n]
+
     def update(self, depth: Optional[torch.Tensor], tf_host: np.ndarray, tf_dev: torch.Tensor, min_depth: float, max_depth: float,
                fx: float, fy: float, topdown_fov: float, slots: Optional[Sequence[int]] = None, explore: bool = True,
                update_obstacles: bool = True) -> None:
         """depth [n,H,W] float32 (device) or None, tf_host [n,4,4] float64 (numpy: the pose scalars of the explore half are
         derived on the host exactly as the reference derives them), tf_dev [n,16] float64 (device, read by the obstacle
         kernels).  ``slots``: grid index of each row (default 0..n-1).  Asynchronous; IndexError conditions are polled by
-        ``check_index_error``."""
+        ``index_error``."""
         n = len(tf_host)
         slots = list(range(n)) if slots is None else [int(s) for s in slots]
         assert n <= self.batch and len(slots) == n
         g, ppm = self.size, self.ppm
-        st = _lib.stream_ptr()
         agents = self.xy_to_px(np.asarray(tf_host, dtype=np.float64)[:, :2, 3])     # (col, row) per env, obstacle_map.py:115-116
+        identity = slots == list(range(n))
         with torch.cuda.device(self.device):
-            slot_t = None
-            if slots != list(range(n)):
-                slot_t = torch.tensor(slots, dtype=torch.int32, device=self.device)
+            slot_t = None if identity else torch.tensor(slots, dtype=torch.int32, device=self.device)
+            p, first = None, False
             if update_obstacles:
                 assert depth is not None and depth.dtype == torch.float32 and depth.is_contiguous() and depth.shape[0] == n
                 h, w = int(depth.shape[1]), int(depth.shape[2])
@@ -121,56 +186,48 @@ class ObstacleMapBatch:
                 p = _lib.ObstacleParams(h, w, g, ppm, float(np.float32(max_depth - min_depth)), float(np.float32(min_depth)),
                                         float(np.float32(max_depth)), float(fx), float(fy), float(self.min_height), float(self.max_height),
                                         self.kernel, 1 if first else 0, half)
-                fill = None
-                if self.hole_area_thresh != -1:          # fill_small_holes (img_utils.py:361-390) on the device
-                    if self._fill is None or self._fill.shape[1:] != (h, w):
-                        nb = ctypes.c_size_t(0)
-                        _lib.check(self.lib.vlfm_holes_batch_workspace_bytes(h, w, self.batch, ctypes.byref(nb)), "vlfm_holes_batch_workspace_bytes")
-                        self._fill = torch.zeros((self.batch, h, w), dtype=torch.uint8, device=self.device)
-                        self._fill_ws = torch.zeros((nb.value + 3) // 4, dtype=torch.int32, device=self.device)
-                    pin = self._pinned()
-                    rc = self.lib.vlfm_fill_small_holes_batch(_lib.ptr(depth), h, w, n, float(self.hole_area_thresh), _lib.ptr(self._fill),
-                                                              _lib.ptr(self._fill_ws), self._fill_ws.numel() * 4, _lib.ptr(self._fill_status),
-                                                              pin.data_ptr(), pin.numel(), st)
-                    self._pinned_done()
-                    _lib.check(rc, "vlfm_fill_small_holes_batch")
-                    fill = self._fill
-                rc = self.lib.vlfm_obstacle_update(ctypes.byref(p), n, _lib.ptr(slot_t), _lib.ptr(self.obst), _lib.ptr(self.nav),
-                                                   _lib.ptr(depth), _lib.ptr(tf_dev), _lib.ptr(fill), _lib.ptr(self.status), st)
-                _lib.check(rc, "vlfm_obstacle_update")
+                if self.hole_area_thresh != -1 and (self._fill is None or self._fill.shape[1:] != (h, w)):
+                    nb = ctypes.c_size_t(0)
+                    _lib.check(self.lib.vlfm_holes_batch_workspace_bytes(h, w, self.batch, ctypes.byref(nb)), "vlfm_holes_batch_workspace_bytes")
+                    self._fill = torch.zeros((self.batch, h, w), dtype=torch.uint8, device=self.device)
+                    self._fill_ws = torch.zeros((nb.value + 3) // 4, dtype=torch.int32, device=self.device)
+                    self._holes_pin = torch.zeros(self._pin[0].numel(), dtype=torch.uint8).pin_memory()
+                    self._graphs.clear()
                 for i, s in enumerate(slots):
-                    col, row = int(agents[i][0]), int(agents[i][1])
-                    self._cover_add(s, _sf.obstacle_window(col, row, half, g))
+                    self._cover_add(s, _sf.obstacle_window(int(agents[i][0]), int(agents[i][1]), half, g))
                     self.nav_valid[s] = True
                 self._last_half = half
-            if not explore:
-                return
-            L = int(max_depth * ppm)
-            envs = self._envs
-            for i, s in enumerate(slots):
-                col, row = int(agents[i][0]), int(agents[i][1])
-                self._cover_add(s, _sf.fog_window(col, row, L))
-                tf = tf_host[i]
-                yaw = float(np.arctan2(tf[1, 0], tf[0, 0]))
-                e = envs[i]
-                e.slot, e.agent_col, e.agent_row = s, col, row
-                fr = self._frame(s)
-                e.frame[0], e.frame[1], e.frame[2], e.frame[3] = fr
-                e.heading_deg = float(np.rad2deg(wrap_heading(yaw + np.pi / 2)))     # current_angle = -yaw (:121)
-                e.fov_deg = float(np.rad2deg(topdown_fov))
-                e.max_line_len = float(max_depth * ppm)
-                e.area_thresh_px = float(self.area_thresh_px)
-            pin = self._pinned()
-            rc = self.lib.vlfm_explore_update_batch(g, n, envs, _lib.ptr(self.explored), _lib.ptr(self.nav), _lib.ptr(self._call_front),
-                                                    _lib.ptr(self._call_count), _lib.ptr(self._call_status), _lib.ptr(self._ex_ws),
-                                                    self._ex_ws.numel() * 4, pin.data_ptr(), pin.numel(), st)
-            self._pinned_done()
-            _lib.check(rc, "vlfm_explore_update_batch")
-            if slots == list(range(n)):
-                self.frontiers[:n].copy_(self._call_front[:n]); self.count[:n].copy_(self._call_count[:n]); self.ex_status[:n].copy_(self._call_status[:n])
+            if explore:
+                self._fill_envs(n, slots, agents, tf_host, max_depth, topdown_fov)
+            # ---- graph replay when the same buffers and parameters come back (the steady state of an episode loop)
+            key = None
+            if self.use_graph and identity and explore and update_obstacles and not first:
+                key = (n, depth.data_ptr(), tf_dev.data_ptr(), tuple(depth.shape), float(min_depth), float(max_depth), float(fx), float(fy), float(topdown_fov))
+            if key is not None and key == self._graph_key:
+                self._graph_seen += 1
             else:
-                idx = slot_t.long()
-                self.frontiers[idx] = self._call_front[:n]; self.count[idx] = self._call_count[:n]; self.ex_status[idx] = self._call_status[:n]
+                self._graph_key, self._graph_seen = key, 0
+            if key is not None and (key in self._graphs or self._graph_seen >= 2):
+                if self._rec_used:
+                    self._rec_ev.synchronize()           # the previous replay's record upload has executed
+                rc = self.lib.vlfm_explore_prepare_batch(g, n, self._envs, _lib.ptr(self.explored), _lib.ptr(self.nav), _lib.ptr(self._call_front),
+                                                         _lib.ptr(self._call_count), _lib.ptr(self._call_status), _lib.ptr(self._ex_ws),
+                                                         self._ex_ws.numel() * 4, self._rec_pin.data_ptr(), self._rec_pin.numel())
+                _lib.check(rc, "vlfm_explore_prepare_batch")
+                gr = self._graphs.get(key)
+                if gr is None:
+                    torch.cuda.synchronize()
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        self._device_sequence(n, depth, tf_dev, p, None, True, True, self._rec_pin)
+                    if len(self._graphs) >= 4:
+                        self._graphs.pop(next(iter(self._graphs)))
+                    self._graphs[key] = gr
+                gr.replay()
+                self._rec_ev.record()
+                self._rec_used = True
+                return
+            self._device_sequence(n, depth, tf_dev, p, slot_t, explore, update_obstacles, None)
 
     # ----------------------------------------------------------------- readback ----
     def check_fill(self, slot: int = 0) -> None:
