@@ -3,7 +3,10 @@ for profiles/: duration, DRAM bytes, DRAM %, tensor-pipe %, L2 %, registers, gri
 import csv, io, subprocess, sys
 
 rep, out = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# input: an .ncu-rep, or the CSV of its raw page (`ncu -i X.ncu-rep --page raw --csv > X.csv`, exported on the GPU box: reports are
+# too large to bring back)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = "\n".join(l for l in raw.splitlines() if l.startswith('"'))
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 want = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "dur"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
