@@ -256,7 +256,7 @@ int vlfm_cast_addpos_f16(const float* d_x, const float* d_pos, void* d_out_x16, 
  * im2col3x3s2: rows [B,h,w,C] fp32 -> fp16 [B*ho*wo, 9*C] ((ky,kx,c) order) for the fourth level's 3x3 stride-2 conv.
  * mask_rows_f16: fp32 rows -> fp16 GEMM operand with invalid rows zeroed (generate_encoder_output_proposals).
  * proposal_scores: score[b,s] = max_t <q[b,s,:], text[b,t,:]> (encoder_output_class_embed + max(-1)).
- * topk_rows: indices of the k best scores per image, descending, ties to the lower index (torch.topk; S <= 16384).
+ * topk_rows: indices of the k best scores per image, descending, ties to the lower index (torch.topk; one-block bitonic sort for S <= 16384, radix select + sort of the k winners above, k <= 16384).
  * gather_rows: dst[b,i,:] = src[b, idx[b,i], :] (torch.gather).
  * box_finish: sigmoid(delta + logit(ref, eps=1e-5)).   contrastive_sigmoid: sigmoid(<hs, text>) padded with 0 to L.       */
 int vlfm_groupnorm_rows(const float* d_y, int B, int HW, int C, int groups, const float* d_gamma, const float* d_beta, float eps,

@@ -394,23 +394,34 @@ __global__ void chain_edges_kernel(const ExEnv* __restrict__ envs, int frame) {
     }
   }
 }
-// rows -> image: img[cell] = value where filled; optionally everything else := 0 (clear_rest)
+// rows -> image: img[cell] = value where filled; optionally everything else := 0 (clear_rest).  One WARP per row: lane = 32-bit
+// word of the toggle plane (rows wider than 1024 cells take several passes); the even-odd state entering a word is the XOR of
+// the parities of the words before it (warp scan), the 32 cells of a word are written by its lane.
 __device__ __forceinline__ void planes_row_to_image(const uint32_t* __restrict__ tog, const uint32_t* __restrict__ orb, uint8_t* __restrict__ img,
-                                                    int W, int pw, int r, int value, int clear_rest) {
-  uint32_t carry = 0;
-  for (int w = 0; w < pw; ++w) {
-    const uint32_t t = tog[r * pw + w];
+                                                    int W, int pw, int r, int value, int clear_rest, int lane) {
+  uint32_t carry = 0;                                   // 0 or ~0: fill state entering this pass
+  for (int w0 = 0; w0 < pw; w0 += 32) {
+    const int w = w0 + lane;
+    const uint32_t t = w < pw ? tog[r * pw + w] : 0u;
     uint32_t x = t;
     x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
-    x ^= carry;
-    if (__popc(t) & 1) carry = ~carry;
-    const uint32_t f = x | orb[r * pw + w];
-    for (int bq = 0; bq < 32; ++bq) {
-      const int col = w * 32 + bq;
-      if (col >= W) break;
-      if ((f >> bq) & 1u) img[r * W + col] = (uint8_t)value;
-      else if (clear_rest) img[r * W + col] = 0;
+    uint32_t par = __popc(t) & 1u;                      // parity of this word, then exclusive XOR-scan over the lanes
+    uint32_t inc = par;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc ^= u; }
+    const uint32_t before = inc ^ par;                  // XOR of the parities of the lower lanes
+    x ^= (before ? ~0u : 0u) ^ carry;
+    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+    if (w < pw) {
+      const uint32_t f = x | orb[r * pw + w];
+      uint8_t* o = img + (size_t)r * W + w * 32;
+      const int nb = min(32, W - w * 32);
+      for (int bq = 0; bq < nb; ++bq) {
+        if ((f >> bq) & 1u) o[bq] = (uint8_t)value;
+        else if (clear_rest) o[bq] = 0;
+      }
     }
+    if (tot) carry = ~carry;
   }
 }
 // dst: 0 = cone (window), 1 = newexp (window), 2 = exS (S frame); gated by *E.which >= 0 when `gated`
@@ -420,10 +431,12 @@ __global__ void planes_to_image_kernel(const ExEnv* __restrict__ envs, int dst, 
   int W, H; frame_dims(E, dst == 2 ? FRAME_S : FRAME_WIN, W, H);
   uint8_t* img = dst == 0 ? E.cone : (dst == 1 ? E.newexp : E.exS);
   const int pw = (W + 31) / 32;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < H; r += gridDim.x * blockDim.x) planes_row_to_image(E.tog, E.orb, img, W, pw, r, 1, clear_rest);
+  const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < H; r += nw) planes_row_to_image(E.tog, E.orb, img, W, pw, r, 1, clear_rest, lane);
 }
 __global__ void planes_to_image_plain_kernel(const uint32_t* __restrict__ tog, const uint32_t* __restrict__ orb, uint8_t* __restrict__ img, int W, int H, int pw) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < H; r += gridDim.x * blockDim.x) planes_row_to_image(tog, orb, img, W, pw, r, 1, 1);
+  const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < H; r += nw) planes_row_to_image(tog, orb, img, W, pw, r, 1, 1, lane);
 }
 __global__ void zero_planes_plain_kernel(uint32_t* tog, uint32_t* orb, int words) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) { tog[i] = 0; orb[i] = 0; }
@@ -879,24 +892,29 @@ __device__ __forceinline__ bool blur_zero(const uint8_t* nav, const uint8_t* ex2
 
 // arc-length midpoint of the frontier q[a..b) followed by q[a2..b2) (second range empty unless merged); q[k] = p[(k+1)/2 mod n];
 // written in GRID coordinates ((fx0, fy0) = S-frame origin) at out[0..1]
+// length of one step of the interpolated chain: consecutive entries coincide or are 8-neighbours, so sqrt(d2) is 0, 1 or sqrt(2)
+// (the correctly rounded double, exactly what np.sqrt returns); only the junction of a merged piece can be longer
+__device__ __forceinline__ double seg_len(int2 u, int2 v) {
+  const int d2 = (u.x - v.x) * (u.x - v.x) + (u.y - v.y) * (u.y - v.y);
+  return d2 == 0 ? 0.0 : (d2 == 1 ? 1.0 : (d2 == 2 ? 1.4142135623730951 : sqrt((double)d2)));
+}
 __device__ void midpoint(const int2* p, int n, int a, int b, int a2, int b2, int fx0, int fy0, double* out) {
   auto Q = [&](int k) { return p[((k + 1) >> 1) % n]; };
   const int len1 = b - a, len2 = b2 - a2, len = len1 + len2;
   auto at = [&](int i) { return i < len1 ? Q(a + i) : Q(a2 + (i - len1)); };
   double total = 0.0;
-  for (int i = 0; i + 1 < len; ++i) { const int2 u = at(i), v = at(i + 1); total += sqrt((double)((u.x - v.x) * (u.x - v.x) + (u.y - v.y) * (u.y - v.y))); }
+  for (int i = 0; i + 1 < len; ++i) total += seg_len(at(i), at(i + 1));
   const double half = total / 2;
   double cum = 0.0, before = 0.0; int seg = 0;
   bool found = false;
   for (int i = 0; i + 1 < len; ++i) {
-    const int2 u = at(i), v = at(i + 1);
-    const double l = sqrt((double)((u.x - v.x) * (u.x - v.x) + (u.y - v.y) * (u.y - v.y)));
+    const double l = seg_len(at(i), at(i + 1));
     if (cum + l > half) { seg = i; before = cum; found = true; break; }
     cum += l;
   }
   if (!found) { seg = 0; before = 0.0; }          // np.argmax of an all-False array is 0
   const int2 u = at(seg), v = at(seg + 1);
-  const double l = sqrt((double)((u.x - v.x) * (u.x - v.x) + (u.y - v.y) * (u.y - v.y)));
+  const double l = seg_len(u, v);
   const double t = (half - before) / l;
   out[0] = (double)(u.x + fx0) + t * (double)(v.x - u.x); out[1] = (double)(u.y + fy0) + t * (double)(v.y - u.y);
 }
@@ -1005,6 +1023,16 @@ __global__ void __launch_bounds__(FRONTIER_THREADS) frontier_kernel(const ExEnv*
 __global__ void zero_mask_kernel(const ExEnv* __restrict__ envs) {
   const ExEnv& E = envs[blockIdx.y];
   const int n = E.Sw * E.Sh;
+  if ((n & 3) == 0) {          // images are contiguous and 16-byte aligned per environment when H*W % 4 == 0
+    const float4* d4 = reinterpret_cast<const float4*>(E.depth);
+    uchar4* m4 = reinterpret_cast<uchar4*>(E.unexp); uchar4* f4 = reinterpret_cast<uchar4*>(E.filled);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += gridDim.x * blockDim.x) {
+      const float4 v = d4[i];
+      m4[i] = make_uchar4(v.x == 0.f, v.y == 0.f, v.z == 0.f, v.w == 0.f);
+      f4[i] = make_uchar4(0, 0, 0, 0);
+    }
+    return;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { E.unexp[i] = E.depth[i] == 0.f ? 1 : 0; E.filled[i] = 0; }
 }
 // RETR_TREE: the outer border of EVERY component and the border of every hole
@@ -1262,7 +1290,7 @@ extern "C" int vlfm_explore_launch_batch(int G, int batch, void* d_workspace, co
   // ---- R1: cone sector (window)
   zero_planes_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, FRAME_WIN);
   sector_edges_kernel<<<dim3(1, B), 64, 0, st>>>(d_envs);
-  planes_to_image_kernel<<<dim3(8, B), 64, 0, st>>>(d_envs, 0, 1, 0);
+  planes_to_image_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, 0, 1, 0);
   fog_masks_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
   // ---- R2/R3/R4: obstacle contours -> rays -> cut
   contours(d_envs, B, IMG_BLOCKED, st, 0, 0, 0);
@@ -1277,7 +1305,7 @@ extern "C" int vlfm_explore_launch_batch(int G, int batch, void* d_workspace, co
   contour_pick_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs, 0);
   zero_planes_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, FRAME_WIN);
   chain_edges_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, FRAME_WIN);
-  planes_to_image_kernel<<<dim3(8, B), 64, 0, st>>>(d_envs, 1, 0, 1);
+  planes_to_image_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs, 1, 0, 1);
   // ---- explored |= dilate3(new); explored[nav == 0] = 0  -> S frame images
   explored_update_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
   // ---- component selection (obstacle_map.py:128-146)
@@ -1286,7 +1314,7 @@ extern "C" int vlfm_explore_launch_batch(int G, int batch, void* d_workspace, co
   contour_pick_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs, 1);
   zero_planes_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs, FRAME_S);
   chain_edges_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs, FRAME_S);
-  planes_to_image_kernel<<<dim3(64, B), 64, 0, st>>>(d_envs, 2, 1, 1);   // no-op when a single contour exists (which == -1)
+  planes_to_image_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs, 2, 1, 1);   // no-op when a single contour exists (which == -1)
   // ---- frontiers (obstacle_map.py:155-169 -> detect_frontier_waypoints)
   paste_grow_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
   contours(d_envs, B, IMG_UNEXP, st, 1, 2, 1);
@@ -1414,7 +1442,7 @@ extern "C" int vlfm_value_cone_template(double fov, double max_depth, int ppm, d
   if (rc) return rc;
   zero_planes_plain_kernel<<<nblk((long)pw * R), 256, 0, st>>>(tog, orb, pw * R);
   sector_edges_plain_kernel<<<1, 64, 0, st>>>(verts, nv, R, tog, orb, pw);
-  planes_to_image_plain_kernel<<<nblk(R, 64), 64, 0, st>>>(tog, orb, sector, R, R, pw);
+  planes_to_image_plain_kernel<<<nblk((long)R * 32, 256), 256, 0, st>>>(tog, orb, sector, R, R, pw);
   cone_template_kernel<<<nblk((long)R * R), 256, 0, st>>>(sector, d_out, R, fov, min_conf);
   rc = check_cuda(cudaStreamSynchronize(st), "cone template");   // hv is a stack buffer: the upload must finish before returning
   if (rc) return rc;

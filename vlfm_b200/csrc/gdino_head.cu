@@ -140,6 +140,66 @@ topk_rows_kernel(const float* __restrict__ scores, int S, int P, int k, long lon
   for (int i = threadIdx.x; i < k; i += 1024) idx_out[(size_t)b * k + i] = (long long)(0xffffffffu - (unsigned)(s_keys[i] & 0xffffffffull));
 }
 
+// S > 16384 (1024 x 1024 frames have 21760 proposals): the keys do not fit one block's shared memory.  Radix-select the k-th largest
+// 64-bit key (8 passes of 8 bits over the scores in global memory; the keys are unique, so exactly k of them are >= the k-th),
+// collect those k into shared memory and bitonic-sort them.  Same order as topk_rows_kernel: descending score, lower index first.
+__device__ __forceinline__ unsigned long long topk_key(const float* __restrict__ row, int i) {
+  float f = row[i];
+  if (f != f) f = -INFINITY;
+  unsigned u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+}
+__global__ void __launch_bounds__(1024)
+topk_select_kernel(const float* __restrict__ scores, int S, int P, int k, long long* __restrict__ idx_out) {
+  extern __shared__ unsigned long long s_keys[];     // P >= k entries
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_need, s_fill;
+  const float* row = scores + (size_t)blockIdx.x * S;
+  if (threadIdx.x == 0) { s_prefix = 0ull; s_need = (unsigned)k; s_fill = 0u; }
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    const unsigned long long hi_mask = pass ? (~0ull << (shift + 8)) : 0ull;
+    for (int i = threadIdx.x; i < S; i += 1024) {
+      const unsigned long long key = topk_key(row, i);
+      if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned need = s_need, d = 255;
+      for (;; --d) { const unsigned c = s_hist[d]; if (c >= need) break; need -= c; }   // some digit holds the need-th largest
+      s_need = need;
+      s_prefix = prefix | ((unsigned long long)d << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned long long kth = s_prefix;
+  for (int i = threadIdx.x; i < P; i += 1024) s_keys[i] = 0ull;
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += 1024) {
+    const unsigned long long key = topk_key(row, i);
+    if (key >= kth) s_keys[atomicAdd(&s_fill, 1u)] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= P; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += 1024) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s_keys[i], c = s_keys[ixj];
+          const bool desc = (i & kk) == 0;
+          if ((a < c) == desc) { s_keys[i] = c; s_keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < k; i += 1024) idx_out[(size_t)blockIdx.x * k + i] = (long long)(0xffffffffu - (unsigned)(s_keys[i] & 0xffffffffull));
+}
+
 // dst[b, i, :] = src[b, idx[b, i], :]
 __global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, int S, int K, int C, float* __restrict__ dst) {
   const int b = blockIdx.y;
@@ -234,7 +294,20 @@ extern "C" int vlfm_proposal_scores(const float* d_q, const float* d_text, int B
 }
 
 extern "C" int vlfm_topk_rows(const float* d_scores, int B, int S, int k, long long* d_idx, void* stream) {
-  if (!d_scores || !d_idx || B < 1 || S < 1 || k < 1 || k > S || S > 16384) { set_error("vlfm_topk_rows: bad argument (k <= S <= 16384)"); return VLFM_E_INVALID; }
+  if (!d_scores || !d_idx || B < 1 || S < 1 || k < 1 || k > S || (S > 16384 && k > 16384)) { set_error("vlfm_topk_rows: bad argument (k <= S; k <= 16384 when S > 16384)"); return VLFM_E_INVALID; }
+  if (S > 16384) {
+    int P = 2; while (P < k) P <<= 1;
+    const size_t smem = (size_t)P * 8;
+    static size_t cfg2 = 0;
+    if (smem > 48 * 1024 && smem > cfg2) {
+      int rc = check_cuda(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr(topk_select)");
+      if (rc) return rc; cfg2 = smem;
+    }
+    topk_select_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(d_scores, S, P, k, d_idx);
+    VLFM_CHECK_LAUNCH("topk_select_kernel");
+    count_launch();
+    return VLFM_OK;
+  }
   int P = 2; while (P < S) P <<= 1;
   const size_t smem = (size_t)P * 8;
   static size_t cfg = 0;

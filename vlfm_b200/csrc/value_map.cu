@@ -328,20 +328,23 @@ struct FuseCtx {
   int R, WPR;
 };
 
-__device__ __forceinline__ double cone_tap(const FuseCtx& c, int sy, int sx) {
-  if ((unsigned)sx >= (unsigned)c.R || (unsigned)sy >= (unsigned)c.R) return 0.0;
-  if ((c.kill[sy * c.WPR + (sx >> 5)] >> (sx & 31)) & 1u) return 0.0;
-  return (double)__ldg(c.tmpl + sy * c.R + sx);
-}
-
 // warpAffine INTER_LINEAR sample of the occlusion-cut template at output (y, x), then
 // the float64 -> float32 cast of the paste into curr_map (value_map.py:316-317).
+// The four template loads are issued unconditionally (clamped addresses) BEFORE the range / kill-bit tests, so they are
+// independent and overlap; round 1 tested each tap's kill bit first, which serialised 16 L2 round trips per 4-cell item
+// (value_cone_fuse_kernel: 33 us for 32 environments at 21 % occupancy).
 __device__ __forceinline__ float cone_sample(const FuseCtx& c, int y, int x) {
-  int X = (c.X0[y] + c.AD[x]) >> 5, Y = (c.Y0[y] + c.BD[x]) >> 5;
-  int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
+  const int X = (c.X0[y] + c.AD[x]) >> 5, Y = (c.Y0[y] + c.BD[x]) >> 5;
+  const int sx = X >> 5, sy = Y >> 5, fx = X & 31, fy = Y & 31;
   if (sx < -1 || sx >= c.R || sy < -1 || sy >= c.R) return 0.f;
-  double v00 = cone_tap(c, sy, sx), v01 = cone_tap(c, sy, sx + 1);
-  double v10 = cone_tap(c, sy + 1, sx), v11 = cone_tap(c, sy + 1, sx + 1);
+  const int R = c.R;
+  const int x0 = max(sx, 0), x1 = min(sx + 1, R - 1), y0 = max(sy, 0), y1 = min(sy + 1, R - 1);
+  const float t00 = __ldg(c.tmpl + y0 * R + x0), t01 = __ldg(c.tmpl + y0 * R + x1);
+  const float t10 = __ldg(c.tmpl + y1 * R + x0), t11 = __ldg(c.tmpl + y1 * R + x1);
+  const bool cx0 = sx >= 0, cx1 = sx + 1 < R, cy0 = sy >= 0, cy1 = sy + 1 < R;
+  auto alive = [&](int yy, int xx) { return !((c.kill[yy * c.WPR + (xx >> 5)] >> (xx & 31)) & 1u); };
+  const double v00 = (cx0 && cy0 && alive(y0, x0)) ? (double)t00 : 0.0, v01 = (cx1 && cy0 && alive(y0, x1)) ? (double)t01 : 0.0;
+  const double v10 = (cx0 && cy1 && alive(y1, x0)) ? (double)t10 : 0.0, v11 = (cx1 && cy1 && alive(y1, x1)) ? (double)t11 : 0.0;
   const double s = 1.0 / 1024.0;
   double acc = v00 * ((32 - fx) * (32 - fy) * s) + v01 * (fx * (32 - fy) * s) +
                v10 * ((32 - fx) * fy * s) + v11 * (fx * fy * s);  // exact in float64
