@@ -48,9 +48,6 @@ const char* vlfm_last_error(void);
 int vlfm_version(void);
 /* number of kernels this library has launched since load (bench `gpu_launches`). */
 unsigned long long vlfm_launch_count(void);
-/* development probe for programmatic dependent launch: each block spins pre_ns, waits for its
- * predecessor grid, spins post_ns. */
-int vlfm_pdl_probe(int blocks, int smem_bytes, int pre_ns, int post_ns, int* d_sink, void* stream);
 
 /* ------------------------------------------------------------------ value map ---- */
 /* Replaces ValueMap.update_map (vlfm/mapping/value_map.py:100-128), i.e.
@@ -153,10 +150,6 @@ int vlfm_fill_small_holes(const float* d_depth, int H, int W, double area_thresh
 #define VLFM_EPI_BIAS_RESID_F32 2
 #define VLFM_EPI_BIAS_F32 3
 #define VLFM_EPI_BIAS_RELU_F16 4
-/* development aid: CTA (0,0,0) of every later GEMM launch writes clock64() at its phase boundaries
- * (start, setup done, dependency wait done, first stage landed, last MMA issued, accumulator ready,
- * epilogue done) and %globaltimer into d_buf8[0..7]; NULL disables. */
-void vlfm_gemm_debug_timeline(unsigned long long* d_buf8);
 #define VLFM_EPI_PARTIAL_F32 5   /* internal to vlfm_gemm_f16_resid_ln: split-K partial sums stored side by side */
 /* x[M,N] (fp32 residual stream) += A @ W^T + bias, then LayerNorm(x) -> d_out16 (fp16) and/or d_out32 (fp32, may
  * alias x for the post-LN Q-Former blocks).  BITWISE REPRODUCIBLE: when the tile plan splits K, the splits store their

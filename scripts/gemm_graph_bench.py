@@ -1,3 +1,4 @@
+# NOTE: needs a development build of the library (NVCC flag -DVLFM_DEV_PROBES): the probe entry points are not in the shipped C-ABI.
 """Per-shape GEMM timing at full clocks: 200 back-to-back launches captured in a CUDA graph
 (no CPU launch bound), optional sweep of the tile plan via VLFM_GEMM_FORCE=bn:splits."""
 import os, sys, itertools

@@ -1,3 +1,4 @@
+# NOTE: needs a development build of the library (NVCC flag -DVLFM_DEV_PROBES): the probe entry points are not in the shipped C-ABI.
 """Per-phase timeline of CTA (0,0,0) of the tcgen05 GEMM (development aid)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -48,7 +48,6 @@ _SIGNATURES = {
     "vlfm_last_error": (C.c_char_p, []),
     "vlfm_version": (C.c_int, []),
     "vlfm_launch_count": (C.c_ulonglong, []),
-    "vlfm_pdl_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vlfm_value_workspace_bytes": (C.c_int, [C.POINTER(ValueParams), C.c_int, C.POINTER(C.c_size_t)]),
     "vlfm_value_update": (C.c_int, [C.POINTER(ValueParams), C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vlfm_value_mask_unexplored": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
@@ -66,7 +65,6 @@ _SIGNATURES = {
     "vlfm_gemm_f16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vlfm_gemm_f16_resid_ln": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 6 + [_P, _P, _P, C.c_int, _P, C.c_int, C.c_float, _P, C.c_size_t, _P]),
     "vlfm_layernorm_reduce": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, _P]),
-    "vlfm_gemm_debug_timeline": (None, [_P]),
     "vlfm_preprocess_im2col": (C.c_int, [_P, _P, _P] + [C.c_int] * 7 + [_P, _P, C.c_int, _P, _P, C.c_int,
                                          C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "vlfm_assemble_tokens": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

@@ -724,7 +724,9 @@ using namespace vlfm;
 static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, int lda, int ldw, GemmArgs g, void* stream, float* d_partials,
                          size_t partial_bytes, int* splits_out);
 
+#ifdef VLFM_DEV_PROBES   // development builds only (scripts/gemm_timeline.py): not part of the shipped C-ABI
 extern "C" void vlfm_gemm_debug_timeline(unsigned long long* d_buf8) { vlfm::g_gemm_dbg = d_buf8; }
+#endif
 
 extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bias, void* d_out, int M, int N,
                              int K, int lda, int ldw, int ldo, int epilogue, void* stream) {

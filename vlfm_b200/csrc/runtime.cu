@@ -30,6 +30,7 @@ extern "C" unsigned long long vlfm_launch_count(void) {
   return vlfm::g_launches.load(std::memory_order_relaxed);
 }
 
+#ifdef VLFM_DEV_PROBES   // development builds only (scripts/pdl_probe.py): not part of the shipped C-ABI
 // ---- development probe: does programmatic dependent launch overlap kernels (in streams / in graphs)?
 namespace vlfm {
 __global__ void pdl_probe_kernel(int pre_ns, int post_ns, int* sink) {
@@ -51,3 +52,4 @@ extern "C" int vlfm_pdl_probe(int blocks, int smem_bytes, int pre_ns, int post_n
   }
   return vlfm::check_cuda(vlfm::launch_pdl(vlfm::pdl_probe_kernel, dim3(blocks), dim3(128), (size_t)smem_bytes, (cudaStream_t)stream, pre_ns, post_ns, d_sink), "pdl_probe_kernel");
 }
+#endif
