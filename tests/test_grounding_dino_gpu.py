@@ -303,58 +303,66 @@ def pair_calibrated():
 def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
     """Decision level: which queries pass box_threshold, which tokens pass text_threshold (the phrase) and where the box is.
     Synthetic-weight scores have no natural gap at 0.35 / 0.25, so the thresholds are put at quantiles of the oracle's own
-    score distribution.  The 900 rows may permute between the two models (top-k over near-tied proposals), so rows are paired by
-    box (nearest L1 over ALL 900 rows of the other model).  The fp16-operand forward of a random-weight network moves a score
-    by up to ~0.06 (measured, printed below; trained weights have margins, random ones do not), so:
-      * a detection the source model keeps with margin (score >= box_thr + DELTA) must have a counterpart box (<= 5e-2), which the
-        other model keeps too, with |score difference| <= DELTA and the same phrase (rows with a token within DELTA of
-        text_thr are exempt from the phrase comparison);
-      * detections within DELTA of box_thr may tip either way (exempt);
-      * at most 3 % of the confident detections may lack a counterpart (their proposal fell out of the other model's top-900)."""
+    score distribution.  The 900 rows may permute between the two models (top-k over near-tied proposals) and neighbouring
+    proposals have near-identical boxes, so rows are paired by PROPOSAL IDENTITY: the initial reference point the decoder receives
+    (anchor spacing >= 1/80 of the image, refinement noise ~1e-3).  Then
+      * a paired detection one model keeps with margin (score >= box_thr + DELTA) is kept by the other, with |score difference|
+        <= DELTA, the same box (<= 2e-2 L1) and the same phrase (rows with a token within DELTA of text_thr are exempt from the
+        phrase comparison); detections within DELTA of box_thr may tip either way (exempt);
+      * at most 5 % of the confident detections may lack a counterpart (proposal outside the other model's top-900)."""
     orc, g = pair_calibrated
-    DELTA = 0.08
+    DELTA = 0.05
     n_checked = n_exempt = n_orphans = 0
-    bad, diffs = [], []
-    for seed, caption in ((21, "chair . person . dog ."), (22, "couch . potted plant . tv ."), (23, "bed . toilet .")):
-        img = make_rgb(np.random.default_rng(seed), 480, 640)
-        ids = g.tokenizer.encode(caption)
-        ref_l, ref_b = (t.cpu().float() for t in orc.raw_outputs(img, ids))
-        got_l, got_b = (t.cpu().float() for t in g.raw_outputs(img, ids))
-        box_thr = float(ref_l.max(dim=1)[0].quantile(0.75))                     # ~225 of 900 queries kept
-        text_thr = box_thr * 0.25 / 0.35
-        assert int((ref_l.max(dim=1)[0] > box_thr + DELTA).sum()) > 20
+    bad, diffs, bdiffs = [], [], []
+    cap = {}
+    h1 = orc.model.model.decoder.register_forward_hook(lambda m_, a_, kw, o_: cap.__setitem__("ref", kw["reference_points"][0].detach().float().cpu()), with_kwargs=True)
+    h2 = g.model.model.decoder.register_forward_hook(lambda m_, a_, kw, o_: cap.__setitem__("got", kw["reference_points"][0].detach().float().cpu()), with_kwargs=True)
+    graph_ok, g._graph_ok = g._graph_ok, False                                  # eager: the hook must see the decoder call
+    try:
+        for seed, caption in ((21, "chair . person . dog ."), (22, "couch . potted plant . tv ."), (23, "bed . toilet .")):
+            img = make_rgb(np.random.default_rng(seed), 480, 640)
+            ids = g.tokenizer.encode(caption)
+            ref_l, ref_b = (t.cpu().float() for t in orc.raw_outputs(img, ids))
+            got_l, got_b = (t.cpu().float() for t in g.raw_outputs(img, ids))
+            ref_p, got_p = cap["ref"], cap["got"]
+            box_thr = float(ref_l.max(dim=1)[0].quantile(0.5))
+            text_thr = box_thr * 0.25 / 0.35
 
-        def phrase(row):
-            pos = row > text_thr
-            pos[0] = False
-            pos[len(ids) - 1:] = False
-            return g.tokenizer.decode([ids[i] for i in pos.nonzero(as_tuple=True)[0].tolist()]).replace(".", "").strip()
+            def phrase(row):
+                pos = row > text_thr
+                pos[0] = False
+                pos[len(ids) - 1:] = False
+                return g.tokenizer.decode([ids[i] for i in pos.nonzero(as_tuple=True)[0].tolist()]).replace(".", "").strip()
 
-        def near_text(row):
-            return bool(((row[1:len(ids) - 1] - text_thr).abs() < DELTA).any())
+            def near_text(row):
+                return bool(((row[1:len(ids) - 1] - text_thr).abs() < DELTA).any())
 
-        for (sl, sb), (dl, db) in (((ref_l, ref_b), (got_l, got_b)), ((got_l, got_b), (ref_l, ref_b))):
-            smx, dmx = sl.max(dim=1)[0], dl.max(dim=1)[0]
-            d = (sb[:, None, :] - db[None, :, :]).abs().sum(-1)                  # [900, 900]
-            dist, j = d.min(dim=1)
-            for i in (smx > box_thr).nonzero(as_tuple=True)[0].tolist():
-                if float(smx[i]) < box_thr + DELTA:
-                    n_exempt += 1
-                    continue
-                if float(dist[i]) > 5e-2:
-                    n_orphans += 1
-                    continue
-                n_checked += 1
-                k = int(j[i])
-                diffs.append(abs(float(smx[i]) - float(dmx[k])))
-                same_phrase = near_text(sl[i]) or near_text(dl[k]) or phrase(sl[i].clone()) == phrase(dl[k].clone())
-                if diffs[-1] > DELTA or not float(dmx[k]) > box_thr or not same_phrase:
-                    bad.append((phrase(sl[i].clone()), phrase(dl[k].clone()), round(float(smx[i]), 4), round(float(dmx[k]), 4), round(float(dist[i]), 4)))
-    diffs = np.asarray(diffs)
-    print(f"decision test: {n_checked} confident detections paired, {n_orphans} without a counterpart, {n_exempt} within {DELTA} of box_thr (exempt); "
-          f"|score difference| mean {diffs.mean():.4f} p99 {np.quantile(diffs, 0.99):.4f} max {diffs.max():.4f}; mismatches {bad[:6]}")
+            for (sl, sb, sp), (dl, db, dp) in (((ref_l, ref_b, ref_p), (got_l, got_b, got_p)), ((got_l, got_b, got_p), (ref_l, ref_b, ref_p))):
+                smx, dmx = sl.max(dim=1)[0], dl.max(dim=1)[0]
+                d = (sp[:, None, :] - dp[None, :, :]).abs().sum(-1)                  # [900, 900] proposal identity
+                dist, j = d.min(dim=1)
+                for i in (smx > box_thr).nonzero(as_tuple=True)[0].tolist():
+                    if float(smx[i]) < box_thr + DELTA:
+                        n_exempt += 1
+                        continue
+                    if float(dist[i]) > 4e-3:
+                        n_orphans += 1
+                        continue
+                    n_checked += 1
+                    k = int(j[i])
+                    diffs.append(abs(float(smx[i]) - float(dmx[k])))
+                    bdiffs.append(float((sb[i] - db[k]).abs().sum()))
+                    same_phrase = near_text(sl[i]) or near_text(dl[k]) or phrase(sl[i].clone()) == phrase(dl[k].clone())
+                    if diffs[-1] > DELTA or bdiffs[-1] > 2e-2 or not float(dmx[k]) > box_thr or not same_phrase:
+                        bad.append((phrase(sl[i].clone()), phrase(dl[k].clone()), round(float(smx[i]), 4), round(float(dmx[k]), 4), round(bdiffs[-1], 4)))
+    finally:
+        h1.remove(); h2.remove(); g._graph_ok = graph_ok
+    diffs, bdiffs = np.asarray(diffs), np.asarray(bdiffs)
+    print(f"decision test: {n_checked} confident detections paired by proposal, {n_orphans} without a counterpart, {n_exempt} within {DELTA} of box_thr "
+          f"(exempt); |score difference| mean {diffs.mean():.4f} p99 {np.quantile(diffs, 0.99):.4f} max {diffs.max():.4f}; box L1 mean {bdiffs.mean():.4f} "
+          f"max {bdiffs.max():.4f}; {len(bad)} mismatches {bad[:6]}")
     assert not bad, f"{len(bad)} of {n_checked} decisions differ"
-    assert n_checked >= 60 and n_orphans <= 0.03 * (n_checked + n_orphans) and float(diffs.mean()) <= 0.03
+    assert n_checked >= 60 and n_orphans <= 0.05 * (n_checked + n_orphans) and float(diffs.mean()) <= 0.01
 
 
 def test_head_kernels_vs_torch():

@@ -5,6 +5,7 @@ scripts/bench_full_step.py.  Reference call sites: base_objectnav_policy.py:153-
 _get_object_detections), itm_policy.py:191-211, 263-294 (_update_value_map / _sort_frontiers_by_value)."""
 from __future__ import annotations
 
+import os
 import time
 from typing import Any, Dict, List, Optional
 
@@ -55,6 +56,7 @@ class FullStep:
         self.acc = {k: 0.0 for k in self.names}
         self.n_front = 0
         self.nf = nf
+        self.serial = os.environ.get("VLFM_FULLSTEP_SERIAL", "0") == "1"     # diagnostic: device sync after every component
 
     def step(self, i: int, timed: bool) -> None:
         i %= self.nf
@@ -66,18 +68,23 @@ class FullStep:
         self.depth_dev.copy_(self.depth_pin[i], non_blocking=True)
         self.tf_dev.copy_(self.tf_pin[i], non_blocking=True)
         ev[1].record()
+        if self.serial: torch.cuda.synchronize()
         if self.gd is not None:
             logits, boxes = self.gd.raw_outputs_device(self.rgb_dev, self.ids)
             keep = logits.max(dim=2)[0] > self.gd.box_threshold    # compaction mask stays on the device
             _ = keep.sum()
         ev[2].record()
+        if self.serial: torch.cuda.synchronize()
         cos = self.itm.cosine_device(self.rgb_dev, PROMPT)
         ev[3].record()
+        if self.serial: torch.cuda.synchronize()
         # all environments' obstacle + explore update: ONE launch sequence (hole fill, scatter, dilate, fog-of-war, frontiers)
         self.omb.update(self.depth_dev, self.tf_host[i], self.tf_dev, MIN_D, MAX_D, self.fx, self.fx, FOV)
         ev[4].record()
+        if self.serial: torch.cuda.synchronize()
         self.vmb.update(cos.double().view(B, 1), self.depth_dev, self.tf_dev.view(B, 4, 4), MIN_D, MAX_D, FOV)
         ev[5].record()
+        if self.serial: torch.cuda.synchronize()
         # ITMPolicy._sort_frontiers_by_value for every environment: one D2H of the frontier lists, one disc-median launch, one D2H
         fronts = self.omb.all_frontiers_px(B)
         pts = []

@@ -86,7 +86,11 @@ def random_state_dict(d: Blip2Dims, seed: int = 0, outliers: bool = False) -> Di
 
     ``outliers=True`` adds what trained ViT / BERT checkpoints show and plain Gaussians do not: a few LayerNorm channels with
     gains several times the rest and offsets of order one, and a handful of residual-stream channels carrying "massive
-    activations" (large biases on the block outputs) -- the cases where half-precision operands lose the most."""
+    activations" (large biases on the block outputs) -- the cases where half-precision operands lose the most.
+
+    The ViT's Linear / Conv weights and biases are fp16-representable values (stored as fp32): the reference keeps them in half
+    precision (lavis `create_eva_vit_g(..., precision="fp16")` -> `convert_weights_to_fp16`, which converts exactly the
+    Conv / Linear parameters; LayerNorm and the Q-Former stay fp32), so a real checkpoint never carries more mantissa there."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     hot = {}
@@ -147,4 +151,7 @@ def random_state_dict(d: Blip2Dims, seed: int = 0, outliers: bool = False) -> Di
     lin("vision_projection", d.proj, H)
     lin("text_projection", d.proj, H)
     lin("itm_head", 2, H)
+    for k in list(sd):  # reference storage precision of the ViT's Conv / Linear parameters (see the docstring)
+        if k.startswith("vision_model.") and ("layer_norm" not in k and "layernorm" not in k and "embedding" not in k.split(".")[-1]):
+            sd[k] = sd[k].half().float()
     return sd
