@@ -34,9 +34,14 @@ class GdinoOracle:
         return [f[0] for f in bb(preprocess(image).unsqueeze(0), return_dict=True).feature_maps]
 
     @torch.inference_mode()
-    def raw_outputs(self, image: np.ndarray, input_ids):
+    def raw_outputs(self, image: np.ndarray, input_ids, input_noise: float = 0.0, noise_seed: int = 0):
+        """``input_noise`` > 0: the normalised pixels are multiplied by (1 + input_noise * N(0,1)) -- the oracle's own conditioning
+        (how far ITS outputs move under a half-precision-rounding-sized perturbation) is the yardstick of the decision tests."""
         ids = torch.tensor([list(input_ids)], dtype=torch.long)
         h, w = image.shape[:2]
-        out = self.model(pixel_values=preprocess(image).unsqueeze(0), input_ids=ids, token_type_ids=torch.zeros_like(ids),
+        px = preprocess(image).unsqueeze(0)
+        if input_noise > 0.0:
+            px = px * (1.0 + input_noise * torch.randn(px.shape, generator=torch.Generator().manual_seed(noise_seed)))
+        out = self.model(pixel_values=px, input_ids=ids, token_type_ids=torch.zeros_like(ids),
                          attention_mask=torch.ones_like(ids), pixel_mask=torch.ones(1, h, w, dtype=torch.long))
         return out.logits[0].sigmoid(), out.pred_boxes[0]

@@ -276,13 +276,13 @@ __device__ __forceinline__ int dir_dy(int d) { return (int)((0x22210001u >> (d *
 __device__ __forceinline__ unsigned rotr8(unsigned v, int r) { return ((v >> r) | (v << (8 - r))) & 0xFFu; }
 // Suzuki-Abe steps 3.1-3.5 (oracle/contours.py::_trace) on the per-pixel neighbour masks written by ccl_merge2_kernel: one
 // byte load per step; the clockwise / counter-clockwise probe loops are a byte rotation + ffs / clz.  WRITE=false only counts.
-template <bool WRITE>
-__device__ int trace_border(const uint8_t* __restrict__ nbm, int W, int x0, int y0, int2* out, Contour* c, int ed = 0) {
+// Writes the first `cap` points to out (when non-null) and always returns the full length and the bounding box.
+__device__ int trace_border(const uint8_t* __restrict__ nbm, int W, int x0, int y0, int2* out, int cap, Contour* c, int ed = 0) {
   int n = 0, minx = x0, maxx = x0, miny = y0, maxy = y0;
   // 3.1 clockwise from the (zero) entry pixel (west for outer, east for hole borders): first set bit among ed+1 .. ed+7
   const unsigned r0 = rotr8(nbm[y0 * W + x0], ed) & 0xFEu;
   if (!r0) {
-    if (WRITE) out[0] = make_int2(x0, y0);
+    if (out && cap > 0) out[0] = make_int2(x0, y0);
     n = 1;
   } else {
     const int df = (ed + __ffs(r0) - 1) & 7;
@@ -294,34 +294,41 @@ __device__ int trace_border(const uint8_t* __restrict__ nbm, int W, int x0, int 
       const unsigned r = rotr8(nbm[y3 * W + x3], d0);
       const int di = (d0 + (31 - __clz(r))) & 7;
       const int x4 = x3 + dir_dx(di), y4 = y3 + dir_dy(di);
-      if (WRITE) { out[n] = make_int2(x3, y3); minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3); }
+      if (out && n < cap) out[n] = make_int2(x3, y3);
+      minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
       ++n;
       if (x4 == x0 && y4 == y0 && x3 == fx && y3 == fy) break;   // 3.5
       x3 = x4; y3 = y4; d0 = (di + 4) & 7;          // seen from the new pixel, the old one lies in the opposite direction
       if (n > (1 << 22)) break;                      // safety
     }
   }
-  if (WRITE) { c->x0 = minx; c->x1 = maxx; c->y0 = miny; c->y1 = maxy; }
+  c->x0 = minx; c->x1 = maxx; c->y0 = miny; c->y1 = maxy;
   return n;
 }
 
 // mode 0: trace every contour; 1: only when more than one contour exists (component selection); 2: skip components
 // flagged in hashole (they enclose a hole -- their filled polygon contains a zero cell -- or reach the exterior: F1 can never
-// absorb them)
+// absorb them).
+// Chain storage: the first half of the chain buffer is cut into one equal slot per contour, which the walk fills directly -- ONE
+// pass in the common case; a border longer than its slot (many contours and a long one among them) is walked a second time into
+// space taken from the second half with the cursor.  (Round 1 always walked twice: count, allocate, write.)
 __global__ void trace_kernel(const ExEnv* __restrict__ envs, int id, int mode) {
   const ExEnv& E = envs[blockIdx.y];
   const View v = view(E, id);
   ExState* st = E.st;
   const int W = v.W;
   const int nc = min(st->n_cont, E.maxc);
+  const int half = E.chain_cap >> 1;
+  const int slot = nc > 0 ? half / nc : 0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
     const int s = E.cont[c].start, y0 = s / W, x0 = s - y0 * W;
     if ((mode == 1 && st->n_cont <= 1) || (mode == 2 && E.hashole[s])) { E.cont[c].off = 0; E.cont[c].len = 0; continue; }
-    const int n = trace_border<false>(E.nbm, W, x0, y0, nullptr, nullptr, E.cont[c].ed);
-    const int off = atomicAdd(&st->cursor, n);
+    const int n = trace_border(E.nbm, W, x0, y0, E.chain + (size_t)c * slot, slot, &E.cont[c], E.cont[c].ed);
+    if (n <= slot) { E.cont[c].off = c * slot; E.cont[c].len = n; continue; }
+    const int off = half + atomicAdd(&st->cursor, n);
     if (off + n > E.chain_cap) { st->overflow = 1; E.cont[c].off = 0; E.cont[c].len = 0; continue; }
     E.cont[c].off = off; E.cont[c].len = n;
-    trace_border<true>(E.nbm, W, x0, y0, E.chain + off, &E.cont[c], E.cont[c].ed);
+    trace_border(E.nbm, W, x0, y0, E.chain + off, n, &E.cont[c], E.cont[c].ed);
   }
 }
 
@@ -639,8 +646,9 @@ __device__ __forceinline__ void put_px(const CutWin& c, long long x, long long y
 __device__ __forceinline__ long long cdiv(long long a, long long b) {   // C truncating division (b > 0)
   return a / b;
 }
-// drawing.cpp Line2: clipLine against the image scaled to 16.16, then a DDA between the clipped end points
-__device__ void line2_fixed(const CutWin& c, int G, long long x1, long long y1, long long x2, long long y2) {
+// drawing.cpp Line2: clipLine against the image scaled to 16.16, then a DDA between the clipped end points.  One WARP per line:
+// step i of the DDA is closed-form (x1 + i, y1 + i * y_step), lanes stride over the steps.
+__device__ void line2_fixed(const CutWin& c, int G, long long x1, long long y1, long long x2, long long y2, int lane) {
   if (!clip_line((long long)G << XYS, (long long)G << XYS, x1, y1, x2, y2)) return;
   long long dx = x2 - x1, dy = y2 - y1;
   const long long ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
@@ -653,18 +661,21 @@ __device__ void line2_fixed(const CutWin& c, int G, long long x1, long long y1, 
     x_step = cdiv(dx << XYS, ay | 1); y_step = XYONE; ecount = (y2 - y1) >> XYS;
   }
   x1 += XYONE >> 1; y1 += XYONE >> 1;
-  put_px(c, (x2 + (XYONE >> 1)) >> XYS, (y2 + (XYONE >> 1)) >> XYS);
+  if (lane == 0) put_px(c, (x2 + (XYONE >> 1)) >> XYS, (y2 + (XYONE >> 1)) >> XYS);
   if (ax > ay) {
-    long long x = x1 >> XYS, y = y1;
-    while (ecount >= 0) { put_px(c, x, y >> XYS); ++x; y += y_step; --ecount; }
+    const long long x = x1 >> XYS;
+    for (long long i = lane; i <= ecount; i += 32) put_px(c, x + i, (y1 + i * y_step) >> XYS);
   } else {
-    long long y = y1 >> XYS, x = x1;
-    while (ecount >= 0) { put_px(c, x >> XYS, y); x += x_step; ++y; --ecount; }
+    const long long y = y1 >> XYS;
+    for (long long i = lane; i <= ecount; i += 32) put_px(c, (x1 + i * x_step) >> XYS, y + i);
   }
 }
 __device__ __forceinline__ long long pick4(const long long (&a)[4], int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3])); }
 
-__device__ void thick_ray(const int4 r, uint8_t* __restrict__ cut, int W, int H, int ox, int oy, int G) {
+// One warp per ray.  The two-edge scan of FillConvexPoly is replayed by every lane WITHOUT drawing, jumping from edge switch to
+// edge switch (<= 4 of them); between two switches both edge x positions are linear in the row, so the rows of such a span are
+// filled by the lanes in parallel.
+__device__ void thick_ray(const int4 r, uint8_t* __restrict__ cut, int W, int H, int ox, int oy, int G, int lane) {
   const CutWin cw{cut, W, H, ox, oy};
   // ThickLine (cv2 4.13): the integer centre line is first clipped to the image grown by the thickness on every side
   long long px0 = r.x + ox + 2, py0 = r.y + oy + 2, px1 = r.z + ox + 2, py1 = r.w + oy + 2;
@@ -679,7 +690,7 @@ __device__ void thick_ray(const int4 r, uint8_t* __restrict__ cut, int W, int H,
     long long vx[4] = {x0 + dpx, x0 - dpx, x1 - dpx, x1 + dpx}, vy[4] = {y0 + dpy, y0 - dpy, y1 - dpy, y1 + dpy};
     // FillConvexPoly (shift = 16): Line2 outline ...
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const int j = (i + 3) & 3; line2_fixed(cw, G, vx[j], vy[j], vx[i], vy[i]); }
+    for (int i = 0; i < 4; ++i) { const int j = (i + 3) & 3; line2_fixed(cw, G, vx[j], vy[j], vx[i], vy[i], lane); }
     // ... + two-edge scan
     const long long delta = XYONE >> 1;
     int imin = 0;
@@ -698,7 +709,7 @@ __device__ void thick_ray(const int4 r, uint8_t* __restrict__ cut, int W, int H,
       e[0].x = e[1].x = -XYONE; e[0].dx = e[1].dx = 0;
       int edges = 4;
       long long y = ymin;
-      do {
+      while (y <= ymax) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           if (y >= e[i].ye) {
@@ -715,32 +726,39 @@ __device__ void thick_ray(const int4 r, uint8_t* __restrict__ cut, int W, int H,
           }
         }
         if (edges < 0) break;
-        {
-          const bool sw = e[0].x > e[1].x;
-          long long xx1 = ((sw ? e[1].x : e[0].x) + delta) >> XYS, xx2 = ((sw ? e[0].x : e[1].x) + delta) >> XYS;
-          const long long wy = y - oy;
-          if (y >= 0 && wy >= 0 && wy < H) {
+        // rows y .. yn-1 use the current pair of edges (the serial loop re-examines an edge only when y reaches its ye)
+        long long yn = e[0].ye < e[1].ye ? e[0].ye : e[1].ye;
+        if (yn > ymax + 1) yn = ymax + 1;
+        if (yn <= y) yn = y + 1;
+        for (long long yy = y + lane; yy < yn; yy += 32) {
+          const long long ex0 = e[0].x + (yy - y) * e[0].dx, ex1 = e[1].x + (yy - y) * e[1].dx;
+          const bool sw = ex0 > ex1;
+          long long xx1 = ((sw ? ex1 : ex0) + delta) >> XYS, xx2 = ((sw ? ex0 : ex1) + delta) >> XYS;
+          const long long wy = yy - oy;
+          if (yy >= 0 && wy >= 0 && wy < H) {
             xx1 -= ox; xx2 -= ox;
             for (long long x = xx1 < 0 ? 0 : xx1; x <= xx2 && x < W; ++x) cut[wy * W + x] = 1;
           }
         }
-        e[0].x += e[0].dx; e[1].x += e[1].dx;
-      } while (++y <= ymax);
+        e[0].x += (yn - y) * e[0].dx; e[1].x += (yn - y) * e[1].dx;
+        y = yn;
+      }
     }
   }
   // Circle(center, 1, filled) at both (clipped) ends
-  const long long cxs[2] = {px0, px1}, cys[2] = {py0, py1};
-  for (int k = 0; k < 2; ++k) {
-    put_px(cw, cxs[k], cys[k]); put_px(cw, cxs[k] - 1, cys[k]); put_px(cw, cxs[k] + 1, cys[k]);
-    put_px(cw, cxs[k], cys[k] - 1); put_px(cw, cxs[k], cys[k] + 1);
+  if (lane < 2) {
+    const long long cx = lane ? px1 : px0, cy = lane ? py1 : py0;
+    put_px(cw, cx, cy); put_px(cw, cx - 1, cy); put_px(cw, cx + 1, cy);
+    put_px(cw, cx, cy - 1); put_px(cw, cx, cy + 1);
   }
 }
 
 __global__ void thick_rays_kernel(const ExEnv* __restrict__ envs) {
   const ExEnv& E = envs[blockIdx.y];
   const int nr = min(E.st->n_rays, E.rays_cap);
-  for (int ri = blockIdx.x * blockDim.x + threadIdx.x; ri < nr; ri += gridDim.x * blockDim.x)
-    thick_ray(E.rays[ri], E.cut, E.W0, E.W0, E.ox, E.oy, E.G);
+  const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int ri = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ri < nr; ri += nw)
+    thick_ray(E.rays[ri], E.cut, E.W0, E.W0, E.ox, E.oy, E.G, lane);
 }
 // visible &= !cut; no obstacle contour in the cone -> reveal_fog_of_war returns the (all-zero) input mask
 __global__ void apply_cut_kernel(const ExEnv* __restrict__ envs) {
@@ -898,23 +916,52 @@ __device__ __forceinline__ double seg_len(int2 u, int2 v) {
   const int d2 = (u.x - v.x) * (u.x - v.x) + (u.y - v.y) * (u.y - v.y);
   return d2 == 0 ? 0.0 : (d2 == 1 ? 1.0 : (d2 == 2 ? 1.4142135623730951 : sqrt((double)d2)));
 }
-__device__ void midpoint(const int2* p, int n, int a, int b, int a2, int b2, int fx0, int fy0, double* out) {
-  auto Q = [&](int k) { return p[((k + 1) >> 1) % n]; };
-  const int len1 = b - a, len2 = b2 - a2, len = len1 + len2;
-  auto at = [&](int i) { return i < len1 ? Q(a + i) : Q(a2 + (i - len1)); };
-  double total = 0.0;
-  for (int i = 0; i + 1 < len; ++i) total += seg_len(at(i), at(i + 1));
-  const double half = total / 2;
-  double cum = 0.0, before = 0.0; int seg = 0;
-  bool found = false;
-  for (int i = 0; i + 1 < len; ++i) {
-    const double l = seg_len(at(i), at(i + 1));
-    if (cum + l > half) { seg = i; before = cum; found = true; break; }
-    cum += l;
+// Entry i of the piece is q[k_i]; k advances by one (same point when k is odd -> a zero-length step that neither changes a sum nor
+// can satisfy cum + 0 > half) except at the junction of a merged piece.  The walk keeps (k, index into p, point) incrementally: one
+// load per chain point, no modulo in the loop.
+struct QWalk {
+  const int2* p; int n, a, len1, a2;
+  int i, k, idx; int2 pt;
+  __device__ void start(const int2* p_, int n_, int a_, int len1_, int a2_) {
+    p = p_; n = n_; a = a_; len1 = len1_; a2 = a2_; i = 0;
+    k = len1 > 0 ? a : a2; idx = ((k + 1) >> 1) % n; pt = p[idx];
   }
-  if (!found) { seg = 0; before = 0.0; }          // np.argmax of an all-False array is 0
-  const int2 u = at(seg), v = at(seg + 1);
-  const double l = seg_len(u, v);
+  // advance to entry i + 1; returns the length of the step
+  __device__ double step() {
+    ++i;
+    int nidx;
+    if (i == len1) { k = a2; nidx = ((k + 1) >> 1) % n; }
+    else { nidx = (k & 1) ? idx : (idx + 1 == n ? 0 : idx + 1); ++k; }
+    if (nidx == idx) return 0.0;
+    const int2 q = p[nidx];
+    const double l = seg_len(pt, q);
+    idx = nidx; pt = q;
+    return l;
+  }
+};
+__device__ void midpoint(const int2* p, int n, int a, int b, int a2, int b2, int fx0, int fy0, double* out) {
+  const int len1 = b - a, len2 = b2 - a2, len = len1 + len2;
+  QWalk w;
+  double total = 0.0;
+  w.start(p, n, a, len1, a2);
+  for (int i = 0; i + 1 < len; ++i) total += w.step();
+  const double half = total / 2;
+  double cum = 0.0, before = 0.0, l = 0.0;
+  int2 u = make_int2(0, 0), v = make_int2(0, 0);
+  bool found = false;
+  w.start(p, n, a, len1, a2);
+  const int2 first = w.pt;
+  int2 second = first; bool have_second = false;
+  for (int i = 0; i + 1 < len; ++i) {
+    const int2 prev = w.pt;
+    const double li = w.step();
+    if (i == 0) { second = w.pt; have_second = true; }
+    if (cum + li > half) { u = prev; v = w.pt; l = li; before = cum; found = true; break; }
+    cum += li;
+  }
+  if (!found) {          // np.argmax of an all-False array is 0: segment 0
+    u = first; v = have_second ? second : first; l = seg_len(u, v); before = 0.0;
+  }
   const double t = (half - before) / l;
   out[0] = (double)(u.x + fx0) + t * (double)(v.x - u.x); out[1] = (double)(u.y + fy0) + t * (double)(v.y - u.y);
 }
@@ -922,9 +969,12 @@ __device__ void midpoint(const int2* p, int n, int a, int b, int a2, int b2, int
 // F3 "bad" test of every traced border point at once (the walk below only reads the flags)
 __global__ void bad_flags_kernel(const ExEnv* __restrict__ envs) {
   const ExEnv& E = envs[blockIdx.y];
-  const int n = min(E.st->cursor, E.chain_cap);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    E.flags[i] = blur_zero(E.navS, E.ex2, E.Sw, E.Sh, E.chain[i].x, E.chain[i].y) ? 1 : 0;
+  const int nc = min(E.st->n_cont, E.maxc);
+  for (int c = blockIdx.x; c < nc; c += gridDim.x) {        // chains live in per-contour slots: block per contour, threads over its points
+    const int off = E.cont[c].off, n = E.cont[c].len;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      E.flags[off + i] = blur_zero(E.navS, E.ex2, E.Sw, E.Sh, E.chain[off + i].x, E.chain[off + i].y) ? 1 : 0;
+  }
 }
 constexpr int FRONTIER_THREADS = 256;
 // ordered compaction step: every thread of the block calls it; returns this thread's slot (or -1); `running` (identical in all
@@ -1297,7 +1347,7 @@ extern "C" int vlfm_explore_launch_batch(int G, int batch, void* d_workspace, co
   fog_gate_kernel<<<dim3(1, B), 32, 0, st>>>(d_envs);
   simple_vertices_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
   rays_kernel<<<dim3(64, B), 256, 0, st>>>(d_envs);
-  thick_rays_kernel<<<dim3(64, B), 64, 0, st>>>(d_envs);
+  thick_rays_kernel<<<dim3(32, B), 256, 0, st>>>(d_envs);
   apply_cut_kernel<<<dim3(bc, B), 256, 0, st>>>(d_envs);
   // ---- R5: contours of the visible area, nearest to the agent, filled
   contours(d_envs, B, IMG_VISIBLE, st, 1, 0, 0);
