@@ -13,11 +13,12 @@ ap.add_argument("--ppm", type=int, default=20)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--bound", type=float, default=15.0)
 ap.add_argument("--profile-step", type=int, default=-1)
+ap.add_argument("--seed0", type=int, default=0)
 a = ap.parse_args()
 B, G, H, W = a.batch, a.grid, 480, 640
 FOV = float(np.deg2rad(79.0))
 fx = focal_from_hfov(W)
-frames = [trajectory(s, a.steps, h=H, w=W, bound_m=a.bound) for s in range(B)]
+frames = [trajectory(a.seed0 + s, a.steps, h=H, w=W, bound_m=a.bound) for s in range(B)]
 om = ObstacleMapBatch(B, 0.61, 0.88, 0.18, area_thresh=1.5, hole_area_thresh=100000, size=G, pixels_per_meter=a.ppm)
 depth = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
 tfd = torch.empty((B, 16), dtype=torch.float64, device="cuda")
