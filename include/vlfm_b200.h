@@ -186,6 +186,31 @@ int vlfm_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, 
  * q rows (b*Nq + i), k/v rows (b*Nk + j), head h at column offset h*hd. Nk <= 272, hd <= 96. */
 int vlfm_attention_f16(const void* d_q, const void* d_k, const void* d_v, void* d_o, int B, int heads, int Nq,
                        int Nk, int hd, int ldq, int ldk, int ldv, int ldo, float scale, void* stream);
+/* ---- "x2" path: float32-grade Q-Former on the fp16 tensor path.  The reference runs the Q-Former in float32 (lavis casts
+ * only the ViT to half); fp16 operands there alone move the ITC cosine by ~3e-5 (measured on the fp32 oracle), the ViT's by 1e-6.
+ * An x2 operand is a pair of fp16 arrays (hi, lo) with value = hi + lo / 2048, hi = fp16(v), lo = fp16((v - hi) * 2048).
+ * vlfm_gemm_f16x2: out = epilogue(A @ W^T + bias), A and W x2 operands, three tcgen05.mma per K step into two TMEM
+ *   accumulators (hi.hi | lo.hi + hi.lo).  epilogue: VLFM_EPI_BIAS_F32, VLFM_EPI_BIAS_RESID_F32, VLFM_EPI_BIAS_GELU_F16X2 (GELU, output
+ *   written as x2 operands d_out / d_out_lo).
+ * vlfm_gemm_f16x2_resid_ln: x += ...; LayerNorm(x) -> x2 operands (+ fp32), deterministic split-K like vlfm_gemm_f16_resid_ln.
+ * vlfm_layernorm_x2 / vlfm_layernorm_reduce_x2: LayerNorm with x2 operand output.
+ * vlfm_attention_f32: softmax(scale * Q K^T) V in float32 (q, k, v fp32; hd in {32, 64}; Nk <= 272), output as x2 operands.
+ * vlfm_split_x2: x2 operands of an fp32 array (d_hi may be NULL when the fp16 rounding already exists). */
+#define VLFM_EPI_BIAS_GELU_F16X2 6
+int vlfm_gemm_f16x2(const void* d_A_hi, const void* d_A_lo, const void* d_W_hi, const void* d_W_lo, const float* d_bias, void* d_out,
+                    void* d_out_lo, int M, int N, int K, int lda, int ldw, int ldo, int epilogue, void* stream);
+int vlfm_gemm_f16x2_resid_ln(const void* d_A_hi, const void* d_A_lo, const void* d_W_hi, const void* d_W_lo, const float* d_bias,
+                             float* d_x, int M, int N, int K, int lda, int ldw, int ldx, const float* d_gamma, const float* d_beta,
+                             void* d_out_hi, void* d_out_lo, int ld16, float* d_out32, int ld32, float eps, float* d_partials,
+                             size_t partial_bytes, void* stream);
+int vlfm_layernorm_x2(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_hi, void* d_out_lo, float* d_out32,
+                      int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream);
+int vlfm_layernorm_reduce_x2(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                             const float* d_beta, void* d_out_hi, void* d_out_lo, float* d_out32, int rows, int D, int ldx, int ldo16,
+                             int ldo32, float eps, void* stream);
+int vlfm_split_x2(const float* d_src, void* d_hi, void* d_lo, long long n, void* stream);
+int vlfm_attention_f32(const float* d_q, const float* d_k, const float* d_v, void* d_o_hi, void* d_o_lo, int B, int heads, int Nq,
+                       int Nk, int hd, int ldq, int ldk, int ldv, int ldo, float scale, void* stream);
 /* ITC head (match_head="itc"): cos[b] = max_q <normalize(proj[b,q,:]), text>.  */
 int vlfm_itc_head(const float* d_proj, const float* d_text, float* d_out, int B, int Q, int D, void* stream);
 

@@ -16,6 +16,7 @@ ST_SCATTER_OOB = 2
 ST_FRONTIER_OVERFLOW = 4
 FUSE_WEIGHTED, FUSE_MAX_CONFIDENCE, FUSE_REPLACE, FUSE_EQUAL = 0, 1, 2, 4
 EPI_BIAS_F16, EPI_BIAS_GELU_F16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_BIAS_RELU_F16 = 0, 1, 2, 3, 4
+EPI_BIAS_GELU_F16X2 = 6
 
 
 class ValueParams(C.Structure):
@@ -70,6 +71,12 @@ _SIGNATURES = {
     "vlfm_assemble_tokens": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vlfm_layernorm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "vlfm_attention_f16": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 9 + [C.c_float, _P]),
+    "vlfm_gemm_f16x2": (C.c_int, [_P] * 7 + [C.c_int] * 7 + [_P]),
+    "vlfm_gemm_f16x2_resid_ln": (C.c_int, [_P] * 6 + [C.c_int] * 6 + [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_float, _P, C.c_size_t, _P]),
+    "vlfm_layernorm_x2": (C.c_int, [_P] * 6 + [C.c_int] * 5 + [C.c_float, _P]),
+    "vlfm_layernorm_reduce_x2": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, _P, _P, _P, _P] + [C.c_int] * 5 + [C.c_float, _P]),
+    "vlfm_split_x2": (C.c_int, [_P, _P, _P, C.c_longlong, _P]),
+    "vlfm_attention_f32": (C.c_int, [_P] * 5 + [C.c_int] * 9 + [C.c_float, _P]),
     "vlfm_swin_patch_im2col": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "vlfm_swin_window_attention": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 6 + [_P]),
     "vlfm_swin_patch_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

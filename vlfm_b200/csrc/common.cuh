@@ -45,6 +45,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// "x2" operands (fp32-grade GEMMs on the fp16 tensor path): y = hi + lo / 2048 with hi = fp16(y), lo = fp16((y - hi) * 2048).
+// The residual is scaled so that it stays a NORMAL fp16 number of y's magnitude (no subnormal precision loss).
+constexpr float X2_SCALE = 2048.f;
+__device__ __forceinline__ void split_x2(float y, __half& hi, __half& lo) {
+  hi = __float2half_rn(y);
+  lo = __float2half_rn((y - __half2float(hi)) * X2_SCALE);
+}
 __device__ __forceinline__ float ld_cg_f32(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
 

@@ -100,6 +100,7 @@ struct GemmArgs {
   // "tail rows": when M = 128*q + r with 1 <= r <= GEMM_TAIL_MAX (ViT: 257 tokens), only q row tiles are launched and the CTAs
   // of the last one also compute the r extra rows on CUDA cores from the W tiles already staged for the tensor core
   const __half* a_tail; int lda, tail_rows, tail_row0;
+  void* out_lo;       // VLFM_EPI_BIAS_GELU_F16X2: the x2 residual of the fp16 output (same ldo)
 };
 constexpr int GEMM_TAIL_MAX = 2;
 constexpr int GEMM_TAIL_KMAX = 6144;   // K elements of one CTA's slice that fit the tail-row staging buffer
@@ -112,14 +113,20 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 
 // Epilogue of one 128-row accumulator slab: TMEM -> registers (32 lanes x 32 columns per tcgen05.ld),
 // fused bias / GELU / residual, vectorised global stores.  `q` = TMEM lane quarter of this warp.
-template <int BN>
+template <int BN, bool X2 = false>
 __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row, int n_blk, const GemmArgs& g, bool split,
-                                              int c_first, const float* sbias = nullptr) {
+                                              int c_first, const float* sbias = nullptr, uint32_t tmem_corr = 0) {
   // the two warps sharing a lane quarter interleave the 32-column chunks
 #pragma unroll 1
   for (int c = c_first; c < BN / 32; c += 2) {
     uint32_t r[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+    if (X2) {   // x2 GEMM: main accumulator (hi.hi) + correction accumulator (lo.hi + hi.lo, scaled by 2048)
+      uint32_t r2[32];
+      tmem_ld32(tmem_corr + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(r2[j]), 1.f / X2_SCALE, __uint_as_float(r[j])));
+    }
     const int n0 = n_blk * BN + c * 32;
     if (row >= g.M || n0 >= g.N) continue;
     float v[32];
@@ -146,8 +153,8 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
         v[j] = __uint_as_float(r[j]) + b;
       }
     }
-    if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16 || g.epi == VLFM_EPI_BIAS_RELU_F16) {
-      if (g.epi == VLFM_EPI_BIAS_GELU_F16) {
+    if (g.epi == VLFM_EPI_BIAS_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16 || g.epi == VLFM_EPI_BIAS_RELU_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16X2) {
+      if (g.epi == VLFM_EPI_BIAS_GELU_F16 || g.epi == VLFM_EPI_BIAS_GELU_F16X2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       } else if (g.epi == VLFM_EPI_BIAS_RELU_F16) {
@@ -164,10 +171,25 @@ __device__ __forceinline__ void epilogue_slab(uint32_t tmem_base, int q, int row
           pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
           pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
           *reinterpret_cast<uint4*>(o + j) = pk;
+          if (g.epi == VLFM_EPI_BIAS_GELU_F16X2) {
+            const __half2 hh[4] = {h0, h1, h2, h3};
+            uint32_t pl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(hh[e]);
+              __half2 l = __floats2half2_rn((v[j + 2 * e] - f.x) * X2_SCALE, (v[j + 2 * e + 1] - f.y) * X2_SCALE);
+              pl[e] = *reinterpret_cast<uint32_t*>(&l);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(g.out_lo) + (size_t)row * g.ldo + n0 + j) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (n0 + j < g.N) o[j] = __float2half_rn(v[j]);   // static indices: keeps v[] in registers
+        for (int j = 0; j < 32; ++j) if (n0 + j < g.N) {   // static indices: keeps v[] in registers
+          const __half hi = __float2half_rn(v[j]);
+          o[j] = hi;
+          if (g.epi == VLFM_EPI_BIAS_GELU_F16X2) reinterpret_cast<__half*>(g.out_lo)[(size_t)row * g.ldo + n0 + j] = __float2half_rn((v[j] - __half2float(hi)) * X2_SCALE);
+        }
       }
     } else {
       const bool partial = (g.epi == VLFM_EPI_PARTIAL_F32);
@@ -379,6 +401,126 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   if (dbg && threadIdx.x == 0) g.dbg[6] = clock64();
   if (g.dbg && threadIdx.x == 0 && cta_lin < 2048) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g.dbg[9 + 2 * cta_lin] = t; }
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// ================================================================================================
+// "x2" GEMM: fp32-grade product on the fp16 tensor path (the Q-Former, which the reference runs in float32).
+//   A = A_hi + A_lo / 2048,  W = W_hi + W_lo / 2048   (fp16 pairs, see split_x2 in common.cuh)
+//   out = A_hi.W_hi  +  (A_lo.W_hi + A_hi.W_lo) / 2048          (the lo.lo term is ~2^-22 relative: dropped)
+// Same structure as gemm_f16_tcgen05_kernel; a stage holds FOUR tiles, the issuer thread emits three tcgen05.mma per K step into
+// TWO TMEM accumulators (main, correction) and the epilogue merges them.  At 32 query rows the tensor pipe is idle anyway: the
+// cost is the second weight tile per stage (fp32-sized weight traffic).
+// ================================================================================================
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16x2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
+                          const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl, GemmArgs g) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256);
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sAl = sA + STAGES * A_BYTES;
+  uint8_t* sB = sAl + STAGES * A_BYTES;
+  uint8_t* sBl = sB + STAGES * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBl + STAGES * B_BYTES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accbar = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // [BN]
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+  const int kb_begin = blockIdx.z * g.kb_per_split;
+  const int num_k = min((g.K + BK - 1) / BK - kb_begin, g.kb_per_split);
+  const bool split = gridDim.z > 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights first (independent of the predecessor kernel), activations after the dependency wait
+      const int pre = num_k < STAGES ? num_k : STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(full0 + 8 * kb, 2 * (A_BYTES + B_BYTES));
+        tma_load_2d(smem_u32(sB + kb * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * kb);
+        tma_load_2d(smem_u32(sBl + kb * B_BYTES), &tmBl, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * kb);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb) {
+        tma_load_2d(smem_u32(sA + kb * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * kb);
+        tma_load_2d(smem_u32(sAl + kb * A_BYTES), &tmAl, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * kb);
+      }
+      int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
+      for (int kb = pre; kb < num_k; ++kb) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + B_BYTES));
+        tma_load_2d(smem_u32(sA + s * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * s);
+        tma_load_2d(smem_u32(sAl + s * A_BYTES), &tmAl, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * s);
+        tma_load_2d(smem_u32(sB + s * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * s);
+        tma_load_2d(smem_u32(sBl + s * B_BYTES), &tmBl, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)BN;
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * A_BYTES), al0 = smem_u32(sAl + s * A_BYTES);
+        const uint32_t b0 = smem_u32(sB + s * B_BYTES), bl0 = smem_u32(sBl + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = umma_desc_k128(a0 + k * 32), dal = umma_desc_k128(al0 + k * 32);
+          const uint64_t db = umma_desc_k128(b0 + k * 32), dbl = umma_desc_k128(bl0 + k * 32);
+          const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+          tc_mma_f16(acc0, da, db, IDESC, first);
+          tc_mma_f16(acc1, dal, db, IDESC, first);
+          tc_mma_f16(acc1, da, dbl, IDESC, 1u);
+        }
+        tc_commit(empty0 + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      tc_commit(accbar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m_blk * BM + q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    if (et < BN) { const int n = n_blk * BN + et; sbias[et] = (g.bias && n < g.N) ? __ldg(g.bias + n) : 0.f; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    pdl_wait();
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    epilogue_slab<BN, true>(tmem_base, q, row, n_blk, g, split, (warp - 2) >> 2, sbias, tmem_base + (uint32_t)BN);
+  }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -717,6 +859,28 @@ static int launch_gemm_2cta_persistent(const CUtensorMap& ta, const void* W, int
   return VLFM_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_gemm_x2(const CUtensorMap& ta, const CUtensorMap& tal, const void* W, const void* Wl, int ldw, const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap tb, tbl;
+  int rc = make_map(&tb, W, g.N, g.K, ldw, BN);
+  if (!rc) rc = make_map(&tbl, Wl, g.N, g.K, ldw, BN);
+  if (rc) return rc;
+  constexpr size_t smem = (size_t)STAGES * 2 * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024 + BN * 4 + 32;
+  static_assert(smem <= 227 * 1024, "x2 GEMM stage ring exceeds shared memory");
+  static bool configured = false;
+  if (!configured) {
+    rc = check_cuda(cudaFuncSetAttribute(gemm_f16x2_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(gemm x2)");
+    if (rc) return rc;
+    configured = true;
+  }
+  const int num_k = (g.K + BK - 1) / BK;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (num_k + g.kb_per_split - 1) / g.kb_per_split);
+  rc = check_cuda(launch_pdl(gemm_f16x2_tcgen05_kernel<BN, STAGES>, grid, dim3(GEMM_THREADS), smem, st, ta, tal, tb, tbl, g), "gemm_f16x2_tcgen05_kernel");
+  if (rc) return rc;
+  count_launch();
+  return VLFM_OK;
+}
+
 }  // namespace vlfm
 
 using namespace vlfm;
@@ -863,4 +1027,78 @@ extern "C" int vlfm_gemm_f16_resid_ln(const void* d_A, const void* d_W, const fl
   if (rc) return rc;
   if (splits > 1) return vlfm_layernorm_reduce(d_x, d_partials, splits, (long long)M * N, d_gamma, d_beta, d_out16, d_out32, M, N, ldx, ld16, ld32, eps, stream);
   return vlfm_layernorm(d_x, d_gamma, d_beta, d_out16, d_out32, M, N, ldx, ld16, ld32, eps, stream);
+}
+
+// ---- x2 GEMMs (fp32-grade, see gemm_f16x2_tcgen05_kernel) ----
+static int gemm_x2_dispatch(const void* d_A_hi, const void* d_A_lo, const void* d_W_hi, const void* d_W_lo, int M, int N, int K, int lda, int ldw,
+                            GemmArgs g, void* stream, float* d_partials, size_t partial_bytes, int* splits_out) {
+  if (splits_out) *splits_out = 1;
+  CUtensorMap ta, tal;
+  int rc = make_map(&ta, d_A_hi, M, K, lda, BM);
+  if (!rc) rc = make_map(&tal, d_A_lo, M, K, lda, BM);
+  if (rc) return rc;
+  const int mt = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
+  // tile width: wide tiles for the one big problem (cross-attention K/V of all layers: 257 x 9216 x 1408), else enough CTAs to
+  // cover the machine; split K (deterministic partial sums) only for the residual epilogue -- at 32 rows a partial slab is 100 KB
+  int bn = 32;
+  if (mt >= 2 && N >= 4096) bn = 128;
+  else if ((long)mt * ((N + 63) / 64) >= 96) bn = 64;
+  const int tiles = mt * ((N + bn - 1) / bn);
+  int sp = 1;
+  if (g.epi == VLFM_EPI_BIAS_RESID_F32 && d_partials) {
+    sp = 148 / tiles; if (sp > num_k / 3) sp = num_k / 3; if (sp > 8) sp = 8; if (sp < 1) sp = 1;
+  }
+  g.kb_per_split = (num_k + sp - 1) / sp;
+  const int launched = (num_k + g.kb_per_split - 1) / g.kb_per_split;
+  if (launched > 1) {
+    if ((size_t)launched * (size_t)M * (size_t)N * 4 > partial_bytes) { g.kb_per_split = num_k; }
+    else { g.epi = VLFM_EPI_PARTIAL_F32; g.out = d_partials; g.ldo = N; g.split_stride = (long long)M * N; if (splits_out) *splits_out = launched; }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 128) return launch_gemm_x2<128, 3>(ta, tal, d_W_hi, d_W_lo, ldw, g, st);
+  if (bn == 64) return launch_gemm_x2<64, 4>(ta, tal, d_W_hi, d_W_lo, ldw, g, st);
+  return launch_gemm_x2<32, 5>(ta, tal, d_W_hi, d_W_lo, ldw, g, st);
+}
+
+static int x2_args_ok(const char* who, const void* a, const void* al, const void* w, const void* wl, const void* out, int M, int N, int K, int lda, int ldw, int ldo) {
+  if (!a || !al || !w || !wl || !out || M < 1 || N < 1 || K < 1) { set_error("%s: bad argument", who); return VLFM_E_INVALID; }
+  if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)a & 15) || ((uintptr_t)al & 15) || ((uintptr_t)w & 15) || ((uintptr_t)wl & 15) || ((uintptr_t)out & 15)) {
+    set_error("%s: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned", who); return VLFM_E_INVALID; }
+  return VLFM_OK;
+}
+
+// out = epilogue((A_hi + A_lo/2048) @ (W_hi + W_lo/2048)^T + bias).  epilogue: VLFM_EPI_BIAS_F32 (fp32 out), VLFM_EPI_BIAS_RESID_F32
+// (fp32 out += ...), VLFM_EPI_BIAS_GELU_F16X2 (GELU, then fp16 x2 operands into d_out / d_out_lo).
+extern "C" int vlfm_gemm_f16x2(const void* d_A_hi, const void* d_A_lo, const void* d_W_hi, const void* d_W_lo, const float* d_bias, void* d_out,
+                               void* d_out_lo, int M, int N, int K, int lda, int ldw, int ldo, int epilogue, void* stream) {
+  int rc = x2_args_ok("vlfm_gemm_f16x2", d_A_hi, d_A_lo, d_W_hi, d_W_lo, d_out, M, N, K, lda, ldw, ldo);
+  if (rc) return rc;
+  if (epilogue != VLFM_EPI_BIAS_F32 && epilogue != VLFM_EPI_BIAS_RESID_F32 && epilogue != VLFM_EPI_BIAS_GELU_F16X2) {
+    set_error("vlfm_gemm_f16x2: epilogue %d unsupported (fp32, fp32 residual, GELU x2)", epilogue); return VLFM_E_INVALID; }
+  if (epilogue == VLFM_EPI_BIAS_GELU_F16X2 && (!d_out_lo || ((uintptr_t)d_out_lo & 15))) { set_error("vlfm_gemm_f16x2: d_out_lo missing / unaligned"); return VLFM_E_INVALID; }
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, nullptr, 0, nullptr, 0, 0, 0, d_out_lo};
+  return gemm_x2_dispatch(d_A_hi, d_A_lo, d_W_hi, d_W_lo, M, N, K, lda, ldw, g, stream, nullptr, 0, nullptr);
+}
+
+extern "C" int vlfm_layernorm_x2(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_hi, void* d_out_lo, float* d_out32,
+                                 int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream);
+extern "C" int vlfm_layernorm_reduce_x2(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                                        const float* d_beta, void* d_out_hi, void* d_out_lo, float* d_out32, int rows, int D, int ldx, int ldo16,
+                                        int ldo32, float eps, void* stream);
+
+// x += (x2 product) + bias ; LayerNorm(x) -> x2 operands (hi, lo) and/or fp32.  Bitwise reproducible like vlfm_gemm_f16_resid_ln.
+extern "C" int vlfm_gemm_f16x2_resid_ln(const void* d_A_hi, const void* d_A_lo, const void* d_W_hi, const void* d_W_lo, const float* d_bias,
+                                        float* d_x, int M, int N, int K, int lda, int ldw, int ldx, const float* d_gamma, const float* d_beta,
+                                        void* d_out_hi, void* d_out_lo, int ld16, float* d_out32, int ld32, float eps, float* d_partials,
+                                        size_t partial_bytes, void* stream) {
+  int rc = x2_args_ok("vlfm_gemm_f16x2_resid_ln", d_A_hi, d_A_lo, d_W_hi, d_W_lo, d_x, M, N, K, lda, ldw, ldx);
+  if (rc) return rc;
+  if (!d_gamma || !d_beta || !d_out_hi || !d_out_lo || (N & 3) || (ld16 & 3) || (ld32 & 3) || ((uintptr_t)d_partials & 15)) {
+    set_error("vlfm_gemm_f16x2_resid_ln: bad argument / alignment"); return VLFM_E_INVALID; }
+  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, nullptr, 0, nullptr, 0, 0, 0, nullptr};
+  int splits = 1;
+  rc = gemm_x2_dispatch(d_A_hi, d_A_lo, d_W_hi, d_W_lo, M, N, K, lda, ldw, g, stream, d_partials, partial_bytes, &splits);
+  if (rc) return rc;
+  if (splits > 1) return vlfm_layernorm_reduce_x2(d_x, d_partials, splits, (long long)M * N, d_gamma, d_beta, d_out_hi, d_out_lo, d_out32, M, N, ldx, ld16, ld32, eps, stream);
+  return vlfm_layernorm_x2(d_x, d_gamma, d_beta, d_out_hi, d_out_lo, d_out32, M, N, ldx, ld16, ld32, eps, stream);
 }

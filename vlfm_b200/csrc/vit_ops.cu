@@ -80,7 +80,7 @@ template <int MAXV4>
 __global__ void __launch_bounds__(128)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __half* __restrict__ out16, float* __restrict__ out32, int rows, int D, int ldx, int ldo16, int ldo32,
-                 float eps) {
+                 float eps, __half* __restrict__ out16_lo) {   // out16_lo: the x2 residual of out16 (same stride), or null
   pdl_trigger();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int D4 = D >> 2;
@@ -128,6 +128,12 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
         __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
         uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
         *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + 4 * j) = pk;
+        if (out16_lo) {
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          __half2 l0 = __floats2half2_rn((y.x - f0.x) * X2_SCALE, (y.y - f0.y) * X2_SCALE), l1 = __floats2half2_rn((y.z - f1.x) * X2_SCALE, (y.w - f1.y) * X2_SCALE);
+          uint2 pl = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+          *reinterpret_cast<uint2*>(out16_lo + (size_t)row * ldo16 + 4 * j) = pl;
+        }
       }
       if (out32) *reinterpret_cast<float4*>(out32 + (size_t)row * ldo32 + 4 * j) = y;
     }
@@ -143,7 +149,7 @@ template <int V4>
 __global__ void __launch_bounds__(128)
 layernorm_reduce_kernel(float* x, const float* __restrict__ partials, int splits, long long split_stride,
                         const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out16,
-                        float* out32, int rows, int D, int ldx, int ldo16, int ldo32, float eps) {   // out32 may alias x (post-LN blocks)
+                        float* out32, int rows, int D, int ldx, int ldo16, int ldo32, float eps, __half* __restrict__ out16_lo) {   // out32 may alias x (post-LN blocks)
   pdl_trigger();
   __shared__ float red[2][4];
   const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -218,6 +224,12 @@ layernorm_reduce_kernel(float* x, const float* __restrict__ partials, int splits
         __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
         uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
         *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + 4 * j) = pk;
+        if (out16_lo) {
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          __half2 l0 = __floats2half2_rn((y.x - f0.x) * X2_SCALE, (y.y - f0.y) * X2_SCALE), l1 = __floats2half2_rn((y.z - f1.x) * X2_SCALE, (y.w - f1.y) * X2_SCALE);
+          uint2 pl = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+          *reinterpret_cast<uint2*>(out16_lo + (size_t)row * ldo16 + 4 * j) = pl;
+        }
       }
       if (out32) *reinterpret_cast<float4*>(out32 + (size_t)row * ldo32 + 4 * j) = y;
     }
@@ -472,6 +484,101 @@ __global__ void itc_head_kernel(const float* __restrict__ proj, const float* __r
   }
 }
 
+
+// x2 operands of an fp32 array: hi = fp16(v) (optional output), lo = fp16((v - hi) * 2048)
+__global__ void split_x2_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long n4) {
+  pdl_trigger();
+  pdl_wait();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    __half h[4], l[4];
+    split_x2(v.x, h[0], l[0]); split_x2(v.y, h[1], l[1]); split_x2(v.z, h[2], l[2]); split_x2(v.w, h[3], l[3]);
+    if (hi) reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+// ----------------------------------------------------------- fp32 attention (Q-Former) ----
+// The reference runs the Q-Former in float32 (lavis keeps only the ViT in half precision), and the ITC cosine is sensitive to
+// it: fp16 operands in the Q-Former alone move the cosine by 3e-5 on average, the ViT's by 1e-6 (measured on the fp32 oracle).
+// 32 queries x <= 272 keys x 12 heads per image is ~25 MFLOP: plain fp32 on CUDA cores.  One CTA per (head, image): K (padded
+// rows: lanes read different keys at the same channel) and V staged in shared memory as fp32; a warp owns a query row at a time:
+// lane = key for the scores, lane = channel for P.V.  Output = x2 operands (hi, lo) of the output projection GEMM.
+constexpr int ATT32_NKMAX = 272;
+__global__ void __launch_bounds__(256)
+attention_f32_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, __half* __restrict__ o_hi,
+                     __half* __restrict__ o_lo, int ldq, int ldk, int ldv, int ldo, int Nq, int Nk, int hd, float scale) {
+  extern __shared__ float sm32[];
+  pdl_trigger();
+  const int h = blockIdx.x, b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kp = hd + 1;
+  float* sK = sm32;                         // [Nk][hd + 1]
+  float* sV = sK + (((size_t)Nk * kp + 3) & ~(size_t)3);   // [Nk][hd], 16-byte aligned
+  float* sQ = sV + (size_t)Nk * hd;         // [8][hd]
+  float* sP = sQ + 8 * hd;                  // [8][Nk]
+  pdl_wait();
+  const int hd4 = hd >> 2;
+  for (int i = threadIdx.x; i < Nk * hd4; i += 256) {
+    const int j = i / hd4, c = (i - j * hd4) << 2;
+    const float4 kv = *reinterpret_cast<const float4*>(k + (size_t)(b * Nk + j) * ldk + h * hd + c);
+    const float4 vv = *reinterpret_cast<const float4*>(v + (size_t)(b * Nk + j) * ldv + h * hd + c);
+    float* kd = sK + (size_t)j * kp + c;
+    kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+    *reinterpret_cast<float4*>(sV + (size_t)j * hd + c) = vv;
+  }
+  __syncthreads();
+  float* myq = sQ + warp * hd;
+  float* myp = sP + (size_t)warp * Nk;
+  for (int r = warp; r < Nq; r += 8) {
+    const float* qr = q + (size_t)(b * Nq + r) * ldq + h * hd;
+    for (int d = lane; d < hd; d += 32) myq[d] = qr[d];
+    __syncwarp();
+    float sc[(ATT32_NKMAX + 31) / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < (ATT32_NKMAX + 31) / 32; ++t) {
+      const int j = lane + 32 * t;
+      float a = -INFINITY;
+      if (j < Nk) {
+        const float* kr = sK + (size_t)j * kp;
+        float acc = 0.f;
+        for (int d = 0; d < hd; ++d) acc = fmaf(myq[d], kr[d], acc);
+        a = acc * scale;
+      }
+      sc[t] = a;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < (ATT32_NKMAX + 31) / 32; ++t) {
+      const int j = lane + 32 * t;
+      const float e = j < Nk ? expf(sc[t] - mx) : 0.f;
+      sc[t] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int t = 0; t < (ATT32_NKMAX + 31) / 32; ++t) {
+      const int j = lane + 32 * t;
+      if (j < Nk) myp[j] = sc[t] * inv;
+    }
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < Nk; ++j) acc = fmaf(myp[j], sV[(size_t)j * hd + d], acc);
+      __half hi, lo;
+      split_x2(acc, hi, lo);
+      const size_t o = (size_t)(b * Nq + r) * ldo + h * hd + d;
+      o_hi[o] = hi; o_lo[o] = lo;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace vlfm
 
 using namespace vlfm;
@@ -506,8 +613,9 @@ extern "C" int vlfm_assemble_tokens(const float* d_patch, const float* d_cls, co
   return VLFM_OK;
 }
 
-extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out16, float* d_out32,
-                              int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream) {
+static int layernorm_impl(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out16, void* d_out16_lo, float* d_out32,
+                          int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream) {
+  __half* lo16 = (__half*)d_out16_lo;
   if (!d_x || !d_gamma || !d_beta || (!d_out16 && !d_out32) || rows < 1 || D < 1) { set_error("vlfm_layernorm: bad argument"); return VLFM_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((rows + 7) / 8);
@@ -515,18 +623,29 @@ extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const floa
   __half* o16 = (__half*)d_out16;
   if ((D & 3) || (ldx & 3) || (ldo16 & 3) || (ldo32 & 3)) { set_error("vlfm_layernorm: D and strides must be multiples of 4"); return VLFM_E_UNSUPPORTED; }
   grid = dim3((rows + 3) / 4);
-  if (D <= 128 * 2) e = launch_pdl(layernorm_kernel<2>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
-  else if (D <= 128 * 6) e = launch_pdl(layernorm_kernel<6>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
-  else if (D <= 128 * 12) e = launch_pdl(layernorm_kernel<12>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  if (D <= 128 * 2) e = launch_pdl(layernorm_kernel<2>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
+  else if (D <= 128 * 6) e = launch_pdl(layernorm_kernel<6>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
+  else if (D <= 128 * 12) e = launch_pdl(layernorm_kernel<12>, grid, dim3(128), 0, st, d_x, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
   else { set_error("vlfm_layernorm: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
   { int rc = check_cuda(e, "layernorm_kernel"); if (rc) return rc; }
   count_launch();
   return VLFM_OK;
 }
+extern "C" int vlfm_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out16, float* d_out32,
+                              int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream) {
+  return layernorm_impl(d_x, d_gamma, d_beta, d_out16, nullptr, d_out32, rows, D, ldx, ldo16, ldo32, eps, stream);
+}
+// LayerNorm with the fp16 output split into x2 operands (hi, lo); d_out32 optional
+extern "C" int vlfm_layernorm_x2(const float* d_x, const float* d_gamma, const float* d_beta, void* d_out_hi, void* d_out_lo, float* d_out32,
+                                 int rows, int D, int ldx, int ldo16, int ldo32, float eps, void* stream) {
+  if (!d_out_hi || !d_out_lo) { set_error("vlfm_layernorm_x2: null output"); return VLFM_E_INVALID; }
+  return layernorm_impl(d_x, d_gamma, d_beta, d_out_hi, d_out_lo, d_out32, rows, D, ldx, ldo16, ldo32, eps, stream);
+}
 
-extern "C" int vlfm_layernorm_reduce(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
-                                     const float* d_beta, void* d_out16, float* d_out32, int rows, int D, int ldx, int ldo16, int ldo32,
-                                     float eps, void* stream) {
+static int layernorm_reduce_impl(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                                 const float* d_beta, void* d_out16, void* d_out16_lo, float* d_out32, int rows, int D, int ldx, int ldo16, int ldo32,
+                                 float eps, void* stream) {
+  __half* lo16 = (__half*)d_out16_lo;
   if (!d_x || !d_partials || !d_gamma || !d_beta || (!d_out16 && !d_out32) || rows < 1 || D < 1 || splits < 1 || splits > 16) {
     set_error("vlfm_layernorm_reduce: bad argument"); return VLFM_E_INVALID; }
   if ((D & 3) || (ldx & 3) || (ldo16 & 3) || (ldo32 & 3) || (split_stride & 3)) { set_error("vlfm_layernorm_reduce: D and strides must be multiples of 4"); return VLFM_E_UNSUPPORTED; }
@@ -534,12 +653,23 @@ extern "C" int vlfm_layernorm_reduce(float* d_x, const float* d_partials, int sp
   const dim3 grid(rows);
   __half* o16 = (__half*)d_out16;
   cudaError_t e;
-  if (D <= 512 * 2) e = launch_pdl(layernorm_reduce_kernel<2>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
-  else if (D <= 512 * 3) e = launch_pdl(layernorm_reduce_kernel<3>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps);
+  if (D <= 512 * 2) e = launch_pdl(layernorm_reduce_kernel<2>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
+  else if (D <= 512 * 3) e = launch_pdl(layernorm_reduce_kernel<3>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
   else { set_error("vlfm_layernorm_reduce: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
   { int rc = check_cuda(e, "layernorm_reduce_kernel"); if (rc) return rc; }
   count_launch();
   return VLFM_OK;
+}
+extern "C" int vlfm_layernorm_reduce(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                                     const float* d_beta, void* d_out16, float* d_out32, int rows, int D, int ldx, int ldo16, int ldo32,
+                                     float eps, void* stream) {
+  return layernorm_reduce_impl(d_x, d_partials, splits, split_stride, d_gamma, d_beta, d_out16, nullptr, d_out32, rows, D, ldx, ldo16, ldo32, eps, stream);
+}
+extern "C" int vlfm_layernorm_reduce_x2(float* d_x, const float* d_partials, int splits, long long split_stride, const float* d_gamma,
+                                        const float* d_beta, void* d_out_hi, void* d_out_lo, float* d_out32, int rows, int D, int ldx, int ldo16,
+                                        int ldo32, float eps, void* stream) {
+  if (!d_out_hi || !d_out_lo) { set_error("vlfm_layernorm_reduce_x2: null output"); return VLFM_E_INVALID; }
+  return layernorm_reduce_impl(d_x, d_partials, splits, split_stride, d_gamma, d_beta, d_out_hi, d_out_lo, d_out32, rows, D, ldx, ldo16, ldo32, eps, stream);
 }
 
 extern "C" int vlfm_attention_f16(const void* d_q, const void* d_k, const void* d_v, void* d_o, int B, int heads, int Nq,
@@ -579,6 +709,36 @@ extern "C" int vlfm_attention_f16(const void* d_q, const void* d_k, const void* 
   else if (hdp == 64) e = big ? launch_pdl(attention_kernel<64, 1>, grid, dim3(32 * ATT_WARPS), sm, st, a) : launch_pdl(attention_kernel<64, 2>, grid, dim3(32 * ATT_WARPS), sm, st, a);
   else e = big ? launch_pdl(attention_kernel<96, 1>, grid, dim3(32 * ATT_WARPS), sm, st, a) : launch_pdl(attention_kernel<96, 2>, grid, dim3(32 * ATT_WARPS), sm, st, a);
   { int rc = check_cuda(e, "attention_kernel"); if (rc) return rc; }
+  count_launch();
+  return VLFM_OK;
+}
+
+// softmax(q k^T * scale) v in float32 for small problems (Q-Former); q, k, v fp32 rows (b * N + i), head h at columns [h*hd, (h+1)*hd);
+// output as x2 operands (hi, lo fp16, same stride).  hd in {32, 64}, Nk <= 272.
+extern "C" int vlfm_attention_f32(const float* d_q, const float* d_k, const float* d_v, void* d_o_hi, void* d_o_lo, int B, int heads, int Nq,
+                                  int Nk, int hd, int ldq, int ldk, int ldv, int ldo, float scale, void* stream) {
+  if (!d_q || !d_k || !d_v || !d_o_hi || !d_o_lo || B < 1 || heads < 1 || Nq < 1 || Nk < 1) { set_error("vlfm_attention_f32: bad argument"); return VLFM_E_INVALID; }
+  if (Nk > ATT32_NKMAX || (hd != 32 && hd != 64) || (ldk & 3) || (ldv & 3) || B > 65535) {
+    set_error("vlfm_attention_f32: unsupported shape (Nk<=%d, hd in {32,64}, strides %%4==0)", ATT32_NKMAX); return VLFM_E_UNSUPPORTED; }
+  const size_t smem = ((((size_t)Nk * (hd + 1) + 3) & ~(size_t)3) + (size_t)Nk * hd + 8 * hd + 8 * (size_t)Nk) * 4;
+  static size_t cfg = 0;
+  if (smem > 48 * 1024 && smem > cfg) {
+    int rc = check_cuda(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr(attention_f32)");
+    if (rc) return rc; cfg = smem;
+  }
+  cudaError_t e = launch_pdl(attention_f32_kernel, dim3(heads, B), dim3(256), smem, (cudaStream_t)stream, d_q, d_k, d_v, (__half*)d_o_hi, (__half*)d_o_lo,
+                             ldq, ldk, ldv, ldo, Nq, Nk, hd, scale);
+  { int rc = check_cuda(e, "attention_f32_kernel"); if (rc) return rc; }
+  count_launch();
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_split_x2(const float* d_src, void* d_hi, void* d_lo, long long n, void* stream) {
+  if (!d_src || !d_lo || n < 4 || (n & 3) || ((uintptr_t)d_src & 15) || ((uintptr_t)d_lo & 7) || ((uintptr_t)d_hi & 7)) {
+    set_error("vlfm_split_x2: bad argument (n %% 4 == 0, aligned pointers)"); return VLFM_E_INVALID; }
+  long blocks = (n / 4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaError_t e = launch_pdl(split_x2_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, d_src, (__half*)d_hi, (__half*)d_lo, (long)(n / 4));
+  { int rc = check_cuda(e, "split_x2_kernel"); if (rc) return rc; }
   count_launch();
   return VLFM_OK;
 }

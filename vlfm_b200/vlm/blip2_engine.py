@@ -39,6 +39,9 @@ class Blip2ITCEngine:
         self._tables: Dict[Tuple[int, int], Tuple[torch.Tensor, ...]] = {}
         self._mean = (ctypes.c_float * 3)(*CLIP_MEAN)
         self._std = (ctypes.c_float * 3)(*CLIP_STD)
+        # Q-Former in float32-grade arithmetic (x2 operands on the fp16 tensor path, fp32 attention): the reference runs it in fp32
+        # (only the ViT is half precision in lavis) and fp16 operands there alone cost ~3e-5 on the cosine.  VLFM_QFORMER_X2=0: fp16.
+        self.x2 = os.environ.get("VLFM_QFORMER_X2", "1") != "0"
         self._load(state_dict)
         self._alloc(max_batch)
         self.text_feat = torch.zeros(dims.proj, dtype=F32, device=self.dev)
@@ -58,6 +61,10 @@ class Blip2ITCEngine:
 
         def f(t):
             return t.to(dev, F32).contiguous()
+
+        def lo(t):  # x2 residual of an fp32 weight: (w - fp16(w)) * 2048 as fp16
+            t = t.to(dev, F32)
+            return ((t - t.to(F16).to(F32)) * 2048.0).to(F16).contiguous()
 
         D = d.v_hidden
         pw = sd["vision_model.embeddings.patch_embedding.weight"].reshape(D, d.patch_k)
@@ -107,21 +114,32 @@ class Blip2ITCEngine:
                 L["cln_w"], L["cln_b"] = f(sd[c + "output.LayerNorm.weight"]), f(sd[c + "output.LayerNorm.bias"])
                 kv_w.append(torch.cat([sd[c + "attention.key.weight"], sd[c + "attention.value.weight"]], 0))
                 kv_b.append(torch.cat([sd[c + "attention.key.bias"], sd[c + "attention.value.bias"]], 0))
+            if self.x2:
+                srcs = {"qkv_w": torch.cat([sd[a + "attention.query.weight"], sd[a + "attention.key.weight"], sd[a + "attention.value.weight"]], 0),
+                        "so_w": sd[a + "output.dense.weight"], "iq_w": sd[p + "intermediate_query.dense.weight"],
+                        "oq_w": sd[p + "output_query.dense.weight"], "it_w": sd[p + "intermediate.dense.weight"], "ot_w": sd[p + "output.dense.weight"]}
+                if L["cross"] >= 0:
+                    srcs["cq_w"], srcs["co_w"] = sd[c + "attention.query.weight"], sd[c + "output.dense.weight"]
+                for k_, w_ in srcs.items():
+                    L[k_ + "l"] = lo(w_)
             self.qf.append(L)
         self.ncross = len(kv_w)
         self.kv_w, self.kv_b = h(torch.cat(kv_w, 0)), f(torch.cat(kv_b, 0))  # one GEMM feeds every cross layer
         self.vp_w, self.vp_b = h(sd["vision_projection.weight"]), f(sd["vision_projection.bias"])
         self.tp_w, self.tp_b = h(sd["text_projection.weight"]), f(sd["text_projection.bias"])
+        if self.x2:
+            self.kv_wl, self.vp_wl, self.tp_wl = lo(torch.cat(kv_w, 0)), lo(sd["vision_projection.weight"]), lo(sd["text_projection.weight"])
         # layernorm(query_tokens) is input independent (modeling: qformer.layernorm on query_embeds)
         q0 = f(sd["query_tokens"].reshape(d.queries, H))
         self.q0_32 = torch.empty_like(q0)
         self.q0_16 = torch.empty(d.queries, H, dtype=F16, device=dev)
-        self._ln(q0, self.q_ln_w, self.q_ln_b, self.q0_16, self.q0_32, d.q_eps)
+        self.q0_lo = torch.empty(d.queries, H, dtype=F16, device=dev)
+        self._ln_x2(q0, self.q_ln_w, self.q_ln_b, self.q0_16, self.q0_lo, self.q0_32, d.q_eps)
 
     def weight_bytes(self) -> int:
         n = 0
-        for t in [self.patch_w, self.kv_w, self.vp_w] + [v for L in self.vit for k, v in L.items() if k.endswith("_w") and v.dtype == F16] \
-                + [v for L in self.qf for k, v in L.items() if isinstance(v, torch.Tensor) and v.dtype == F16 and k[:2] not in ("it", "ot")]:
+        for t in [self.patch_w, self.kv_w, self.vp_w] + ([self.kv_wl, self.vp_wl] if self.x2 else []) + [v for L in self.vit for k, v in L.items() if k.endswith("_w") and v.dtype == F16] \
+                + [v for L in self.qf for k, v in L.items() if isinstance(v, torch.Tensor) and v.dtype == F16 and k[:2] not in ("it", "ot")]:   # text-branch FFN weights are not on the per-image path
             n += t.numel() * 2
         return n
 
@@ -146,6 +164,15 @@ class Blip2ITCEngine:
         self.q_ao = e(B * Q, H)
         self.q_f = e(B * Q, I)
         self.q_proj = e(B * Q, d.proj, dt=F32)
+        if self.x2:
+            self.b_img32 = e(B * T, D, dt=F32)
+            self.b_img_lo = e(B * T, D)
+            self.b_kv32 = e(B * T, self.ncross * 2 * H, dt=F32)
+            self.q_h_lo = e(B * Q, H)
+            self.q_qkv32 = e(B * Q, 3 * H, dt=F32)
+            self.q_q32 = e(B * Q, H, dt=F32)
+            self.q_ao_lo = e(B * Q, H)
+            self.q_f_lo = e(B * Q, I)
         self.out = torch.zeros(B, dtype=F32, device=dev)
 
     # ---------------------------------------------------------------- primitives ----
@@ -168,6 +195,36 @@ class Blip2ITCEngine:
                                              out32.stride(0) if out32 is not None else 0, eps, self._partials.data_ptr(),
                                              self._partials.numel() * 4, _lib.stream_ptr())
         _lib.check(rc, "vlfm_gemm_f16_resid_ln")
+
+    def _gemm_x2(self, a, al, w, wl, bias, epi, out, out_lo=None):
+        """x2 operands (hi, lo) on both sides -> fp32 (EPI_BIAS_F32 / EPI_BIAS_RESID_F32) or GELU + x2 operands (EPI_BIAS_GELU_F16X2)"""
+        M, K = a.shape
+        rc = self.lib.vlfm_gemm_f16x2(a.data_ptr(), al.data_ptr(), w.data_ptr(), wl.data_ptr(), _lib.ptr(bias), out.data_ptr(), _lib.ptr(out_lo),
+                                      M, w.shape[0], K, a.stride(0), w.stride(0), out.stride(0), epi, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_gemm_f16x2")
+
+    def _gemm_x2_resid_ln(self, a, al, w, wl, bias, x, g, b, out_hi, out_lo, out32, eps):
+        if not self.fuse_ln:
+            self._gemm_x2(a, al, w, wl, bias, _lib.EPI_BIAS_RESID_F32, x)
+            self._ln_x2(x, g, b, out_hi, out_lo, out32, eps)
+            return
+        M, K = a.shape
+        rc = self.lib.vlfm_gemm_f16x2_resid_ln(a.data_ptr(), al.data_ptr(), w.data_ptr(), wl.data_ptr(), _lib.ptr(bias), x.data_ptr(), M, w.shape[0], K,
+                                               a.stride(0), w.stride(0), x.stride(0), g.data_ptr(), b.data_ptr(), out_hi.data_ptr(), out_lo.data_ptr(),
+                                               out_hi.stride(0), _lib.ptr(out32), out32.stride(0) if out32 is not None else 0, eps,
+                                               self._partials.data_ptr(), self._partials.numel() * 4, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_gemm_f16x2_resid_ln")
+
+    def _ln_x2(self, x, g, b, out_hi, out_lo, out32, eps):
+        rows, D = x.shape
+        rc = self.lib.vlfm_layernorm_x2(x.data_ptr(), g.data_ptr(), b.data_ptr(), out_hi.data_ptr(), out_lo.data_ptr(), _lib.ptr(out32), rows, D,
+                                        x.stride(0), out_hi.stride(0), out32.stride(0) if out32 is not None else 0, eps, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_layernorm_x2")
+
+    def _attn32(self, q, k, v, o_hi, o_lo, B, heads, Nq, Nk, hd, scale):
+        rc = self.lib.vlfm_attention_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), o_hi.data_ptr(), o_lo.data_ptr(), B, heads, Nq, Nk, hd,
+                                         q.stride(0), k.stride(0), v.stride(0), o_hi.stride(0), scale, _lib.stream_ptr())
+        _lib.check(rc, "vlfm_attention_f32")
 
     def _ln(self, x, g, b, out16, out32, eps):
         rows, D = x.shape
@@ -219,14 +276,25 @@ class Blip2ITCEngine:
                 nx = self.vit[i + 1]
                 self._gemm_resid_ln(hb_, L["fc2_w"], L["fc2_b"], x, nx["ln1_w"], nx["ln1_b"], xn, None, d.v_eps)
             else:                       # ... and the post-LayerNorm on the last one
-                self._gemm_resid_ln(hb_, L["fc2_w"], L["fc2_b"], x, self.post_w, self.post_b, img16, None, d.v_eps)
-        kv = self.b_kv[:n]
-        self._gemm(img16, self.kv_w, self.kv_b, _lib.EPI_BIAS_F16, kv)
+                self._gemm_resid_ln(hb_, L["fc2_w"], L["fc2_b"], x, self.post_w, self.post_b, img16, self.b_img32[:n] if self.x2 else None, d.v_eps)
         h32, h16 = self.q_h32[:nq], self.q_h16[:nq]
         h32.view(B, Q, H).copy_(self.q0_32)
         h16.view(B, Q, H).copy_(self.q0_16)
-        self._qformer_layers(h32, h16, B, Q, kv, T, text=False)
-        self._gemm(h16, self.vp_w, self.vp_b, _lib.EPI_BIAS_F32, self.q_proj[:nq])
+        if self.x2:
+            # image embeds as x2 operands: hi is the fp16 LayerNorm output itself, lo its residual against the fp32 one
+            img_lo = self.b_img_lo[:n]
+            _lib.check(self.lib.vlfm_split_x2(self.b_img32.data_ptr(), 0, img_lo.data_ptr(), n * D, _lib.stream_ptr()), "vlfm_split_x2")
+            kv = self.b_kv32[:n]
+            self._gemm_x2(img16, img_lo, self.kv_w, self.kv_wl, self.kv_b, _lib.EPI_BIAS_F32, kv)
+            hlo = self.q_h_lo[:nq]
+            hlo.view(B, Q, H).copy_(self.q0_lo)
+            self._qformer_layers_x2(h32, h16, hlo, B, Q, kv, T, text=False)
+            self._gemm_x2(h16, hlo, self.vp_w, self.vp_wl, self.vp_b, _lib.EPI_BIAS_F32, self.q_proj[:nq])
+        else:
+            kv = self.b_kv[:n]
+            self._gemm(img16, self.kv_w, self.kv_b, _lib.EPI_BIAS_F16, kv)
+            self._qformer_layers(h32, h16, B, Q, kv, T, text=False)
+            self._gemm(h16, self.vp_w, self.vp_b, _lib.EPI_BIAS_F32, self.q_proj[:nq])
         rc = self.lib.vlfm_itc_head(self.q_proj.data_ptr(), self.text_feat.data_ptr(), self.out.data_ptr(), B, Q, d.proj,
                                     _lib.stream_ptr())
         _lib.check(rc, "vlfm_itc_head")
@@ -252,6 +320,27 @@ class Blip2ITCEngine:
             self._gemm(h16, iw, ib, _lib.EPI_BIAS_GELU_F16, ff)
             self._gemm_resid_ln(ff, ow, ob, h32, lw, lb, h16, h32, d.q_eps)
 
+    def _qformer_layers_x2(self, h32, hhi, hlo, B, S, kv, T, text: bool) -> None:
+        """the same layers with x2 operands everywhere and float32 attention (modeling: Blip2QFormerLayer; float32 in the reference)"""
+        d = self.d
+        H = d.q_hidden
+        hd = H // d.q_heads
+        n = B * S
+        qkv, qq, ahi, alo, fhi, flo = self.q_qkv32[:n], self.q_q32[:n], self.q_ao[:n], self.q_ao_lo[:n], self.q_f[:n], self.q_f_lo[:n]
+        sc = 1.0 / math.sqrt(hd)
+        for L in self.qf:
+            self._gemm_x2(hhi, hlo, L["qkv_w"], L["qkv_wl"], L["qkv_b"], _lib.EPI_BIAS_F32, qkv)
+            self._attn32(qkv[:, 0:H], qkv[:, H : 2 * H], qkv[:, 2 * H : 3 * H], ahi, alo, B, d.q_heads, S, S, hd, sc)
+            self._gemm_x2_resid_ln(ahi, alo, L["so_w"], L["so_wl"], L["so_b"], h32, L["sln_w"], L["sln_b"], hhi, hlo, h32, d.q_eps)
+            if not text and L["cross"] >= 0:
+                j = L["cross"]
+                self._gemm_x2(hhi, hlo, L["cq_w"], L["cq_wl"], L["cq_b"], _lib.EPI_BIAS_F32, qq)
+                self._attn32(qq, kv[:, j * 2 * H : j * 2 * H + H], kv[:, j * 2 * H + H : (j + 1) * 2 * H], ahi, alo, B, d.q_heads, S, T, hd, sc)
+                self._gemm_x2_resid_ln(ahi, alo, L["co_w"], L["co_wl"], L["co_b"], h32, L["cln_w"], L["cln_b"], hhi, hlo, h32, d.q_eps)
+            k1, k2, kl = ("it", "ot", "otln") if text else ("iq", "oq", "oqln")
+            self._gemm_x2(hhi, hlo, L[k1 + "_w"], L[k1 + "_wl"], L[k1 + "_b"], _lib.EPI_BIAS_GELU_F16X2, fhi, flo)
+            self._gemm_x2_resid_ln(fhi, flo, L[k2 + "_w"], L[k2 + "_wl"], L[k2 + "_b"], h32, L[kl + "_w"], L[kl + "_b"], hhi, hlo, h32, d.q_eps)
+
     # ------------------------------------------------------------------- public ----
     @torch.inference_mode()
     def encode_text(self, token_ids: Sequence[int]) -> torch.Tensor:
@@ -263,10 +352,16 @@ class Blip2ITCEngine:
         emb = (self.word_emb[ids] + self.pos_emb[:S]).contiguous()
         h32, h16 = self.q_h32[:S], self.q_h16[:S]
         with torch.cuda.device(self.dev):
-            self._ln(emb, self.q_ln_w, self.q_ln_b, h16, h32, d.q_eps)
-            self._qformer_layers(h32, h16, 1, S, None, 0, text=True)
             tp = torch.empty(1, d.proj, dtype=F32, device=self.dev)
-            self._gemm(h16[:1], self.tp_w, self.tp_b, _lib.EPI_BIAS_F32, tp)
+            if self.x2:
+                hlo = self.q_h_lo[:S]
+                self._ln_x2(emb, self.q_ln_w, self.q_ln_b, h16, hlo, h32, d.q_eps)
+                self._qformer_layers_x2(h32, h16, hlo, 1, S, None, 0, text=True)
+                self._gemm_x2(h16[:1], hlo[:1], self.tp_w, self.tp_wl, self.tp_b, _lib.EPI_BIAS_F32, tp)
+            else:
+                self._ln(emb, self.q_ln_w, self.q_ln_b, h16, h32, d.q_eps)
+                self._qformer_layers(h32, h16, 1, S, None, 0, text=True)
+                self._gemm(h16[:1], self.tp_w, self.tp_b, _lib.EPI_BIAS_F32, tp)
         return torch.nn.functional.normalize(tp[0], dim=-1)
 
     def set_text(self, feat: torch.Tensor) -> None:
