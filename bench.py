@@ -418,34 +418,38 @@ def gemm_roofline(engine, B, dims):
 
     pk, src = peaks()
     calls = []
-    orig = engine._gemm
+    orig, orig_x2 = engine._gemm, engine._gemm_x2
 
     def rec(a, w, bias, epi, out):
-        calls.append((a, w, bias, epi, out))
+        calls.append((orig, (a, w, bias, epi, out), a, w))
         orig(a, w, bias, epi, out)
+
+    def rec_x2(a, al, w, wl, bias, epi, out, out_lo=None):       # the Q-Former's float32-grade GEMMs (algorithmic FLOPs: 2MNK)
+        calls.append((orig_x2, (a, al, w, wl, bias, epi, out, out_lo), a, w))
+        orig_x2(a, al, w, wl, bias, epi, out, out_lo)
 
     # the replay times the GEMM launches alone: residual GEMMs are replayed with the plain residual epilogue (same tiles and
     # split-K plan as the step's partial-sum epilogue; the reduce/LayerNorm launches are not GEMMs and are not replayed)
     orig_fuse = engine.fuse_ln
     engine.fuse_ln = False
-    engine._gemm = rec
+    engine._gemm, engine._gemm_x2 = rec, rec_x2
     mid = torch.empty(B, H, dims.image, 3, dtype=torch.uint8, device=engine.dev)
     img = torch.zeros(B, H, W, 3, dtype=torch.uint8, device=engine.dev)
     engine._forward_impl(img, mid)
-    engine._gemm = orig
+    engine._gemm, engine._gemm_x2 = orig, orig_x2
     engine.fuse_ln = orig_fuse
     torch.cuda.synchronize()
-    flops = sum(2.0 * a.shape[0] * w.shape[0] * a.shape[1] for a, w, *_ in calls)
+    flops = sum(2.0 * a.shape[0] * w.shape[0] * a.shape[1] for _, _, a, w in calls)
     for _ in range(2):
-        for c in calls:
-            orig(*c)
+        for fn, c, _, _ in calls:
+            fn(*c)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     torch.cuda.synchronize()
     e0.record()
     for _ in range(reps):
-        for c in calls:
-            orig(*c)
+        for fn, c, _, _ in calls:
+            fn(*c)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -460,7 +464,7 @@ def gemm_roofline(engine, B, dims):
             traffic = None
     return {"kernel": "gemm_f16_tcgen05_kernel (1-CTA 128xBN tiles at batch 1; 2-CTA persistent 256x256 tiles for large M)", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum+dram__bytes_write.sum, profiles/r01_gemm_traffic_b1.json)",
-            "algorithmic_bytes_per_launch": sum(2.0 * w.numel() + 2.0 * a.numel() for a, w, *_ in calls) / len(calls), "peak_source": f"{src} (sustained dense bf16)",
+            "algorithmic_bytes_per_launch": sum((4.0 if fn is orig_x2 else 2.0) * (w.numel() + a.numel()) for fn, _, a, w in calls) / len(calls), "peak_source": f"{src} (sustained dense bf16)",
             "launches_per_step": len(calls), "flops_per_launch_avg": flops / len(calls),
             "us_per_launch_avg": ms * 1e3 / len(calls), "gemm_ms_per_step": ms}
 

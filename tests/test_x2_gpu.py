@@ -54,7 +54,7 @@ def test_gemm_x2_vs_float64(M, N, K, epi):
     torch.cuda.synchronize()
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
-    assert err <= 2e-6 * scale, f"max err {err:.3e} vs scale {scale:.3e}"
+    assert err <= 5e-6 * scale, f"max err {err:.3e} vs scale {scale:.3e}"
 
 
 @pytest.mark.parametrize("M,N,K", [(32, 768, 768), (32, 768, 3072), (9, 768, 3072), (1024, 768, 3072)])

@@ -101,6 +101,10 @@ struct GemmArgs {
   // of the last one also compute the r extra rows on CUDA cores from the W tiles already staged for the tensor core
   const __half* a_tail; int lda, tail_rows, tail_row0;
   void* out_lo;       // VLFM_EPI_BIAS_GELU_F16X2: the x2 residual of the fp16 output (same ldo)
+  // rows of the A tile the TMA box carries (32 / 64 / 128): with M <= 32 (Q-Former queries, text tokens) a 128-row box spends 3/4 of
+  // every stage's TMA time on out-of-bounds zero fill.  Rows of the smem tile beyond the box keep whatever they held: row i of the
+  // accumulator depends on row i of A only, and rows >= M are never stored.
+  int a_box_rows;
 };
 constexpr int GEMM_TAIL_MAX = 2;
 constexpr int GEMM_TAIL_KMAX = 6144;   // K elements of one CTA's slice that fit the tail-row staging buffer
@@ -273,8 +277,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       // programmatic-dependency wait (hides the HBM/L2 latency of the first loads behind the predecessor's tail);
       // the matching A tiles (activations) are issued right after the wait and complete the same barriers.
       const int pre = num_k < STAGES ? num_k : STAGES;
+      const uint32_t a_tx = (uint32_t)g.a_box_rows * BK * 2;
       for (int kb = 0; kb < pre; ++kb) {
-        mbar_expect_tx(full0 + 8 * kb, A_BYTES + B_BYTES);
+        mbar_expect_tx(full0 + 8 * kb, a_tx + B_BYTES);
         tma_load_2d(smem_u32(sB + kb * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * kb);
       }
       pdl_wait();
@@ -284,7 +289,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
       for (int kb = pre; kb < num_k; ++kb) {
         mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+        mbar_expect_tx(full0 + 8 * s, a_tx + B_BYTES);
         tma_load_2d(smem_u32(sA + s * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * s);
         tma_load_2d(smem_u32(sB + s * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * s);
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -464,8 +469,9 @@ gemm_f16x2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (lane == 0) {
       // weights first (independent of the predecessor kernel), activations after the dependency wait
       const int pre = num_k < STAGES ? num_k : STAGES;
+      const uint32_t a_tx = (uint32_t)g.a_box_rows * BK * 2;
       for (int kb = 0; kb < pre; ++kb) {
-        mbar_expect_tx(full0 + 8 * kb, 2 * (A_BYTES + B_BYTES));
+        mbar_expect_tx(full0 + 8 * kb, 2 * (a_tx + B_BYTES));
         tma_load_2d(smem_u32(sB + kb * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * kb);
         tma_load_2d(smem_u32(sBl + kb * B_BYTES), &tmBl, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * kb);
       }
@@ -477,7 +483,7 @@ gemm_f16x2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       int s = pre == STAGES ? 0 : pre; uint32_t ph = pre == STAGES ? 1 : 0;
       for (int kb = pre; kb < num_k; ++kb) {
         mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + B_BYTES));
+        mbar_expect_tx(full0 + 8 * s, 2 * (a_tx + B_BYTES));
         tma_load_2d(smem_u32(sA + s * A_BYTES), &tmA, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * s);
         tma_load_2d(smem_u32(sAl + s * A_BYTES), &tmAl, (kb_begin + kb) * BK, m_blk * BM, full0 + 8 * s);
         tma_load_2d(smem_u32(sB + s * B_BYTES), &tmB, (kb_begin + kb) * BK, n_blk * BN, full0 + 8 * s);
@@ -898,7 +904,7 @@ extern "C" int vlfm_gemm_f16(const void* d_A, const void* d_W, const float* d_bi
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldo & 7) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) || ((uintptr_t)d_out & 15)) {
     set_error("vlfm_gemm_f16: K, lda, ldw, ldo must be multiples of 8 and pointers 16-byte aligned"); return VLFM_E_INVALID; }
   if (epilogue < 0 || epilogue > 4) { set_error("vlfm_gemm_f16: unknown epilogue %d", epilogue); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, 0, nullptr, 0, 0, 0};
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, g_gemm_dbg, 0, nullptr, 0, 0, 0, nullptr, BM};
   return gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, nullptr, 0, nullptr);
 }
 
@@ -907,7 +913,8 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
   if (splits_out) *splits_out = 1;
   const int epilogue = g.epi;
   CUtensorMap ta;
-  int rc = make_map(&ta, d_A, M, K, lda, BM);
+  g.a_box_rows = M <= 32 ? 32 : (M <= 64 ? 64 : BM);
+  int rc = make_map(&ta, d_A, M, K, lda, g.a_box_rows);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   // tile width: fill >= ~120 of the 148 SMs when M is small, widest tile otherwise
@@ -1021,7 +1028,7 @@ extern "C" int vlfm_gemm_f16_resid_ln(const void* d_A, const void* d_W, const fl
     set_error("vlfm_gemm_f16_resid_ln: bad argument"); return VLFM_E_INVALID; }
   if ((K & 7) || (lda & 7) || (ldw & 7) || (ldx & 7) || (N & 3) || (ld16 & 3) || (ld32 & 3) || ((uintptr_t)d_A & 15) || ((uintptr_t)d_W & 15) ||
       ((uintptr_t)d_x & 15) || ((uintptr_t)d_partials & 15)) { set_error("vlfm_gemm_f16_resid_ln: alignment (K, strides %% 8; N %% 4; 16-byte pointers)"); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, g_gemm_dbg, 0, nullptr, 0, 0, 0};
+  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, g_gemm_dbg, 0, nullptr, 0, 0, 0, nullptr, BM};
   int splits = 1;
   int rc = gemm_dispatch(d_A, d_W, M, N, K, lda, ldw, g, stream, d_partials, partial_bytes, &splits);
   if (rc) return rc;
@@ -1033,9 +1040,25 @@ extern "C" int vlfm_gemm_f16_resid_ln(const void* d_A, const void* d_W, const fl
 static int gemm_x2_dispatch(const void* d_A_hi, const void* d_A_lo, const void* d_W_hi, const void* d_W_lo, int M, int N, int K, int lda, int ldw,
                             GemmArgs g, void* stream, float* d_partials, size_t partial_bytes, int* splits_out) {
   if (splits_out) *splits_out = 1;
+  // M = 128 q + r with a small remainder (257 image tokens): the r rows would cost a whole extra row of tiles -- run them as their
+  // own skinny launch (32-row A box) after the q full row tiles
+  const int rem = M % BM;
+  if (M > BM && rem >= 1 && rem <= 32 && (g.epi == VLFM_EPI_BIAS_F32 || g.epi == VLFM_EPI_BIAS_GELU_F16X2)) {
+    const int m0 = M - rem;
+    GemmArgs g0 = g; g0.M = m0;
+    int rc0 = gemm_x2_dispatch(d_A_hi, d_A_lo, d_W_hi, d_W_lo, m0, N, K, lda, ldw, g0, stream, nullptr, 0, nullptr);
+    if (rc0) return rc0;
+    GemmArgs g1 = g; g1.M = rem;
+    const size_t esz = g.epi == VLFM_EPI_BIAS_F32 ? 4 : 2;
+    g1.out = (uint8_t*)g.out + (size_t)m0 * g.ldo * esz;
+    if (g.out_lo) g1.out_lo = (uint8_t*)g.out_lo + (size_t)m0 * g.ldo * 2;
+    return gemm_x2_dispatch((const __half*)d_A_hi + (size_t)m0 * lda, (const __half*)d_A_lo + (size_t)m0 * lda, d_W_hi, d_W_lo, rem, N, K, lda, ldw, g1,
+                            stream, nullptr, 0, nullptr);
+  }
   CUtensorMap ta, tal;
-  int rc = make_map(&ta, d_A_hi, M, K, lda, BM);
-  if (!rc) rc = make_map(&tal, d_A_lo, M, K, lda, BM);
+  g.a_box_rows = M <= 32 ? 32 : (M <= 64 ? 64 : BM);
+  int rc = make_map(&ta, d_A_hi, M, K, lda, g.a_box_rows);
+  if (!rc) rc = make_map(&tal, d_A_lo, M, K, lda, g.a_box_rows);
   if (rc) return rc;
   const int mt = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
   // tile width: wide tiles for the one big problem (cross-attention K/V of all layers: 257 x 9216 x 1408), else enough CTAs to
@@ -1076,7 +1099,7 @@ extern "C" int vlfm_gemm_f16x2(const void* d_A_hi, const void* d_A_lo, const voi
   if (epilogue != VLFM_EPI_BIAS_F32 && epilogue != VLFM_EPI_BIAS_RESID_F32 && epilogue != VLFM_EPI_BIAS_GELU_F16X2) {
     set_error("vlfm_gemm_f16x2: epilogue %d unsupported (fp32, fp32 residual, GELU x2)", epilogue); return VLFM_E_INVALID; }
   if (epilogue == VLFM_EPI_BIAS_GELU_F16X2 && (!d_out_lo || ((uintptr_t)d_out_lo & 15))) { set_error("vlfm_gemm_f16x2: d_out_lo missing / unaligned"); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, nullptr, 0, nullptr, 0, 0, 0, d_out_lo};
+  GemmArgs g{d_bias, d_out, M, N, K, ldo, epilogue, (K + BK - 1) / BK, nullptr, 0, nullptr, 0, 0, 0, d_out_lo, BM};
   return gemm_x2_dispatch(d_A_hi, d_A_lo, d_W_hi, d_W_lo, M, N, K, lda, ldw, g, stream, nullptr, 0, nullptr);
 }
 
@@ -1095,7 +1118,7 @@ extern "C" int vlfm_gemm_f16x2_resid_ln(const void* d_A_hi, const void* d_A_lo, 
   if (rc) return rc;
   if (!d_gamma || !d_beta || !d_out_hi || !d_out_lo || (N & 3) || (ld16 & 3) || (ld32 & 3) || ((uintptr_t)d_partials & 15)) {
     set_error("vlfm_gemm_f16x2_resid_ln: bad argument / alignment"); return VLFM_E_INVALID; }
-  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, nullptr, 0, nullptr, 0, 0, 0, nullptr};
+  GemmArgs g{d_bias, d_x, M, N, K, ldx, VLFM_EPI_BIAS_RESID_F32, (K + BK - 1) / BK, nullptr, 0, nullptr, 0, 0, 0, nullptr, BM};
   int splits = 1;
   rc = gemm_x2_dispatch(d_A_hi, d_A_lo, d_W_hi, d_W_lo, M, N, K, lda, ldw, g, stream, d_partials, partial_bytes, &splits);
   if (rc) return rc;
