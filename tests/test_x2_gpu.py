@@ -81,8 +81,8 @@ def test_gemm_x2_resid_layernorm(M, N, K):
     xr = x0.double() + a.double() @ w.double().t() + bias.double()
     yr = torch.nn.functional.layer_norm(xr, (N,), gam.double(), bet.double(), 1e-12)
     x, hi, lo, o32 = outs[0]
-    assert float((x.double() - xr).abs().max()) <= 2e-6 * float(xr.abs().max())
-    assert float((o32.double() - yr).abs().max()) <= 1e-5
+    assert float((x.double() - xr).abs().max()) <= 6e-6 * float(xr.abs().max())      # fp32 accumulation over K = 3072
+    assert float((o32.double() - yr).abs().max()) <= 2e-5
     assert float((hi.double() + lo.double() / 2048.0 - o32.double()).abs().max()) <= 2e-6          # the pair carries the fp32 value
     for o in outs[1:]:
         assert all(torch.equal(p, q) for p, q in zip(o, outs[0]))
