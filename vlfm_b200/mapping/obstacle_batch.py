@@ -207,7 +207,7 @@ class ObstacleMapBatch:
                 self._graph_seen += 1
             else:
                 self._graph_key, self._graph_seen = key, 0
-            if key is not None and (key in self._graphs or self._graph_seen >= 2):
+            if key is not None and (key in self._graphs or self._graph_seen >= 1):
                 if self._rec_used:
                     self._rec_ev.synchronize()           # the previous replay's record upload has executed
                 rc = self.lib.vlfm_explore_prepare_batch(g, n, self._envs, _lib.ptr(self.explored), _lib.ptr(self.nav), _lib.ptr(self._call_front),
