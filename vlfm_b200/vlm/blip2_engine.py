@@ -51,6 +51,7 @@ class Blip2ITCEngine:
         self.fuse_ln = os.environ.get("VLFM_DET_SPLITK", "1") != "0"
         rows = min(max_batch * dims.tokens, 1024)      # larger problems never split K (2-CTA 256x256 tiles)
         self._partials = torch.empty(8 * rows * max(dims.v_hidden, dims.q_hidden), dtype=F32, device=self.dev)
+        self._fold_layer0()
 
     # ------------------------------------------------------------------ weights ----
     def _load(self, sd: Dict[str, torch.Tensor]) -> None:
@@ -278,8 +279,9 @@ class Blip2ITCEngine:
             else:                       # ... and the post-LayerNorm on the last one
                 self._gemm_resid_ln(hb_, L["fc2_w"], L["fc2_b"], x, self.post_w, self.post_b, img16, self.b_img32[:n] if self.x2 else None, d.v_eps)
         h32, h16 = self.q_h32[:nq], self.q_h16[:nq]
-        h32.view(B, Q, H).copy_(self.q0_32)
-        h16.view(B, Q, H).copy_(self.q0_16)
+        if not (self.x2 and self.fold0):
+            h32.view(B, Q, H).copy_(self.q0_32)
+            h16.view(B, Q, H).copy_(self.q0_16)
         if self.x2:
             # image embeds as x2 operands: hi is the fp16 LayerNorm output itself, lo its residual against the fp32 one
             img_lo = self.b_img_lo[:n]
@@ -287,8 +289,11 @@ class Blip2ITCEngine:
             kv = self.b_kv32[:n]
             self._gemm_x2(img16, img_lo, self.kv_w, self.kv_wl, self.kv_b, _lib.EPI_BIAS_F32, kv)
             hlo = self.q_h_lo[:nq]
-            hlo.view(B, Q, H).copy_(self.q0_lo)
-            self._qformer_layers_x2(h32, h16, hlo, B, Q, kv, T, text=False)
+            if self.fold0:      # only the residual stream needs its start value: hhi / hlo are rewritten by layer 0's cross block
+                h32.copy_(self.f0_32x[:nq])
+            else:
+                hlo.view(B, Q, H).copy_(self.q0_lo)
+            self._qformer_layers_x2(h32, h16, hlo, B, Q, kv, T, text=False, folded=self.fold0)
             self._gemm_x2(h16, hlo, self.vp_w, self.vp_wl, self.vp_b, _lib.EPI_BIAS_F32, self.q_proj[:nq])
         else:
             kv = self.b_kv[:n]
@@ -320,22 +325,55 @@ class Blip2ITCEngine:
             self._gemm(h16, iw, ib, _lib.EPI_BIAS_GELU_F16, ff)
             self._gemm_resid_ln(ff, ow, ob, h32, lw, lb, h16, h32, d.q_eps)
 
-    def _qformer_layers_x2(self, h32, hhi, hlo, B, S, kv, T, text: bool) -> None:
-        """the same layers with x2 operands everywhere and float32 attention (modeling: Blip2QFormerLayer; float32 in the reference)"""
+    def _fold_layer0(self) -> None:
+        """Layer 0's self-attention block sees only LayerNorm(query_tokens): it (and the query projection of layer 0's
+        cross-attention that follows it) is the same for every image -- computed once here with the step's own kernels."""
+        self.fold0 = False
+        if not self.x2:
+            return
+        d = self.d
+        Q, H = d.queries, d.q_hidden
+        hd = H // d.q_heads
+        L = self.qf[0]
+        with torch.cuda.device(self.dev):
+            h32, hhi, hlo = self.q0_32.clone(), self.q0_16.clone(), self.q0_lo.clone()
+            qkv, ahi, alo = self.q_qkv32[:Q], self.q_ao[:Q], self.q_ao_lo[:Q]
+            self._gemm_x2(hhi, hlo, L["qkv_w"], L["qkv_wl"], L["qkv_b"], _lib.EPI_BIAS_F32, qkv)
+            self._attn32(qkv[:, 0:H], qkv[:, H : 2 * H], qkv[:, 2 * H : 3 * H], ahi, alo, 1, d.q_heads, Q, Q, hd, 1.0 / math.sqrt(hd))
+            self._gemm_x2_resid_ln(ahi, alo, L["so_w"], L["so_wl"], L["so_b"], h32, L["sln_w"], L["sln_b"], hhi, hlo, h32, d.q_eps)
+            self.f0_32, self.f0_hi, self.f0_lo = h32, hhi, hlo
+            self.f0_q = None
+            if L["cross"] >= 0:
+                self.f0_q = torch.empty(Q, H, dtype=F32, device=self.dev)
+                self._gemm_x2(hhi, hlo, L["cq_w"], L["cq_wl"], L["cq_b"], _lib.EPI_BIAS_F32, self.f0_q)
+            torch.cuda.synchronize()
+        self.f0_32x = self.f0_32.repeat(self.max_batch, 1)
+        self.f0_qx = self.f0_q.repeat(self.max_batch, 1) if self.f0_q is not None else None
+        self.fold0 = os.environ.get("VLFM_QFORMER_FOLD0", "1") != "0" and L["cross"] >= 0
+
+    def _qformer_layers_x2(self, h32, hhi, hlo, B, S, kv, T, text: bool, folded: bool = False) -> None:
+        """the same layers with x2 operands everywhere and float32 attention (modeling: Blip2QFormerLayer; float32 in the reference).
+        ``folded``: h32 / hhi / hlo already hold layer 0's self-attention block output (``_fold_layer0``)."""
         d = self.d
         H = d.q_hidden
         hd = H // d.q_heads
         n = B * S
         qkv, qq, ahi, alo, fhi, flo = self.q_qkv32[:n], self.q_q32[:n], self.q_ao[:n], self.q_ao_lo[:n], self.q_f[:n], self.q_f_lo[:n]
         sc = 1.0 / math.sqrt(hd)
-        for L in self.qf:
-            self._gemm_x2(hhi, hlo, L["qkv_w"], L["qkv_wl"], L["qkv_b"], _lib.EPI_BIAS_F32, qkv)
-            self._attn32(qkv[:, 0:H], qkv[:, H : 2 * H], qkv[:, 2 * H : 3 * H], ahi, alo, B, d.q_heads, S, S, hd, sc)
-            self._gemm_x2_resid_ln(ahi, alo, L["so_w"], L["so_wl"], L["so_b"], h32, L["sln_w"], L["sln_b"], hhi, hlo, h32, d.q_eps)
+        for li, L in enumerate(self.qf):
+            skip = folded and li == 0
+            if not skip:
+                self._gemm_x2(hhi, hlo, L["qkv_w"], L["qkv_wl"], L["qkv_b"], _lib.EPI_BIAS_F32, qkv)
+                self._attn32(qkv[:, 0:H], qkv[:, H : 2 * H], qkv[:, 2 * H : 3 * H], ahi, alo, B, d.q_heads, S, S, hd, sc)
+                self._gemm_x2_resid_ln(ahi, alo, L["so_w"], L["so_wl"], L["so_b"], h32, L["sln_w"], L["sln_b"], hhi, hlo, h32, d.q_eps)
             if not text and L["cross"] >= 0:
                 j = L["cross"]
-                self._gemm_x2(hhi, hlo, L["cq_w"], L["cq_wl"], L["cq_b"], _lib.EPI_BIAS_F32, qq)
-                self._attn32(qq, kv[:, j * 2 * H : j * 2 * H + H], kv[:, j * 2 * H + H : (j + 1) * 2 * H], ahi, alo, B, d.q_heads, S, T, hd, sc)
+                cq = qq
+                if skip:
+                    cq = self.f0_qx[:n]                  # constant: never written
+                else:
+                    self._gemm_x2(hhi, hlo, L["cq_w"], L["cq_wl"], L["cq_b"], _lib.EPI_BIAS_F32, qq)
+                self._attn32(cq, kv[:, j * 2 * H : j * 2 * H + H], kv[:, j * 2 * H + H : (j + 1) * 2 * H], ahi, alo, B, d.q_heads, S, T, hd, sc)
                 self._gemm_x2_resid_ln(ahi, alo, L["co_w"], L["co_wl"], L["co_b"], h32, L["cln_w"], L["cln_b"], hhi, hlo, h32, d.q_eps)
             k1, k2, kl = ("it", "ot", "otln") if text else ("iq", "oq", "oqln")
             self._gemm_x2(hhi, hlo, L[k1 + "_w"], L[k1 + "_wl"], L[k1 + "_b"], _lib.EPI_BIAS_GELU_F16X2, fhi, flo)
