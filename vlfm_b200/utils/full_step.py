@@ -92,7 +92,8 @@ class FullStep:
             self.n_front += len(px)
             if len(px):
                 xy = self.omb.px_to_xy(px)                     # ObstacleMap.frontiers (metres) ...
-                q = self.omb.xy_to_px(xy[:, :2])                # ... and back to cells, as the policy does through sort_waypoints
+                with np.errstate(invalid="ignore"):             # a zero-length frontier piece has a NaN midpoint (0/0), as in the reference
+                    q = self.omb.xy_to_px(xy[:, :2])            # ... and back to cells, as the policy does through sort_waypoints
                 pts.append(np.stack([np.full(len(q), e), q[:, 1], q[:, 0]], axis=1))
         if pts:
             self.vmb.disc_median_batch(np.concatenate(pts), int(0.5 * self.ppm))
