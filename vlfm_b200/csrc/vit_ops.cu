@@ -145,94 +145,69 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // per thread), the partial sums of up to four splits are loaded before the first add: with a warp per row and a runtime loop
 // over the splits (first version) the kernel paid one L2 round trip per split (9.5 us for 8 splits at 257 x 1408; the
 // deterministic forward was 12 % slower than the red.add one).  The adds stay in split order -> bitwise reproducible.
-template <int V4>
-__global__ void __launch_bounds__(128)
+// One float4 per thread, D/4 threads per row (<= 384): 11 warps per 1408-wide row keep ~20 warps per SM in flight (the 128-thread
+// version ran at 10 % occupancy, 6.5-8.5 us per launch, 78 launches per ViT forward).
+__global__ void __launch_bounds__(384)
 layernorm_reduce_kernel(float* x, const float* __restrict__ partials, int splits, long long split_stride,
                         const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out16,
                         float* out32, int rows, int D, int ldx, int ldo16, int ldo32, float eps, __half* __restrict__ out16_lo) {   // out32 may alias x (post-LN blocks)
   pdl_trigger();
-  __shared__ float red[2][4];
-  const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  __shared__ float red[2][12];
+  const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
   const int D4 = D >> 2;
-  float4 g[V4], bt[V4], v[V4];
-#pragma unroll
-  for (int i = 0; i < V4; ++i) {   // parameters do not depend on the predecessor kernel
-    const int j = t + 128 * i;
-    g[i] = j < D4 ? __ldg(reinterpret_cast<const float4*>(gamma) + j) : make_float4(0, 0, 0, 0);
-    bt[i] = j < D4 ? __ldg(reinterpret_cast<const float4*>(beta) + j) : make_float4(0, 0, 0, 0);
-  }
+  const bool on = t < D4;
+  const float4 g = on ? __ldg(reinterpret_cast<const float4*>(gamma) + t) : make_float4(0, 0, 0, 0);   // parameters do not depend on
+  const float4 bt = on ? __ldg(reinterpret_cast<const float4*>(beta) + t) : make_float4(0, 0, 0, 0);   // the predecessor kernel
   pdl_wait();
   float4* xr = reinterpret_cast<float4*>(x + (size_t)row * ldx);
-#pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    const int j = t + 128 * i;
-    v[i] = j < D4 ? xr[j] : make_float4(0, 0, 0, 0);
-  }
+  float4 v = on ? xr[t] : make_float4(0, 0, 0, 0);
   for (int sp0 = 0; sp0 < splits; sp0 += 4) {
-    float4 pv[4][V4];
+    float4 pv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float4* pr = reinterpret_cast<const float4*>(partials + (size_t)(sp0 + u) * (size_t)split_stride + (size_t)row * D);
-#pragma unroll
-      for (int i = 0; i < V4; ++i) {
-        const int j = t + 128 * i;
-        pv[u][i] = (sp0 + u < splits && j < D4) ? __ldcg(pr + j) : make_float4(0, 0, 0, 0);
-      }
+      pv[u] = (sp0 + u < splits && on) ? __ldcg(pr + t) : make_float4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {          // fixed order: bitwise reproducible
-      if (sp0 + u < splits) {
-#pragma unroll
-        for (int i = 0; i < V4; ++i) { v[i].x += pv[u][i].x; v[i].y += pv[u][i].y; v[i].z += pv[u][i].z; v[i].w += pv[u][i].w; }
-      }
-    }
+    for (int u = 0; u < 4; ++u)          // fixed order: bitwise reproducible
+      if (sp0 + u < splits) { v.x += pv[u].x; v.y += pv[u].y; v.z += pv[u].z; v.w += pv[u].w; }
   }
   float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    const int j = t + 128 * i;
-    if (j < D4) { xr[j] = v[i]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
-  }
+  if (on) { xr[t] = v; s = (v.x + v.y) + (v.z + v.w); }
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) red[0][w] = s;
   __syncthreads();
-  const float mean = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / (float)D;
+  float tot = 0.f;
+  for (int i = 0; i < nw; ++i) tot += red[0][i];          // same order in every thread
+  const float mean = tot / (float)D;
   float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    if (t + 128 * i < D4) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  }
+  if (on) { const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean; q = (a * a + b * b) + (c * c + d * d); }
 #pragma unroll
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   if (lane == 0) red[1][w] = q;
   __syncthreads();
-  const float rstd = rsqrtf(((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) / (float)D + eps);
-#pragma unroll
-  for (int i = 0; i < V4; ++i) {
-    const int j = t + 128 * i;
-    if (j < D4) {
-      float4 y;
-      y.x = (v[i].x - mean) * rstd * g[i].x + bt[i].x;
-      y.y = (v[i].y - mean) * rstd * g[i].y + bt[i].y;
-      y.z = (v[i].z - mean) * rstd * g[i].z + bt[i].z;
-      y.w = (v[i].w - mean) * rstd * g[i].w + bt[i].w;
-      if (out16) {
-        __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
-        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-        *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + 4 * j) = pk;
-        if (out16_lo) {
-          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-          __half2 l0 = __floats2half2_rn((y.x - f0.x) * X2_SCALE, (y.y - f0.y) * X2_SCALE), l1 = __floats2half2_rn((y.z - f1.x) * X2_SCALE, (y.w - f1.y) * X2_SCALE);
-          uint2 pl = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
-          *reinterpret_cast<uint2*>(out16_lo + (size_t)row * ldo16 + 4 * j) = pl;
-        }
+  float qt = 0.f;
+  for (int i = 0; i < nw; ++i) qt += red[1][i];
+  const float rstd = rsqrtf(qt / (float)D + eps);
+  if (on) {
+    float4 y;
+    y.x = (v.x - mean) * rstd * g.x + bt.x;
+    y.y = (v.y - mean) * rstd * g.y + bt.y;
+    y.z = (v.z - mean) * rstd * g.z + bt.z;
+    y.w = (v.w - mean) * rstd * g.w + bt.w;
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(out16 + (size_t)row * ldo16 + 4 * t) = pk;
+      if (out16_lo) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        __half2 l0 = __floats2half2_rn((y.x - f0.x) * X2_SCALE, (y.y - f0.y) * X2_SCALE), l1 = __floats2half2_rn((y.z - f1.x) * X2_SCALE, (y.w - f1.y) * X2_SCALE);
+        uint2 pl = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+        *reinterpret_cast<uint2*>(out16_lo + (size_t)row * ldo16 + 4 * t) = pl;
       }
-      if (out32) *reinterpret_cast<float4*>(out32 + (size_t)row * ldo32 + 4 * j) = y;
     }
+    if (out32) *reinterpret_cast<float4*>(out32 + (size_t)row * ldo32 + 4 * t) = y;
   }
 }
 
@@ -678,9 +653,9 @@ static int layernorm_reduce_impl(float* d_x, const float* d_partials, int splits
   const dim3 grid(rows);
   __half* o16 = (__half*)d_out16;
   cudaError_t e;
-  if (D <= 512 * 2) e = launch_pdl(layernorm_reduce_kernel<2>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
-  else if (D <= 512 * 3) e = launch_pdl(layernorm_reduce_kernel<3>, grid, dim3(128), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
-  else { set_error("vlfm_layernorm_reduce: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
+  if (D > 1536) { set_error("vlfm_layernorm_reduce: D=%d too large (max 1536)", D); return VLFM_E_UNSUPPORTED; }
+  const int threads = (((D >> 2) + 31) / 32) * 32;
+  e = launch_pdl(layernorm_reduce_kernel, grid, dim3(threads), 0, st, d_x, d_partials, splits, split_stride, d_gamma, d_beta, o16, d_out32, rows, D, ldx, ldo16, ldo32, eps, lo16);
   { int rc = check_cuda(e, "layernorm_reduce_kernel"); if (rc) return rc; }
   count_launch();
   return VLFM_OK;
