@@ -377,7 +377,7 @@ def run_extras(args, dev, world, rank, sd, dims, itm32):
     except Exception as e:
         out["gdino_error"] = repr(e)
 
-    def full(name, workload, B, h, w, g, ppm, steps, warm, bound):
+    def full(name, workload, B, h, w, g, ppm, steps, warm, bound, release=True):
         # warm >= 3: the map update is captured into a CUDA graph on its third call with the same buffers (ObstacleMapBatch.update)
         try:
             fs = FullStep(dev, B, h, w, g, ppm, itm, gd, frames_per_env=steps + warm, seed0=2000 + rank * B, bound_m=bound)
@@ -391,15 +391,16 @@ def run_extras(args, dev, world, rank, sd, dims, itm32):
             del fs
         except Exception as e:
             out[name] = {"workload": workload, "error": repr(e)}
-        torch.cuda.empty_cache()
+        if release:        # hand the cached blocks back only when the next workload has different shapes: re-growing the detector's
+            torch.cuda.empty_cache()   # temporaries costs cudaMalloc calls inside the next workload's first steps
 
     full("configs2_full_step", f"configs[2]: full step (GroundingDINO + BLIP-2 ITC + Obstacle/Value/Frontier update), batch={EB} envs/GPU, 640x480 RGB-D, 1000^2 grid",
-         EB, H, W, 1000, 20, 4, 3, 15.0)
+         EB, H, W, 1000, 20, 4, 3, 15.0, release=False)
     full("configs3_slice", f"configs[3] slice: full step, {EB} envs/GPU (256 envs = 32/GPU x 8), 640x480 RGB-D, 2000^2 x 0.05 m grid",
-         EB, H, W, 2000, 20, 3, 3, 30.0)
+         EB, H, W, 2000, 20, 4, 4, 30.0)
     b4 = max(1, EB // 4)
     full("configs4_slice", f"configs[4] slice: full step, {b4} envs/GPU (64 envs on 8 GPUs), 1024x1024 RGB-D, ViT-g at 224 (reference semantics), 4000^2 x 0.025 m grid",
-         b4, 1024, 1024, 4000, 40, 3, 3, 30.0)
+         b4, 1024, 1024, 4000, 40, 4, 4, 30.0)
     names = ["configs1_b%d" % EB, "configs2_full_step", "configs3_slice", "configs4_slice"]
     for nme in names:
         ent = out.get(nme, {})
