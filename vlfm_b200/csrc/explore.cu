@@ -187,13 +187,30 @@ __global__ void ccl_merge2_kernel(const ExEnv* __restrict__ envs, int id, int wa
     }
   }
 }
+// Every cell of a horizontal run still points at the run's first cell (only roots are ever re-linked), so the cells of a run
+// would all walk the same parent chain: the lanes of a warp that share a parent elect one walker (__match_any_sync) and take its
+// answer.  32 consecutive cells are usually one or two runs -- the walks drop by an order of magnitude.
 __global__ void ccl_flatten2_kernel(const ExEnv* __restrict__ envs, int id) {
   const ExEnv& E = envs[blockIdx.y];
   const View v = view(E, id);
   int* Lfg = E.Lfg; int* Lbg = E.Lbg;
   const int n = v.W * v.H;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (Lfg[i] >= 0) Lfg[i] = uf_find(Lfg, i); else Lbg[i] = uf_find(Lbg, i);
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {      // warp-uniform trip count
+    const int i = i0 + lane;
+    const bool in = i < n;
+    int lf = -1, parent = -1;
+    if (in) { lf = Lfg[i]; parent = lf >= 0 ? lf : Lbg[i]; }
+    const bool fg = lf >= 0;
+    // key: parent cell, foreground / background arrays apart; lanes past the end get private keys
+    const int key = in ? (fg ? parent : parent + n) : -1 - lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    int root = 0;
+    if (in && lane == leader) root = uf_find(fg ? Lfg : Lbg, parent);
+    root = __shfl_sync(0xffffffffu, root, leader);
+    if (in) { if (fg) Lfg[i] = root; else Lbg[i] = root; }
   }
 }
 // background components touching the image frame are the "outer" background (the frame is background for Suzuki).
@@ -339,32 +356,47 @@ __device__ __forceinline__ bool simple_vertex(const int2* p, int n, int i) {
   return (b.x - a.x != c.x - b.x) || (b.y - a.y != c.y - b.y);
 }
 
-// cv2.pointPolygonTest(cnt, pt, True) on the SIMPLE vertices (oracle/contours.py::point_polygon_distance)
-__device__ double ppt_distance(const int2* p, int n, int ptx, int pty) {
+// cv2.pointPolygonTest(cnt, pt, True) on the SIMPLE vertices (oracle/contours.py::point_polygon_distance): float32 vertices, double
+// arithmetic, first strictly smaller squared distance wins, crossing parity gives the sign.  One WARP per contour: lane L scans the L-th contiguous chunk of the chain with the sequential rule (first
+// strictly smaller squared distance wins), the 32 chunk results are then combined in chunk order with the same comparison, the
+// crossing counts add up.  A vertex ON the point (distance 0) ends the sequential scan with +-0: any lane finding one decides.
+__device__ double ppt_distance_warp(const int2* p, int n, int ptx, int pty, int lane) {
   if (n == 0) return -1.7976931348623157e308;
   const float px = (float)ptx, py = (float)pty;
-  int last = -1;
-  for (int i = n - 1; i >= 0; --i) if (simple_vertex(p, n, i)) { last = i; break; }
-  if (last < 0) last = n - 1;
-  float vx = (float)p[last].x, vy = (float)p[last].y;
+  const int chunk = (n + 31) >> 5;
+  const int c0 = min(n, lane * chunk), c1 = min(n, c0 + chunk);
   double min_num = 3.4028234663852886e38, min_den = 1.0;
-  int counter = 0;
-  for (int i = 0; i < n; ++i) {
-    if (!simple_vertex(p, n, i)) continue;
-    const float v0x = vx, v0y = vy;
-    vx = (float)p[i].x; vy = (float)p[i].y;
-    const double dx = vx - v0x, dy = vy - v0y, dx1 = px - v0x, dy1 = py - v0y, dx2 = px - vx, dy2 = py - vy;
-    double num, den = 1.0;
-    if (dx1 * dx + dy1 * dy <= 0) num = dx1 * dx1 + dy1 * dy1;
-    else if (dx2 * dx + dy2 * dy >= 0) num = dx2 * dx2 + dy2 * dy2;
-    else { num = dy1 * dx - dx1 * dy; num *= num; den = dx * dx + dy * dy; }
-    if (num * min_den < min_num * den) { min_num = num; min_den = den; if (min_num == 0) break; }
-    if ((v0y <= py && vy <= py) || (v0y > py && vy > py)) continue;
-    double cr = dy1 * dx - dx1 * dy;
-    if (dy < 0) cr = -cr;
-    counter += cr > 0;
+  int counter = 0, zero = 0;
+  if (c0 < c1) {
+    int last = -1;                                     // the simple vertex preceding this chunk (cyclically)
+    for (int k = 1; k <= n; ++k) { const int i = c0 - k < 0 ? c0 - k + n : c0 - k; if (simple_vertex(p, n, i)) { last = i; break; } }
+    if (last < 0) last = n - 1;
+    float vx = (float)p[last].x, vy = (float)p[last].y;
+    for (int i = c0; i < c1; ++i) {
+      if (!simple_vertex(p, n, i)) continue;
+      const float v0x = vx, v0y = vy;
+      vx = (float)p[i].x; vy = (float)p[i].y;
+      const double dx = vx - v0x, dy = vy - v0y, dx1 = px - v0x, dy1 = py - v0y, dx2 = px - vx, dy2 = py - vy;
+      double num, den = 1.0;
+      if (dx1 * dx + dy1 * dy <= 0) num = dx1 * dx1 + dy1 * dy1;
+      else if (dx2 * dx + dy2 * dy >= 0) num = dx2 * dx2 + dy2 * dy2;
+      else { num = dy1 * dx - dx1 * dy; num *= num; den = dx * dx + dy * dy; }
+      if (num * min_den < min_num * den) { min_num = num; min_den = den; if (min_num == 0) { zero = 1; break; } }
+      if ((v0y <= py && vy <= py) || (v0y > py && vy > py)) continue;
+      double cr = dy1 * dx - dx1 * dy;
+      if (dy < 0) cr = -cr;
+      counter += cr > 0;
+    }
   }
-  const double r = sqrt(min_num / min_den);
+  if (__any_sync(0xffffffffu, zero)) return 0.0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) counter += __shfl_xor_sync(0xffffffffu, counter, o);
+  double bn = __shfl_sync(0xffffffffu, min_num, 0), bd = __shfl_sync(0xffffffffu, min_den, 0);
+  for (int l = 1; l < 32; ++l) {                        // chunk order, the sequential comparison
+    const double num = __shfl_sync(0xffffffffu, min_num, l), den = __shfl_sync(0xffffffffu, min_den, l);
+    if (num * bd < bn * den) { bn = num; bd = den; }
+  }
+  const double r = sqrt(bn / bd);
   return (counter & 1) ? r : -r;
 }
 
@@ -776,8 +808,11 @@ __global__ void contour_dist_kernel(const ExEnv* __restrict__ envs, int what) {
   const int nc = E.st->n_cont;
   if (what == 1 && nc <= 1) return;
   const int px = what == 0 ? E.sx : E.ax - E.fx0, py = what == 0 ? E.sy : E.ay - E.fy0;
-  for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < nc; ci += gridDim.x * blockDim.x)
-    E.dist[ci] = ppt_distance(E.chain + E.cont[ci].off, E.cont[ci].len, px, py);
+  const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < nc; ci += nw) {
+    const double d = ppt_distance_warp(E.chain + E.cont[ci].off, E.cont[ci].len, px, py, lane);
+    if (lane == 0) E.dist[ci] = d;
+  }
 }
 __global__ void contour_pick_kernel(const ExEnv* __restrict__ envs, int what) {
   const ExEnv& E = envs[blockIdx.y];
