@@ -960,8 +960,10 @@ static int gemm_dispatch(const void* d_A, const void* d_W, int M, int N, int K, 
       // 1 % slower inside the forward (weights from HBM): opt-in only
       if (bn == 96 && (!use_tail || !bn96)) continue;
       int smax = (epilogue == VLFM_EPI_BIAS_RESID_F32) ? num_k / 4 : 1;
+      static int smax_cap = -1;
+      if (smax_cap < 0) { const char* e = getenv("VLFM_GEMM_SMAX"); smax_cap = e ? atoi(e) : 8; if (smax_cap < 1 || smax_cap > 8) smax_cap = 8; }
       if (smax < 1) smax = 1;
-      if (smax > 8) smax = 8;
+      if (smax > smax_cap) smax = smax_cap;
       for (int sp = 1; sp <= smax; ++sp) {
         const double ctas = (double)mte * nt * sp;
         const int kb = (num_k + sp - 1) / sp;
