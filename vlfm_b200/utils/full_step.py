@@ -56,52 +56,83 @@ class FullStep:
         self.acc = {k: 0.0 for k in self.names}
         self.n_front = 0
         self.nf = nf
-        self.serial = os.environ.get("VLFM_FULLSTEP_SERIAL", "0") == "1"     # diagnostic: device sync after every component
+        self.serial = os.environ.get("VLFM_FULLSTEP_SERIAL", "0") == "1"     # one stream, device sync after every component
+        self._streams = None
 
     def step(self, i: int, timed: bool) -> None:
+        """One policy step.  The detector, the ITC model and the obstacle / explore update consume the same uploaded frame and do not
+        depend on each other (base_objectnav_policy.py:153-241 calls them one after the other because each call is a blocking HTTP /
+        numpy round trip): they are issued on three streams and joined before the value-map fuse (needs the cosine) and the
+        frontier scoring (needs both maps).  VLFM_FULLSTEP_SERIAL=1 issues them back to back on one stream."""
         i %= self.nf
         B = self.B
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.names) + 1)]
         main = torch.cuda.current_stream()
-        ev[0].record()
+        E = lambda: torch.cuda.Event(enable_timing=True)
+        e_in0, e_in1 = E(), E()
+        e_in0.record()
         self.rgb_dev.copy_(self.rgb_pin[i], non_blocking=True)
         self.depth_dev.copy_(self.depth_pin[i], non_blocking=True)
         self.tf_dev.copy_(self.tf_pin[i], non_blocking=True)
-        ev[1].record()
-        if self.serial: torch.cuda.synchronize()
-        if self.gd is not None:
+        e_in1.record()
+        conc = not self.serial
+        if conc and self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
+        s_det, s_itc, s_map = self._streams if conc else (main, main, main)
+        spans = {}
+
+        def on(stream, name, fn):
+            with torch.cuda.stream(stream):
+                if conc:
+                    stream.wait_event(e_in1)
+                a, b = E(), E()
+                a.record()
+                out = fn()
+                b.record()
+                spans[name] = (a, b)
+                if self.serial:
+                    torch.cuda.synchronize()
+            return out
+
+        def detect():
+            if self.gd is None:
+                return None
             logits, boxes = self.gd.raw_outputs_device(self.rgb_dev, self.ids)
-            keep = logits.max(dim=2)[0] > self.gd.box_threshold    # compaction mask stays on the device
-            _ = keep.sum()
-        ev[2].record()
-        if self.serial: torch.cuda.synchronize()
-        cos = self.itm.cosine_device(self.rgb_dev, PROMPT)
-        ev[3].record()
-        if self.serial: torch.cuda.synchronize()
+            keep = logits.max(dim=2)[0] > self.gd.box_threshold        # compaction mask stays on the device
+            return keep.sum()
+
+        det = on(s_det, "gdino", detect)
+        cos = on(s_itc, "itc", lambda: self.itm.cosine_device(self.rgb_dev, PROMPT))
         # all environments' obstacle + explore update: ONE launch sequence (hole fill, scatter, dilate, fog-of-war, frontiers)
-        self.omb.update(self.depth_dev, self.tf_host[i], self.tf_dev, MIN_D, MAX_D, self.fx, self.fx, FOV)
-        ev[4].record()
-        if self.serial: torch.cuda.synchronize()
-        self.vmb.update(cos.double().view(B, 1), self.depth_dev, self.tf_dev.view(B, 4, 4), MIN_D, MAX_D, FOV)
-        ev[5].record()
-        if self.serial: torch.cuda.synchronize()
-        # ITMPolicy._sort_frontiers_by_value for every environment: one D2H of the frontier lists, one disc-median launch, one D2H
-        fronts = self.omb.all_frontiers_px(B)
-        pts = []
-        for e, px in enumerate(fronts):
-            self.n_front += len(px)
-            if len(px):
-                xy = self.omb.px_to_xy(px)                     # ObstacleMap.frontiers (metres) ...
-                with np.errstate(invalid="ignore"):             # a zero-length frontier piece has a NaN midpoint (0/0), as in the reference
-                    q = self.omb.xy_to_px(xy[:, :2])            # ... and back to cells, as the policy does through sort_waypoints
-                pts.append(np.stack([np.full(len(q), e), q[:, 1], q[:, 0]], axis=1))
-        if pts:
-            self.vmb.disc_median_batch(np.concatenate(pts), int(0.5 * self.ppm))
-        ev[6].record()
+        on(s_map, "obstacle+explore", lambda: self.omb.update(self.depth_dev, self.tf_host[i], self.tf_dev, MIN_D, MAX_D, self.fx, self.fx, FOV))
+        if conc:
+            main.wait_event(spans["itc"][1])
+        on(main, "value_fuse", lambda: self.vmb.update(cos.double().view(B, 1), self.depth_dev, self.tf_dev.view(B, 4, 4), MIN_D, MAX_D, FOV))
+        if conc:
+            main.wait_event(spans["obstacle+explore"][1])
+
+        def score():
+            # ITMPolicy._sort_frontiers_by_value for every environment: one D2H of the frontier lists, one disc-median launch, one D2H
+            fronts = self.omb.all_frontiers_px(B)
+            pts = []
+            for e, px in enumerate(fronts):
+                self.n_front += len(px)
+                if len(px):
+                    xy = self.omb.px_to_xy(px)                     # ObstacleMap.frontiers (metres) ...
+                    with np.errstate(invalid="ignore"):             # a zero-length frontier piece has a NaN midpoint (0/0), as in the reference
+                        q = self.omb.xy_to_px(xy[:, :2])            # ... and back to cells, as the policy does through sort_waypoints
+                    pts.append(np.stack([np.full(len(q), e), q[:, 1], q[:, 0]], axis=1))
+            if pts:
+                self.vmb.disc_median_batch(np.concatenate(pts), int(0.5 * self.ppm))
+
+        on(main, "frontier_scoring", score)
+        if conc:
+            main.wait_event(spans["gdino"][1])
         torch.cuda.synchronize()
+        _ = det
         if timed:
-            for k, nme in enumerate(self.names):
-                self.acc[nme] += ev[k].elapsed_time(ev[k + 1])
+            self.acc["h2d"] += e_in0.elapsed_time(e_in1)
+            for nme, (a, b) in spans.items():
+                self.acc[nme] += a.elapsed_time(b)
 
     def run(self, steps: int, warmup: int) -> Dict[str, Any]:
         for i in range(warmup):
@@ -123,7 +154,8 @@ class FullStep:
         comp = {k: v / steps for k, v in self.acc.items()}
         gb = grid_bytes(self.H, self.W, self.G, self.ppm)
         return {"env_steps_per_s": self.B * steps / wall, "ms_per_step": 1e3 * wall / steps, "wall_s": wall, "steps": steps, "warmup": warmup,
-                "batch": self.B, "component_ms_per_step": comp, "frontiers_per_env_step": self.n_front / (self.B * steps),
+                "batch": self.B, "component_ms_per_step": comp,
+                "component_note": "CUDA-event spans; gdino / itc / obstacle+explore run on three streams and OVERLAP (their sum exceeds the step)" if not self.serial else "serial: one stream", "frontiers_per_env_step": self.n_front / (self.B * steps),
                 "grid_bytes_per_env_step": gb}
 
     def grid_rooflines(self, hbm_gbs: float, reps: int = 6) -> Dict[str, Any]:
