@@ -384,7 +384,7 @@ def run_extras(args, dev, world, rank, sd, dims, itm32):
             r = fs.run(steps, warm)
             roofs = fs.grid_rooflines(hbm)
             out[name] = {"workload": workload, "value": agg(B, steps, r["wall_s"]), "unit": "env-steps/s", "ms_per_step": r["ms_per_step"],
-                         "steps": steps, "warmup": warm, "envs_per_gpu": B, "component_ms_per_step": r["component_ms_per_step"],
+                         "steps": steps, "warmup": warm, "envs_per_gpu": B, "component_ms_per_step": r["component_ms_per_step"], "component_note": r.get("component_note"),
                          "frontiers_per_env_step": r["frontiers_per_env_step"], "grid_bytes_per_env_step": r["grid_bytes_per_env_step"],
                          "grid_rooflines": roofs,
                          "timing": "host wall clock around whole steps (H2D of the page-locked RGB-D batch and D2H of the frontier lists inside), max over ranks; components by CUDA events"}
