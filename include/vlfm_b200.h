@@ -283,6 +283,10 @@ int vlfm_im2col3x3s2(const float* d_x, void* d_col16, int B, int h, int w, int C
 int vlfm_mask_rows_f16(const float* d_x, const uint8_t* d_valid, void* d_out16, long rows, int D, void* stream);
 int vlfm_proposal_scores(const float* d_q, const float* d_text, int B, int S, int T, int D, float* d_scores, void* stream);
 int vlfm_topk_rows(const float* d_scores, int B, int S, int k, long long* d_idx, void* stream);
+/* decoder_query_pos: per decoder layer, reference_points_input [B,nq,L,4] = ref * (valid ratio pairs) and the sine embedding of its
+ * level-0 slice (GroundingDinoDecoder.forward + get_sine_pos_embed) as the fp16 operand [B*nq, 4*P] of reference_points_head. */
+int vlfm_decoder_query_pos(const float* d_ref, const float* d_valid_ratios, const float* d_dim_t, int B, int nq, int L, int P,
+                           float* d_ref_in, void* d_embed16, void* stream);
 int vlfm_gather_rows(const float* d_src, const long long* d_idx, int B, int S, int K, int C, float* d_dst, void* stream);
 int vlfm_box_finish(const float* d_delta, const float* d_ref, float* d_out, long n, void* stream);
 int vlfm_contrastive_sigmoid(const float* d_hs, const float* d_text, int B, int Q, int T, int D, int L, float* d_out, void* stream);

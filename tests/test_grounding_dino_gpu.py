@@ -326,7 +326,7 @@ def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
             ref_l, ref_b = (t.cpu().float() for t in orc.raw_outputs(img, ids))
             ref_p = cap["ref"]
             got_l, got_b = (t.cpu().float() for t in g.raw_outputs(img, ids))
-            got_p = cap["got"]
+            got_p = g.fwd.last_reference_points[0].detach().float().cpu() if g.fwd is not None else cap["got"]   # own forward keeps its own
             per_l, per_b = (t.cpu().float() for t in orc.raw_outputs(img, ids, input_noise=EPS16, noise_seed=seed))
             per_p = cap["ref"]
             box_thr = float(ref_l.max(dim=1)[0].quantile(0.5))
@@ -413,6 +413,18 @@ def test_head_kernels_vs_torch():
         assert torch.equal(bi[r], torch.argsort(ks)[:900])
     gat = ops.gather_rows(q.view(B, Sq, 256), idx)
     assert torch.equal(gat, torch.gather(q.view(B, Sq, 256), 1, idx.unsqueeze(-1).repeat(1, 1, 256)))
+    # decoder query positions: reference_points_input and the sine embedding operand, against the module code's expressions
+    from transformers.models.grounding_dino.modeling_grounding_dino import get_sine_pos_embed
+
+    rp = torch.rand(B, 900, 4, generator=g).cuda()
+    vr = (0.7 + 0.3 * torch.rand(B, 4, 2, generator=g)).cuda()
+    dim_t = (10000 ** (2 * torch.div(torch.arange(128, dtype=torch.float32), 2, rounding_mode="floor") / 128)).cuda()
+    rin, emb = ops.decoder_query_pos(rp, vr, dim_t)
+    rin_ref = rp[:, :, None] * torch.cat([vr, vr], -1)[:, None]
+    assert torch.equal(rin, rin_ref)
+    emb_ref = get_sine_pos_embed(rin_ref[:, :, 0, :], num_pos_feats=128).reshape(B * 900, 512)
+    assert float((emb.float() - emb_ref.half().float()).abs().max()) <= 1e-3          # sinf / cosf of the same float32 argument, then fp16
+    assert float((emb.float() - emb_ref).abs().max()) <= 1e-3
     # heads
     delta, refp = torch.randn(B, 900, 4, generator=g).cuda(), torch.rand(B, 900, 4, generator=g).cuda()
     refp[0, 0] = torch.tensor([0.0, 1.0, 0.5, 1e-7])

@@ -200,6 +200,34 @@ topk_select_kernel(const float* __restrict__ scores, int S, int P, int k, long l
   for (int i = threadIdx.x; i < k; i += 1024) idx_out[(size_t)blockIdx.x * k + i] = (long long)(0xffffffffu - (unsigned)(s_keys[i] & 0xffffffffull));
 }
 
+// ------------------------------------------------------------------------- decoder query positions ----
+// GroundingDinoDecoder.forward, per layer:  reference_points_input = ref[:, :, None] * cat([valid_ratios, valid_ratios], -1)[:, None]
+// and get_sine_pos_embed(reference_points_input[:, :, 0, :], num_pos_feats = P): for every coordinate c and j < P
+//   v = c * 2*pi / dim_t[j];  e[j] = j even ? sin(v) : cos(v);   output order (y, x, w, h) x P  (exchange_xy).
+// One launch instead of ~30 elementwise ones (mul, div, pow, sin, cos, stack, cat per coordinate).  IEEE mul / div in the
+// reference's order, sinf / cosf as torch's CUDA kernels use them; dim_t is computed by the caller with the reference's own expression.
+__global__ void __launch_bounds__(128)
+decoder_query_pos_kernel(const float* __restrict__ ref, const float* __restrict__ vr, const float* __restrict__ dim_t, int nq, int L, int P,
+                         float* __restrict__ ref_in, __half* __restrict__ embed) {
+  const int row = blockIdx.x, b = row / nq;
+  const float4 r = *reinterpret_cast<const float4*>(ref + (size_t)row * 4);
+  const float* v = vr + (size_t)b * L * 2;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const float vx = v[2 * l], vy = v[2 * l + 1];
+    *reinterpret_cast<float4*>(ref_in + ((size_t)row * L + l) * 4) = make_float4(__fmul_rn(r.x, vx), __fmul_rn(r.y, vy), __fmul_rn(r.z, vx), __fmul_rn(r.w, vy));
+  }
+  const float c[4] = {__fmul_rn(r.y, v[1]), __fmul_rn(r.x, v[0]), __fmul_rn(r.z, v[0]), __fmul_rn(r.w, v[1])};   // (y, x, w, h) of level 0
+  __half* e = embed + (size_t)row * 4 * P;
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    const float dt = dim_t[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = __fdiv_rn(__fmul_rn(c[k], 6.283185307179586f), dt);
+      e[k * P + j] = __float2half_rn((j & 1) ? cosf(a) : sinf(a));
+    }
+  }
+}
+
 // dst[b, i, :] = src[b, idx[b, i], :]
 __global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, int S, int K, int C, float* __restrict__ dst) {
   const int b = blockIdx.y;
@@ -317,6 +345,16 @@ extern "C" int vlfm_topk_rows(const float* d_scores, int B, int S, int k, long l
   }
   topk_rows_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(d_scores, S, P, k, d_idx);
   VLFM_CHECK_LAUNCH("topk_rows_kernel");
+  count_launch();
+  return VLFM_OK;
+}
+
+extern "C" int vlfm_decoder_query_pos(const float* d_ref, const float* d_valid_ratios, const float* d_dim_t, int B, int nq, int L, int P,
+                                      float* d_ref_in, void* d_embed16, void* stream) {
+  if (!d_ref || !d_valid_ratios || !d_dim_t || !d_ref_in || !d_embed16 || B < 1 || nq < 1 || L < 1 || P < 1 || ((uintptr_t)d_ref & 15) || ((uintptr_t)d_ref_in & 15)) {
+    set_error("vlfm_decoder_query_pos: bad argument"); return VLFM_E_INVALID; }
+  decoder_query_pos_kernel<<<B * nq, 128, 0, (cudaStream_t)stream>>>(d_ref, d_valid_ratios, d_dim_t, nq, L, P, d_ref_in, (__half*)d_embed16);
+  VLFM_CHECK_LAUNCH("decoder_query_pos_kernel");
   count_launch();
   return VLFM_OK;
 }

@@ -75,7 +75,16 @@ class GdinoForward:
             return out
 
         self.enc_bbox = mlp(core.encoder_output_bbox_embed)
-        self.last_bbox = mlp(model.bbox_embed[self.cfg.decoder_layers - 1])
+        self.layer_bbox = [mlp(model.bbox_embed[i]) for i in range(self.cfg.decoder_layers)]     # iterative box refinement, one head per layer
+        self.last_bbox = self.layer_bbox[-1]
+        self.ref_head = mlp(core.decoder.reference_points_head)
+        ln = core.decoder.layer_norm
+        self.dec_norm = (ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous(), ln.eps)
+        # get_sine_pos_embed's frequency table, by the reference's own expression (float32)
+        P = self.d // 2
+        dim_t = torch.arange(P, dtype=torch.float32, device=core.level_embed.device)
+        self.dim_t = (10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / P)).contiguous()
+        self.last_reference_points: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------------------ caches ----
     def _shape_constants(self, B: int, H: int, W: int, shapes: Sequence[Tuple[int, int]], device) -> Dict[str, Any]:
@@ -192,14 +201,8 @@ class GdinoForward:
         anchors = ops.gather_rows(sc["anchor_logits"], topk)                                           # [B, nq, 4]
         reference_points = (x[:, :4].reshape(B, self.nq, 4) + anchors).sigmoid()
         target = core.query_position_embeddings.weight.detach().unsqueeze(0).repeat(B, 1, 1)
-        # ---- decoder (HF module, accelerated layers)
-        dec = core.decoder(inputs_embeds=target, vision_encoder_hidden_states=memory, vision_encoder_attention_mask=sc["mask_flatten"],
-                           text_encoder_hidden_states=text_mem, text_encoder_attention_mask=~tx["token_mask"],
-                           reference_points=reference_points, spatial_shapes=sc["spatial_shapes"], spatial_shapes_list=sc["shapes"],
-                           level_start_index=sc["level_start"], valid_ratios=sc["valid_ratios"], self_attn_mask=None, return_dict=True)
-        hs = dec.intermediate_hidden_states[:, -1]                                                     # [B, nq, 256] last layer (post-norm)
-        refs = dec.intermediate_reference_points
-        ref_last = refs[:, -2] if refs.shape[1] >= 2 else reference_points                             # reference fed to the last layer
+        self.last_reference_points = reference_points
+        hs, ref_last = self._decoder(target, memory, text_mem, reference_points, sc, tx, B)
         # ---- heads of the last layer
         x = hs.reshape(B * self.nq, d)
         for i, (w_, b_) in enumerate(self.last_bbox):
@@ -207,6 +210,36 @@ class GdinoForward:
         boxes = ops.box_finish(x[:, :4].reshape(B, self.nq, 4).contiguous(), ref_last.contiguous())    # sigmoid(delta + logit(ref, eps=1e-5))
         logits = ops.contrastive_sigmoid(hs.contiguous(), text_mem.contiguous(), self.cfg.max_text_len)   # [B, nq, max_text_len]
         return logits, boxes
+
+    def _decoder(self, hidden, memory, text_mem, ref, sc, tx, B):
+        """GroundingDinoDecoder.forward restated for inference (no auxiliary outputs): per layer the query position embedding
+        (one kernel + the two-layer reference_points_head on the GEMM), the decoder layer (HF module, accelerated), and -- between
+        layers -- the iterative box refinement ref <- sigmoid(bbox_embed[i](h) + logit(ref)).  Returns the post-norm hidden state of the
+        last layer and the reference points that layer received (what the final box head refines)."""
+        ops, core, d, nq = self.ops, self.core, self.d, self.nq
+        dec = core.decoder
+        tmask = tx.get("dec_text_mask")
+        if tmask is None:       # as the module builds it (additive, all zeros for the never-padded captions of this path)
+            m = (~tx["token_mask"])[:, None, None, :].repeat(1, self.cfg.decoder_attention_heads, nq, 1).to(text_mem.dtype)
+            tmask = tx["dec_text_mask"] = m * torch.finfo(text_mem.dtype).min
+        n_layers = len(dec.layers)
+        for idx, layer in enumerate(dec.layers):
+            ref_in, emb = ops.decoder_query_pos(ref, sc["valid_ratios"], self.dim_t)
+            x = emb
+            for i, (w_, b_) in enumerate(self.ref_head):
+                x = ops.linear(x, w_, b_, relu=i < len(self.ref_head) - 1)
+            query_pos = x.view(B, nq, d)
+            hidden = layer(hidden_states=hidden, position_embeddings=query_pos, reference_points=ref_in, spatial_shapes=sc["spatial_shapes"],
+                           spatial_shapes_list=sc["shapes"], level_start_index=sc["level_start"], vision_encoder_hidden_states=memory,
+                           vision_encoder_attention_mask=sc["mask_flatten"], text_encoder_hidden_states=text_mem,
+                           text_encoder_attention_mask=tmask, self_attn_mask=None, output_attentions=False)[0]
+            if idx + 1 < n_layers:
+                x = hidden.reshape(B * nq, d)
+                for i, (w_, b_) in enumerate(self.layer_bbox[idx]):
+                    x = ops.linear(x, w_, b_, relu=i < len(self.layer_bbox[idx]) - 1)
+                ref = ops.box_finish(x[:, :4].reshape(B, nq, 4).contiguous(), ref.contiguous())
+        hs = ops.layernorm(hidden.reshape(B * nq, d).contiguous(), *self.dec_norm).view(B, nq, d)
+        return hs, ref
 
     @torch.inference_mode()
     def forward(self, images: torch.Tensor, input_ids: Sequence[int]):

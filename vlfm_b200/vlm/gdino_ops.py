@@ -71,6 +71,16 @@ class LibOps:
         _lib.check(self.lib.vlfm_topk_rows(scores.data_ptr(), B, S, k, idx.data_ptr(), _lib.stream_ptr()), "vlfm_topk_rows")
         return idx
 
+    def decoder_query_pos(self, ref: torch.Tensor, valid_ratios: torch.Tensor, dim_t: torch.Tensor):
+        """ref [B, nq, 4], valid_ratios [B, L, 2], dim_t [P] -> (reference_points_input [B, nq, L, 4] fp32, sine embedding operand [B*nq, 4P])"""
+        B, nq, _ = ref.shape
+        L, P = valid_ratios.shape[1], dim_t.shape[0]
+        ref_in = torch.empty((B, nq, L, 4), dtype=F32, device=ref.device)
+        emb = torch.empty((B * nq, 4 * P), dtype=F16, device=ref.device)
+        _lib.check(self.lib.vlfm_decoder_query_pos(ref.contiguous().data_ptr(), valid_ratios.contiguous().data_ptr(), dim_t.data_ptr(), B, nq, L, P,
+                                                   ref_in.data_ptr(), emb.data_ptr(), _lib.stream_ptr()), "vlfm_decoder_query_pos")
+        return ref_in, emb
+
     def gather_rows(self, src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
         B, S, C = src.shape
         K = idx.shape[1]
