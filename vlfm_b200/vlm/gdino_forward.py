@@ -181,13 +181,25 @@ class GdinoForward:
                 a = ops.im2col3x3s2(rows4, B, hh, ww)
             y = ops.linear_operand(a, nk["w"], nk["b"])                                     # [B*h*w, 256] fp32
             ops.groupnorm_rows(y, B, h * w, d, nk["groups"], nk["g"], nk["be"], nk["eps"], src, sc["offsets"][lvl], S)
-        # ---- encoder (HF module, accelerated layers)
-        enc = core.encoder(vision_features=src, vision_attention_mask=~sc["mask_flatten"], vision_position_embedding=sc["pos"],
-                           spatial_shapes=sc["spatial_shapes"], spatial_shapes_list=sc["shapes"], level_start_index=sc["level_start"],
-                           valid_ratios=sc["valid_ratios"], text_features=tx["features"], text_attention_mask=~tx["token_mask"],
-                           text_position_embedding=None, text_self_attention_masks=~tx["self_masks"], text_position_ids=tx["position_ids"],
-                           return_dict=True)
-        memory, text_mem = enc.last_hidden_state_vision, enc.last_hidden_state_text
+        # ---- encoder: GroundingDinoEncoder.forward is a loop over its layers; the per-call constants it rebuilds -- the deformable
+        # reference points (shapes only) and, inside EVERY layer, the sine embedding of the text position ids (caption only) -- come
+        # from the caches instead (~80 elementwise launches per image batch)
+        if "enc_ref" not in sc:
+            sc["enc_ref"] = core.encoder.get_reference_points(sc["shapes"], sc["valid_ratios"], device=dev)
+        if "pos_embed" not in tx:
+            from transformers.models.grounding_dino.modeling_grounding_dino import get_sine_pos_embed
+
+            tx["pos_embed"] = get_sine_pos_embed(tx["position_ids"][..., None], num_pos_feats=d, exchange_xy=False)
+            tx["not_token_mask"], tx["not_self_masks"] = ~tx["token_mask"], ~tx["self_masks"]
+        if "not_mask_flatten" not in sc:
+            sc["not_mask_flatten"] = ~sc["mask_flatten"]
+        memory, text_mem = src, tx["features"]
+        for layer in core.encoder.layers:
+            (memory, text_mem), _ = layer(vision_features=memory, vision_position_embedding=sc["pos"], spatial_shapes=sc["spatial_shapes"],
+                                          spatial_shapes_list=sc["shapes"], level_start_index=sc["level_start"],
+                                          key_padding_mask=sc["not_mask_flatten"], reference_points=sc["enc_ref"], text_features=text_mem,
+                                          text_attention_mask=tx["not_token_mask"], text_position_embedding=tx["pos_embed"],
+                                          text_self_attention_masks=tx["not_self_masks"], text_position_ids=None)
         # ---- two-stage proposals: object queries, scores, top-k, box head on the selected rows
         oq = ops.mask_rows(memory.reshape(B * S, d), sc["anchor_valid"].reshape(B * S))                # invalid anchors -> 0
         oq = ops.linear(oq, self.enc_out_w, self.enc_out_b)
