@@ -310,7 +310,7 @@ def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
       * decision = (kept: score > box_thr, phrase: tokens > text_thr), thresholds at quantiles of the twin's score distribution
         (synthetic scores have no natural gap at 0.35 / 0.25);
       * the fraction of paired decisions that differ between OUR forward and the twin, the mean |score difference| and the mean box
-        L1 distance must not exceed 3x (+ a small floor) what the twin shows against its own perturbed run, and at most 5 % of
+        L1 distance must not exceed 2x (+ a small floor; measured 1.6-1.7x) what the twin shows against its own perturbed run, and at most 5 % of
         the proposals may be unpaired."""
     orc, g = pair_calibrated
     EPS16 = 2.0 ** -11
@@ -359,9 +359,9 @@ def test_detection_decisions_match_the_fp32_twin(pair_calibrated):
     print("decision test (fp16-operand forward vs fp32 twin | twin vs twin with 2^-11 relative input noise):", rep)
     o, t = rep["ours"], rep["twin"]
     assert o["paired"] >= 1700 and o["unpaired"] <= 0.05 * (o["paired"] + o["unpaired"])
-    assert o["flipped"] <= 3.0 * t["flipped"] + 0.01, rep
-    assert o["dscore"] <= 3.0 * t["dscore"] + 2e-3, rep
-    assert o["dbox"] <= 3.0 * t["dbox"] + 2e-3, rep
+    assert o["flipped"] <= 2.0 * t["flipped"] + 0.01, rep
+    assert o["dscore"] <= 2.0 * t["dscore"] + 2e-3, rep
+    assert o["dbox"] <= 2.0 * t["dbox"] + 2e-3, rep
 
 
 def test_head_kernels_vs_torch():
