@@ -17,8 +17,11 @@ which this class restates for inference on fully valid images (pixel_mask all on
     running it on all 6380 proposals, which is what the module graph does);
   * the heads run for the LAST decoder layer only (the other five are training-time auxiliary outputs).
 
-The encoder and decoder stacks themselves are the HF modules whose layers ``gdino_accel`` replaced (tcgen05 GEMMs, fused deformable
-sampling, bi-attention).  Every array operation here goes through ``ops`` (C-ABI kernels, ``gdino_ops.LibOps``); tests substitute a
+The encoder and decoder LAYERS are the HF layer objects whose sublayers ``gdino_accel`` replaced (tcgen05 GEMMs, fused deformable
+sampling, bi-attention); the stacks are sequenced here: the encoder loop feeds every layer the cached deformable reference points
+and the cached sine embedding of the text position ids (the module code rebuilds both per call / per layer), the decoder loop
+computes each layer's query position embedding with one kernel + the reference_points_head GEMMs and refines the reference points
+with the per-layer box head + ``box_finish`` (no auxiliary outputs).  Every array operation here goes through ``ops`` (C-ABI kernels, ``gdino_ops.LibOps``); tests substitute a
 torch implementation of the same interface to check the orchestration against HF on the CPU (tests/test_gdino_forward_cpu.py).
 """
 from __future__ import annotations
