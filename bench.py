@@ -284,10 +284,9 @@ def run_b200(args):
         sps, n, threads = cpu_reference(4, 1, 30.0, fr0, sd, dims)
         cpu = {"value": sps, "unit": "env-steps/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{n} env-steps (fp32 HF BLIP-2 ITC forward + numpy/cv2 value-map oracle), 1 warm-up"}
-    extra = None
-    if not args.no_extra:
-        extra = run_extras(args, dev, world, rank, sd, dims, itm if B >= 32 else None)
-    if rank == 0:
+    def emit(extra):
+        if rank != 0:
+            return
         line = {
             "metric": "value-map steps/sec (ITM+cone-fuse)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -305,7 +304,25 @@ def run_b200(args):
             "per_rank": [{"rank": int(r[0]), "ms": r[1], "conf_checksum": r[2]} for r in per_rank],
             "extra": extra,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+
+    extra = None
+    if not args.no_extra:
+        # The extras (four more workloads) must never cost the headline: a watchdog thread prints the line without them and ends
+        # the process if they have not finished inside their budget (a stuck device call cannot be interrupted from Python).
+        import faulthandler
+
+        def give_up():
+            faulthandler.dump_traceback(file=sys.stderr)
+            emit({"error": f"extras did not finish within {args.extra_budget:.0f} s; skipped (traceback on stderr)"})
+            os._exit(0)
+
+        dog = threading.Timer(args.extra_budget, give_up)
+        dog.daemon = True
+        dog.start()
+        extra = run_extras(args, dev, world, rank, sd, dims, itm if B >= 32 else None)
+        dog.cancel()
+    emit(extra)
     if world > 1:
         dist.destroy_process_group()
 
@@ -491,6 +508,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--extra-budget", type=float, default=420.0, help="seconds the extra workloads may take before the line is printed without them")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1]@32 / [2] / [3] / [4] slices")
     ap.add_argument("--extra-batch", type=int, default=32, help="envs per GPU of the extra slices")
     args = ap.parse_args()
