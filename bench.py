@@ -226,6 +226,43 @@ def run_b200(args):
     ms_local = ms
     ms = max_over_ranks(ms, dev)                       # slowest rank defines the job
     value = aggregate_throughput(world, B, K, ms)
+    # Everything below (end-to-end legs, roofline replay, CPU baseline, extra workloads) decorates the line; none of it may cost the
+    # headline.  A watchdog thread prints the line with what has been measured so far and ends the process if the rest has not
+    # finished inside its budget (a stuck device or subprocess call cannot be interrupted from Python).
+    e2e = e2e_pageable = e2e_blocks = roof = cpu = clocks = extra = None
+    per_rank = [[rank, ms_local, None]]
+    def emit(extra):
+        if rank != 0:
+            return
+        line = {
+            "metric": "value-map steps/sec (ITM+cone-fuse)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD if B == 1 else WORKLOAD.replace("batch=1 env/GPU", f"batch={B} env/GPU"),
+                       "envs_per_gpu": B, "l2": "per-step working set 2.0 GB of weights > 126 MB L2 (no flush needed)",
+                       "timing": "CUDA events, max over ranks"},
+            "e2e": None if e2e is None else {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": H * W * 3 + H * W * 4 + 17 * 8,
+                    "d2h_bytes_per_step": 4, "api": "BLIP2ITM.cosine + ValueMap.update_map (page-locked host numpy frames in, DMA to HBM, float out)",
+                    "blocks_s": e2e_blocks, "blocks_note": "three K-step blocks, median reported",
+                    "pageable_value": e2e_pageable,
+                    "pageable_note": "same loop with ordinary (pageable) numpy frames: staged through the classes' page-locked buffers"},
+            "gpu_launches": launches_per_step * K,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "per_rank": [{"rank": int(r[0]), "ms": r[1], "conf_checksum": r[2]} for r in per_rank],
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+
+    import faulthandler
+
+    def give_up():
+        faulthandler.dump_traceback(file=sys.stderr)
+        emit({"error": f"the legs after the headline did not finish within {args.extra_budget + 240:.0f} s; line printed by the watchdog (traceback on stderr)"})
+        os._exit(0)
+
+    dog = threading.Timer(args.extra_budget + 240.0, give_up)
+    dog.daemon = True
+    dog.start()
 
     # ---- e2e: public class API, host buffers, H2D/D2H inside the timed region
     vm = ValueMap(1, size=G, use_max_confidence=False, device=dev)
@@ -284,44 +321,9 @@ def run_b200(args):
         sps, n, threads = cpu_reference(4, 1, 30.0, fr0, sd, dims)
         cpu = {"value": sps, "unit": "env-steps/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{n} env-steps (fp32 HF BLIP-2 ITC forward + numpy/cv2 value-map oracle), 1 warm-up"}
-    def emit(extra):
-        if rank != 0:
-            return
-        line = {
-            "metric": "value-map steps/sec (ITM+cone-fuse)", "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD if B == 1 else WORKLOAD.replace("batch=1 env/GPU", f"batch={B} env/GPU"),
-                       "envs_per_gpu": B, "l2": "per-step working set 2.0 GB of weights > 126 MB L2 (no flush needed)",
-                       "timing": "CUDA events, max over ranks"},
-            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": H * W * 3 + H * W * 4 + 17 * 8,
-                    "d2h_bytes_per_step": 4, "api": "BLIP2ITM.cosine + ValueMap.update_map (page-locked host numpy frames in, DMA to HBM, float out)",
-                    "blocks_s": e2e_blocks, "blocks_note": "three K-step blocks, median reported",
-                    "pageable_value": e2e_pageable,
-                    "pageable_note": "same loop with ordinary (pageable) numpy frames: staged through the classes' page-locked buffers"},
-            "gpu_launches": launches_per_step * K,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-            "per_rank": [{"rank": int(r[0]), "ms": r[1], "conf_checksum": r[2]} for r in per_rank],
-            "extra": extra,
-        }
-        print(json.dumps(line), flush=True)
-
-    extra = None
     if not args.no_extra:
-        # The extras (four more workloads) must never cost the headline: a watchdog thread prints the line without them and ends
-        # the process if they have not finished inside their budget (a stuck device call cannot be interrupted from Python).
-        import faulthandler
-
-        def give_up():
-            faulthandler.dump_traceback(file=sys.stderr)
-            emit({"error": f"extras did not finish within {args.extra_budget:.0f} s; skipped (traceback on stderr)"})
-            os._exit(0)
-
-        dog = threading.Timer(args.extra_budget, give_up)
-        dog.daemon = True
-        dog.start()
         extra = run_extras(args, dev, world, rank, sd, dims, itm if B >= 32 else None)
-        dog.cancel()
+    dog.cancel()
     emit(extra)
     if world > 1:
         dist.destroy_process_group()
