@@ -322,21 +322,76 @@ def run_b200(args):
         cpu = {"value": sps, "unit": "env-steps/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{n} env-steps (fp32 HF BLIP-2 ITC forward + numpy/cv2 value-map oracle), 1 warm-up"}
     if not args.no_extra:
-        extra = run_extras(args, dev, world, rank, sd, dims, itm if B >= 32 else None)
+        extra = run_extras(args, dev, world, rank, local)
     dog.cancel()
     emit(extra)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_extras(args, dev, world, rank, sd, dims, itm32):
-    """The other BASELINE.json configs, a few steps each, on every rank (env shards, no collective): configs[1] at 32 env/GPU,
+EXTRAS_MARK = "VLFM_EXTRAS_JSON "
+
+
+def extras_names(EB):
+    return ["configs1_b%d" % EB, "configs2_full_step", "configs3_slice", "configs4_slice"]
+
+
+def run_extras(args, dev, world, rank, local):
+    """The extra workloads run in a CHILD process (`bench.py --extras-child`, same GPU) under a hard time limit: whatever happens
+    in there -- an exception, a stuck device call -- costs at most the `extra` block, never the line.  The parent only aggregates:
+    `value` of each entry = whole-job env-steps/s from the max over ranks of the elapsed seconds."""
+    from vlfm_b200.utils.dist import max_over_ranks
+
+    out, pending = {}, []
+    try:
+        env = dict(os.environ)
+        env["LOCAL_RANK"], env["RANK"] = str(local), str(rank)
+        cmd = [sys.executable, os.path.abspath(__file__), "--extras-child", "--extra-batch", str(args.extra_batch)]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.extra_budget)
+        lines = [l for l in r.stdout.splitlines() if l.startswith(EXTRAS_MARK)]
+        if lines:
+            got = json.loads(lines[-1][len(EXTRAS_MARK):])
+            out, pending = got["out"], got["pending"]
+        else:
+            out = {"error": f"extras child ended with code {r.returncode} and no result: {r.stderr[-300:]}"}
+    except subprocess.TimeoutExpired:
+        out = {"error": f"extras child exceeded {args.extra_budget:.0f} s and was killed"}
+    except Exception as e:
+        out = {"error": repr(e)}
+    for nme in extras_names(args.extra_batch):          # the same four collectives on every rank, whatever happened locally
+        ent = out.get(nme) if isinstance(out.get(nme), dict) else None
+        idx = ent.get("value") if ent else None
+        ok = ent is not None and isinstance(idx, int) and "error" not in ent and idx < len(pending)
+        worst = max_over_ranks(pending[idx][2] if ok else 1e30, dev)
+        if ent is not None and "error" not in ent:
+            if worst >= 1e29 or not ok:
+                ent["error"] = "failed on another rank"; ent["value"] = None
+            else:
+                envs, steps, _ = pending[idx]
+                ent["value"] = world * envs * steps / worst
+    return out
+
+
+def extras_child(args):
+    import torch
+
+    from vlfm_b200.vlm.blip2_config import Blip2Dims, random_state_dict
+
+    local, rank = int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dims = Blip2Dims()
+    out, pending = extras_local(args, dev, rank, random_state_dict(dims, 0), dims)
+    print(EXTRAS_MARK + json.dumps({"out": out, "pending": pending}), flush=True)
+
+
+def extras_local(args, dev, rank, sd, dims):
+    """The other BASELINE.json configs, a few steps each, on this rank's GPU (env shards, no collective): configs[1] at 32 env/GPU,
     configs[2] (full step, 32 envs), a configs[3] slice (32 env/GPU, 2000^2 grid) and a configs[4] slice (1024^2 RGB-D,
-    4000^2 x 0.025 m grid, 8 env/GPU).  `value` of each = whole-job env-steps/s (max over ranks of the elapsed time)."""
+    4000^2 x 0.025 m grid, 8 env/GPU).  Returns (entries, [(envs, steps, seconds)]): an entry's `value` is an index into the list."""
     import torch
 
     from vlfm_b200.mapping.value_map import ValueMapBatch
-    from vlfm_b200.utils.dist import max_over_ranks
     from vlfm_b200.utils.full_step import FullStep, grid_bytes
     from vlfm_b200.vlm.blip2itm import BLIP2ITM
     from vlfm_b200.vlm.grounding_dino import GroundingDINO
@@ -345,7 +400,7 @@ def run_extras(args, dev, world, rank, sd, dims, itm32):
     hbm = float(pk["hbm_gbs"])
     out = {"peak_hbm_gbs": hbm, "peak_source": src}
     EB = args.extra_batch
-    itm = itm32 if itm32 is not None else BLIP2ITM(state_dict=sd, dims=dims, max_batch=EB, device=dev)
+    itm = BLIP2ITM(state_dict=sd, dims=dims, max_batch=EB, device=dev)
 
     # every rank records its own elapsed seconds; ONE max-over-ranks at the end turns them into whole-job values (an extra
     # that fails on one rank must not desynchronise the collective)
@@ -420,19 +475,7 @@ def run_extras(args, dev, world, rank, sd, dims, itm32):
     b4 = max(1, EB // 4)
     full("configs4_slice", f"configs[4] slice: full step, {b4} envs/GPU (64 envs on 8 GPUs), 1024x1024 RGB-D, ViT-g at 224 (reference semantics), 4000^2 x 0.025 m grid",
          b4, 1024, 1024, 4000, 40, 4, 4, 30.0)
-    names = ["configs1_b%d" % EB, "configs2_full_step", "configs3_slice", "configs4_slice"]
-    for nme in names:
-        ent = out.get(nme, {})
-        idx = ent.get("value")
-        local = pending[idx][2] if isinstance(idx, int) and "error" not in ent else 1e30
-        worst = max_over_ranks(local, dev)
-        if "error" not in ent:
-            if worst >= 1e29:
-                ent["error"] = "failed on another rank"; ent["value"] = None
-            else:
-                envs, steps, _ = pending[idx]
-                ent["value"] = world * envs * steps / worst
-    return out
+    return out, pending
 
 
 def gemm_roofline(engine, B, dims):
@@ -510,11 +553,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--extra-budget", type=float, default=420.0, help="seconds the extra workloads may take before the line is printed without them")
+    ap.add_argument("--extra-budget", type=float, default=300.0, help="seconds the extra workloads (a child process) may take before they are killed and the line is printed without them")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1]@32 / [2] / [3] / [4] slices")
     ap.add_argument("--extra-batch", type=int, default=32, help="envs per GPU of the extra slices")
+    ap.add_argument("--extras-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.extras_child:
+        extras_child(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -56,14 +56,18 @@ class FullStep:
         self.acc = {k: 0.0 for k in self.names}
         self.n_front = 0
         self.nf = nf
-        self.serial = os.environ.get("VLFM_FULLSTEP_SERIAL", "0") == "1"     # one stream, device sync after every component
+        # Three streams (detector | ITC | map update) are opt-in: VLFM_FULLSTEP_STREAMS=1.  Measured +5 % at 32 envs and +27 % at one
+        # env (profiles/r02_full_step_streams.txt), but two of three full bench.py runs with them stopped making progress at the end of
+        # round 2 (never reproduced in scripts/bench_full_step.py; not root-caused) -- the default is the one-stream sequence.
+        self.serial = os.environ.get("VLFM_FULLSTEP_STREAMS", "0") != "1"
+        self.sync_each = os.environ.get("VLFM_FULLSTEP_SERIAL", "0") == "1"   # diagnostic: device sync after every component
         self._streams = None
 
     def step(self, i: int, timed: bool) -> None:
         """One policy step.  The detector, the ITC model and the obstacle / explore update consume the same uploaded frame and do not
         depend on each other (base_objectnav_policy.py:153-241 calls them one after the other because each call is a blocking HTTP /
-        numpy round trip): they are issued on three streams and joined before the value-map fuse (needs the cosine) and the
-        frontier scoring (needs both maps).  VLFM_FULLSTEP_SERIAL=1 issues them back to back on one stream."""
+        numpy round trip): with VLFM_FULLSTEP_STREAMS=1 they are issued on three streams and joined before the value-map fuse (needs the
+        cosine) and the frontier scoring (needs both maps); by default they are issued back to back on one stream."""
         i %= self.nf
         B = self.B
         main = torch.cuda.current_stream()
@@ -91,7 +95,7 @@ class FullStep:
                 out = fn()
                 b.record()
                 spans[name] = (a, b)
-                if self.serial:
+                if self.sync_each:
                     torch.cuda.synchronize()
             return out
 
