@@ -257,10 +257,15 @@ def run_b200(args):
 
     def give_up():
         faulthandler.dump_traceback(file=sys.stderr)
-        emit({"error": f"the legs after the headline did not finish within {args.extra_budget + 240:.0f} s; line printed by the watchdog (traceback on stderr)"})
+        try:
+            if sampler.proc is not None:
+                sampler.proc.terminate()
+        except Exception:
+            pass
+        emit({"error": f"the legs after the headline did not finish within {args.extra_budget + 150:.0f} s; line printed by the watchdog (traceback on stderr)"})
         os._exit(0)
 
-    dog = threading.Timer(args.extra_budget + 240.0, give_up)
+    dog = threading.Timer(args.extra_budget + 150.0, give_up)
     dog.daemon = True
     dog.start()
 
@@ -553,7 +558,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--extra-budget", type=float, default=300.0, help="seconds the extra workloads (a child process) may take before they are killed and the line is printed without them")
+    ap.add_argument("--extra-budget", type=float, default=240.0, help="seconds the extra workloads (a child process) may take before they are killed and the line is printed without them")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1]@32 / [2] / [3] / [4] slices")
     ap.add_argument("--extra-batch", type=int, default=32, help="envs per GPU of the extra slices")
     ap.add_argument("--extras-child", action="store_true", help=argparse.SUPPRESS)
