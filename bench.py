@@ -352,15 +352,24 @@ def run_extras(args, dev, world, rank, local):
         env = dict(os.environ)
         env["LOCAL_RANK"], env["RANK"] = str(local), str(rank)
         cmd = [sys.executable, os.path.abspath(__file__), "--extras-child", "--extra-batch", str(args.extra_batch)]
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.extra_budget)
-        lines = [l for l in r.stdout.splitlines() if l.startswith(EXTRAS_MARK)]
-        if lines:
-            got = json.loads(lines[-1][len(EXTRAS_MARK):])
-            out, pending = got["out"], got["pending"]
-        else:
-            out = {"error": f"extras child ended with code {r.returncode} and no result: {r.stderr[-300:]}"}
-    except subprocess.TimeoutExpired:
-        out = {"error": f"extras child exceeded {args.extra_budget:.0f} s and was killed"}
+        def last_result(stdout):
+            if isinstance(stdout, bytes):
+                stdout = stdout.decode("utf-8", "replace")
+            lines = [l for l in (stdout or "").splitlines() if l.startswith(EXTRAS_MARK)]
+            return json.loads(lines[-1][len(EXTRAS_MARK):]) if lines else None
+
+        try:
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.extra_budget)
+            got = last_result(r.stdout)
+            if got:
+                out, pending = got["out"], got["pending"]
+            else:
+                out = {"error": f"extras child ended with code {r.returncode} and no result: {r.stderr[-300:]}"}
+        except subprocess.TimeoutExpired as te:      # keep what the child had finished (it prints a cumulative line per workload)
+            got = last_result(te.stdout)
+            if got:
+                out, pending = got["out"], got["pending"]
+            out["error"] = f"extras child exceeded {args.extra_budget:.0f} s and was killed; entries above are the workloads it had finished"
     except Exception as e:
         out = {"error": repr(e)}
     for nme in extras_names(args.extra_batch):          # the same four collectives on every rank, whatever happened locally
@@ -386,11 +395,14 @@ def extras_child(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dims = Blip2Dims()
-    out, pending = extras_local(args, dev, rank, random_state_dict(dims, 0), dims)
-    print(EXTRAS_MARK + json.dumps({"out": out, "pending": pending}), flush=True)
+    def progress(out, pending):          # a cumulative result line after every workload: a later stall costs only what follows
+        print(EXTRAS_MARK + json.dumps({"out": out, "pending": pending}), flush=True)
+
+    out, pending = extras_local(args, dev, rank, random_state_dict(dims, 0), dims, progress)
+    progress(out, pending)
 
 
-def extras_local(args, dev, rank, sd, dims):
+def extras_local(args, dev, rank, sd, dims, progress=lambda out, pending: None):
     """The other BASELINE.json configs, a few steps each, on this rank's GPU (env shards, no collective): configs[1] at 32 env/GPU,
     configs[2] (full step, 32 envs), a configs[3] slice (32 env/GPU, 2000^2 grid) and a configs[4] slice (1024^2 RGB-D,
     4000^2 x 0.025 m grid, 8 env/GPU).  Returns (entries, [(envs, steps, seconds)]): an entry's `value` is an index into the list."""
@@ -449,6 +461,7 @@ def extras_local(args, dev, rank, sd, dims):
     except Exception as e:   # an extra never takes the headline down with it
         out["configs1_b%d" % EB] = {"error": repr(e)}
     torch.cuda.empty_cache()
+    progress(out, pending)
 
     gd = None
     try:
@@ -472,6 +485,7 @@ def extras_local(args, dev, rank, sd, dims):
             out[name] = {"workload": workload, "error": repr(e)}
         if release:        # hand the cached blocks back only when the next workload has different shapes: re-growing the detector's
             torch.cuda.empty_cache()   # temporaries costs cudaMalloc calls inside the next workload's first steps
+        progress(out, pending)
 
     full("configs2_full_step", f"configs[2]: full step (GroundingDINO + BLIP-2 ITC + Obstacle/Value/Frontier update), batch={EB} envs/GPU, 640x480 RGB-D, 1000^2 grid",
          EB, H, W, 1000, 20, 4, 3, 15.0, release=False)
