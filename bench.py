@@ -326,8 +326,10 @@ def run_b200(args):
         sps, n, threads = cpu_reference(4, 1, 30.0, fr0, sd, dims)
         cpu = {"value": sps, "unit": "env-steps/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"{n} env-steps (fp32 HF BLIP-2 ITC forward + numpy/cv2 value-map oracle), 1 warm-up"}
-    if not args.no_extra:
+    if not args.no_extra and (world == 1 or args.extra_multi):
         extra = run_extras(args, dev, world, rank, local)
+    elif not args.no_extra:
+        extra = {"skipped": "the extra workloads run at N=1 by default (--extra-multi runs them on every rank; profiles/r02_bench_n2.json)"}
     dog.cancel()
     emit(extra)
     if world > 1:
@@ -575,6 +577,7 @@ def main():
     ap.add_argument("--extra-budget", type=float, default=240.0, help="seconds the extra workloads (a child process) may take before they are killed and the line is printed without them")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1]@32 / [2] / [3] / [4] slices")
     ap.add_argument("--extra-batch", type=int, default=32, help="envs per GPU of the extra slices")
+    ap.add_argument("--extra-multi", action="store_true", help="run the extra workloads on every rank of a multi-GPU launch too")
     ap.add_argument("--extras-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.extras_child:
